@@ -1,0 +1,235 @@
+"""Triangle mesh container + synthetic structured mesh generators.
+
+Mirrors the slice of scikit-fem's ``MeshTri`` that the waveguide path of femwell
+touches (reference call sites: femwell/maxwell/waveguide.py:574-575, 615;
+docs/benchmarks/mode_solver_rectangle.py:59-66).  Conventions follow SURVEY.md
+Appendix A.1:
+
+* ``p``  float64 (2, Nv) vertex coordinates,
+* ``t``  int32   (3, Ne) vertex indices, **sorted ascending per column**,
+* local edges ``(0,1), (1,2), (0,2)``; global ``facets`` (2, Nf) are the unique
+  sorted vertex pairs in lexicographic order; ``t2f`` (3, Ne) is the inverse map,
+* ``subdomains[name]`` -> element indices, ``boundaries[name]`` -> facet indices.
+
+gmsh / shapely are not available in the target image, so the BASELINE configs
+are generated synthetically here.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, Iterable, Optional, Sequence
+
+import numpy as np
+
+
+@dataclass
+class MeshTri:
+    p: np.ndarray
+    t: np.ndarray
+    subdomains: Dict[str, np.ndarray] = field(default_factory=dict)
+    boundaries: Dict[str, np.ndarray] = field(default_factory=dict)
+
+    def __post_init__(self):
+        self.p = np.ascontiguousarray(self.p, dtype=np.float64)
+        t = np.sort(np.asarray(self.t, dtype=np.int64), axis=0)
+        self.t = np.ascontiguousarray(t.astype(np.int32))
+        self._build_facets()
+
+    # ------------------------------------------------------------------ topology
+    def _build_facets(self):
+        nv = self.nvertices
+        t = self.t.astype(np.int64)
+        # local edges (0,1),(1,2),(0,2); t sorted => (low, high) already
+        lo = np.concatenate([t[0], t[1], t[0]])
+        hi = np.concatenate([t[1], t[2], t[2]])
+        keys = lo * nv + hi
+        uniq, inv = np.unique(keys, return_inverse=True)
+        self.facets = np.ascontiguousarray(
+            np.stack([uniq // nv, uniq % nv]).astype(np.int32)
+        )
+        self.t2f = np.ascontiguousarray(inv.reshape(3, -1).astype(np.int32))
+        counts = np.bincount(inv, minlength=uniq.size)
+        self._facet_count = counts
+
+    @property
+    def nvertices(self) -> int:
+        return self.p.shape[1]
+
+    @property
+    def nelements(self) -> int:
+        return self.t.shape[1]
+
+    @property
+    def nfacets(self) -> int:
+        return self.facets.shape[1]
+
+    def boundary_facets(self) -> np.ndarray:
+        """Facets belonging to exactly one element."""
+        return np.nonzero(self._facet_count == 1)[0].astype(np.int32)
+
+    def facet_midpoints(self) -> np.ndarray:
+        return 0.5 * (self.p[:, self.facets[0]] + self.p[:, self.facets[1]])
+
+    def centroids(self) -> np.ndarray:
+        return (self.p[:, self.t[0]] + self.p[:, self.t[1]] + self.p[:, self.t[2]]) / 3.0
+
+    def facets_satisfying(self, test: Callable, boundaries_only: bool = True) -> np.ndarray:
+        mid = self.facet_midpoints()
+        ok = np.asarray(test(mid), dtype=bool)
+        if boundaries_only:
+            ok &= self._facet_count == 1
+        return np.nonzero(ok)[0].astype(np.int32)
+
+    def elements_satisfying(self, test: Callable) -> np.ndarray:
+        return np.nonzero(np.asarray(test(self.centroids()), dtype=bool))[0].astype(np.int32)
+
+    def with_boundaries(self, tests: Dict[str, Callable]) -> "MeshTri":
+        for name, test in tests.items():
+            self.boundaries[name] = self.facets_satisfying(test)
+        return self
+
+    def with_subdomains(self, tests: Dict[str, Callable]) -> "MeshTri":
+        for name, test in tests.items():
+            self.subdomains[name] = self.elements_satisfying(test)
+        return self
+
+    def normalize_elements(self, elements) -> np.ndarray:
+        """Resolve an element selector (name, list of names, index array, callable)."""
+        if elements is None:
+            return np.arange(self.nelements, dtype=np.int32)
+        if isinstance(elements, str):
+            return np.asarray(self.subdomains[elements], dtype=np.int32)
+        if callable(elements):
+            return self.elements_satisfying(elements)
+        if isinstance(elements, (list, tuple)) and len(elements) and isinstance(elements[0], str):
+            return np.unique(np.concatenate([self.subdomains[n] for n in elements])).astype(np.int32)
+        return np.asarray(elements, dtype=np.int32)
+
+    # --------------------------------------------------------------- generators
+    @classmethod
+    def structured(
+        cls,
+        xs: Sequence[float],
+        ys: Sequence[float],
+        jitter: float = 0.0,
+        seed: int = 1234,
+        frozen_x: Iterable[float] = (),
+        frozen_y: Iterable[float] = (),
+    ) -> "MeshTri":
+        """Tensor grid of ``len(xs)-1`` x ``len(ys)-1`` cells, each split along the
+        same diagonal.  ``jitter`` (fraction of the local cell size) perturbs the
+        interior vertices (avoids accidental exact zeros); vertices
+        on the outer boundary or on the ``frozen`` grid lines (material
+        interfaces) stay put.
+        """
+        xs = np.asarray(xs, dtype=np.float64)
+        ys = np.asarray(ys, dtype=np.float64)
+        nx, ny = xs.size, ys.size
+        X, Y = np.meshgrid(xs, ys, indexing="xy")  # (ny, nx)
+        if jitter > 0:
+            rng = np.random.default_rng(seed)
+            hx = np.minimum(np.diff(xs, prepend=xs[0] - 1e300), np.diff(xs, append=xs[-1] + 1e300))
+            hy = np.minimum(np.diff(ys, prepend=ys[0] - 1e300), np.diff(ys, append=ys[-1] + 1e300))
+            mx = np.ones(nx, dtype=bool)
+            my = np.ones(ny, dtype=bool)
+            mx[[0, -1]] = False
+            my[[0, -1]] = False
+            for f in frozen_x:
+                mx[np.isclose(xs, f)] = False
+            for f in frozen_y:
+                my[np.isclose(ys, f)] = False
+            dx = rng.uniform(-jitter, jitter, size=(ny, nx)) * hx[None, :]
+            dy = rng.uniform(-jitter, jitter, size=(ny, nx)) * hy[None, :]
+            # a vertex on a frozen x-line may still slide along it (dy) and vice versa,
+            # so outer boundaries and material interfaces stay straight
+            X = X + dx * mx[None, :]
+            Y = Y + dy * my[:, None]
+        p = np.stack([X.ravel(), Y.ravel()])
+        idx = np.arange(nx * ny, dtype=np.int64).reshape(ny, nx)
+        v00 = idx[:-1, :-1].ravel()
+        v10 = idx[:-1, 1:].ravel()
+        v01 = idx[1:, :-1].ravel()
+        v11 = idx[1:, 1:].ravel()
+        t = np.concatenate(
+            [np.stack([v00, v10, v11]), np.stack([v00, v11, v01])], axis=1
+        )
+        # interleave the two triangles of each cell so that element order is spatial
+        ne = t.shape[1] // 2
+        order = np.empty(2 * ne, dtype=np.int64)
+        order[0::2] = np.arange(ne)
+        order[1::2] = np.arange(ne) + ne
+        t = t[:, order]
+        m = cls(p, t)
+        x0, x1, y0, y1 = xs[0], xs[-1], ys[0], ys[-1]
+        tol = 1e-9 * max(x1 - x0, y1 - y0)
+        m.with_boundaries(
+            {
+                "left": lambda q: np.abs(q[0] - x0) < tol,
+                "right": lambda q: np.abs(q[0] - x1) < tol,
+                "bottom": lambda q: np.abs(q[1] - y0) < tol,
+                "top": lambda q: np.abs(q[1] - y1) < tol,
+            }
+        )
+        return m
+
+    @classmethod
+    def rectangle(cls, n: int, bbox=(0.0, 1.0, 0.0, 1.0), **kw) -> "MeshTri":
+        x0, x1, y0, y1 = bbox
+        return cls.structured(np.linspace(x0, x1, n + 1), np.linspace(y0, y1, n + 1), **kw)
+
+
+def graded_axis(breaks: Sequence[float], cells: Sequence[int]) -> np.ndarray:
+    """Piecewise-uniform 1-D grid whose lines hit every break point exactly."""
+    out = [np.array([breaks[0]], dtype=np.float64)]
+    for a, b, n in zip(breaks[:-1], breaks[1:], cells):
+        out.append(np.linspace(a, b, int(n) + 1)[1:])
+    return np.concatenate(out)
+
+
+def _split_cells(breaks, total):
+    """Distribute ``total`` cells over the intervals proportionally to length (>=1 each)."""
+    lens = np.diff(np.asarray(breaks, dtype=np.float64))
+    raw = lens / lens.sum() * total
+    cells = np.maximum(1, np.floor(raw).astype(int))
+    while cells.sum() < total:
+        cells[np.argmax(raw - cells)] += 1
+    while cells.sum() > total:
+        i = np.argmax(np.where(cells > 1, cells - raw, -np.inf))
+        cells[i] -= 1
+    return cells
+
+
+def waveguide_mesh(
+    n: int,
+    core_w: float = 0.5,
+    core_h: float = 0.22,
+    slab_h: float = 0.0,
+    bbox=(-1.5, 1.5, -1.0, 1.22),
+    jitter: float = 0.15,
+    seed: int = 1234,
+    extra_x: Sequence[float] = (),
+) -> MeshTri:
+    """Strip (``slab_h=0``) or rib waveguide cross-section on an ``n x n`` grid
+    (``2 n^2`` triangles) whose grid lines coincide with the material interfaces
+    (geometry after
+    docs/photonics/examples/bent_waveguide.py:43-49).
+    Sub-domains: ``core``, ``slab`` (if any), ``box`` (y<0), ``clad``.
+    """
+    x0, x1, y0, y1 = bbox
+    xb = sorted({x0, -core_w / 2, core_w / 2, x1, *extra_x})
+    yb = sorted({y0, 0.0, core_h, y1} | ({slab_h} if slab_h > 0 else set()))
+    xs = graded_axis(xb, _split_cells(xb, n))
+    ys = graded_axis(yb, _split_cells(yb, n))
+    m = MeshTri.structured(xs, ys, jitter=jitter, seed=seed, frozen_x=xb, frozen_y=yb)
+    c = m.centroids()
+    core = (np.abs(c[0]) < core_w / 2) & (c[1] > 0) & (c[1] < core_h)
+    slab = (c[1] > 0) & (c[1] < slab_h) & ~core if slab_h > 0 else np.zeros_like(core)
+    box = c[1] < 0
+    clad = ~(core | slab | box)
+    m.subdomains = {
+        "core": np.nonzero(core)[0].astype(np.int32),
+        "slab": np.nonzero(slab)[0].astype(np.int32),
+        "box": np.nonzero(box)[0].astype(np.int32),
+        "clad": np.nonzero(clad)[0].astype(np.int32),
+    }
+    return m
