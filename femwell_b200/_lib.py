@@ -1,0 +1,126 @@
+"""ctypes binding of libfemwell_b200.so (C ABI in include/femwell_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is
+present when a handle is created, the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfemwell_b200.so")
+
+c_i32, c_i64, c_f64, c_vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
+P = C.POINTER
+
+
+class FwSpace(C.Structure):
+    _fields_ = [
+        ("order", c_i32), ("n_vertices", c_i32), ("n_elements", c_i32), ("n_dofs", c_i32),
+        ("nbfun", c_i32), ("nqp", c_i32),
+        ("p", c_vp), ("t", c_vp), ("element_dofs", c_vp), ("kind", c_vp), ("vec", c_vp),
+        ("sc", c_vp), ("X", c_vp), ("W", c_vp),
+    ]
+
+
+class FwEigsParams(C.Structure):
+    _fields_ = [
+        ("k", c_i32), ("ncv", c_i32), ("maxiter", c_i32), ("tol", c_f64),
+        ("sigma_re", c_f64), ("sigma_im", c_f64),
+        ("n_dirichlet", c_i32), ("dirichlet", c_vp), ("v0", c_vp),
+        ("refine", c_i32), ("leaf_elements", c_i32),
+    ]
+
+
+class FwEigsStats(C.Structure):
+    _fields_ = [
+        ("nconv", c_i32), ("iterations", c_i32), ("restarts", c_i32), ("n_op", c_i32),
+        ("pivots_perturbed", c_i32), ("lu_levels", c_i32), ("lu_fronts", c_i32),
+        ("lu_factor_entries", c_i64),
+        ("t_symbolic_ms", c_f64), ("t_factor_ms", c_f64), ("t_arnoldi_ms", c_f64),
+        ("t_solve_ms_total", c_f64), ("max_residual", c_f64),
+    ]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class FwModesParams(C.Structure):
+    _fields_ = [
+        ("wavelength", c_f64), ("mu_r", c_f64), ("radius", c_f64),
+        ("eps_kind", c_i32), ("eps_is_complex", c_i32), ("eps", c_vp),
+        ("eigs", FwEigsParams), ("reuse_symbolic", c_i32),
+    ]
+
+
+class FwTimings(C.Structure):
+    _fields_ = [
+        ("upload_ms", c_f64), ("symbolic_ms", c_f64), ("element_kernel_ms", c_f64), ("reduce_ms", c_f64),
+        ("lu_symbolic_ms", c_f64), ("lu_factor_ms", c_f64), ("arnoldi_ms", c_f64), ("postprocess_ms", c_f64),
+        ("total_ms", c_f64), ("element_kernel_launches", c_i64), ("kernel_launches", c_i64),
+    ]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class FemwellB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libfemwell_b200 error {code}: {msg}")
+        self.code = code
+
+
+# every symbol include/femwell_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "fw_last_error", "fw_version", "fw_create", "fw_destroy", "fw_synchronize", "fw_set_space",
+    "fw_symbolic", "fw_assemble_waveguide", "fw_matrix_nnz", "fw_matrix_export", "fw_coo_to_csr",
+    "fw_coo_to_csr_export", "fw_matrix_spmv", "fw_eigs", "fw_lu_factor_shifted", "fw_lu_solve",
+    "fw_postprocess_modes", "fw_hfield", "fw_functional", "fw_compute_modes", "fw_get_timings",
+    "fw_host_dense_eig", "fw_debug_lu_symbolic", "fw_debug_lu_symbolic_get",
+]
+
+_lib = None
+
+
+def load():
+    """Load the shared library; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -m femwell_b200.build` "
+                "(the b200 path has no CPU fallback)"
+            )
+        lib = C.CDLL(LIB_PATH)
+        lib.fw_last_error.restype = C.c_char_p
+        lib.fw_version.restype = C.c_int
+        for name in EXPORTS:
+            fn = getattr(lib, name)
+            if name not in ("fw_last_error",):
+                fn.restype = C.c_int
+        _lib = lib
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        raise FemwellB200Error(code, load().fw_last_error().decode())
+
+
+def ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def as_c128(a):
+    return np.ascontiguousarray(a, dtype=np.complex128)
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def as_i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)

@@ -1,0 +1,206 @@
+"""Host-side owner of one library handle (= one GPU, one stream, one resident FE space).
+
+Thin: marshals numpy arrays across the C ABI (include/femwell_b200.h); no arithmetic here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib as L
+from .basis import Basis
+from .element import eps_kind_of
+
+MAT_A, MAT_B, MAT_MASS, MAT_C0, MAT_C1 = 0, 1, 2, 3, 4
+FUN_OVERLAP, FUN_EX2_EY2, FUN_EX2_EY2_EALL, FUN_COUPLING, FUN_E2_E4, FUN_CONFINEMENT = range(6)
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.lib = L.load()
+        self._h = C.c_void_p()
+        L.check(self.lib.fw_create(C.byref(self._h), C.c_int(device)))
+        self.device = device
+        self.basis: Optional[Basis] = None
+        self._space_key = None
+        self.n = 0
+        self.nnz_structural = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.fw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- space / symbolic
+    def set_space(self, basis: Basis):
+        """Upload mesh + FE space (a1).  ``basis`` must carry the mixed N x P element."""
+        tb = basis.tables()
+        m = basis.mesh
+        ed = basis.element_dofs
+        s = L.FwSpace()
+        s.order = basis.elem.order
+        s.n_vertices, s.n_elements, s.n_dofs = m.nvertices, m.nelements, basis.N
+        s.nbfun, s.nqp = tb.nbfun, tb.nqp
+        keep = [L.as_f64(m.p), L.as_i32(m.t), L.as_i32(ed), L.as_i32(tb.kind), L.as_f64(tb.vec), L.as_f64(tb.sc),
+                L.as_f64(tb.X), L.as_f64(tb.W)]
+        (s.p, s.t, s.element_dofs, s.kind, s.vec, s.sc, s.X, s.W) = [a.ctypes.data for a in keep]
+        L.check(self.lib.fw_set_space(self._h, C.byref(s)))
+        self.basis = basis
+        self.n = basis.N
+        self.nnz_structural = None
+        self._space_key = (id(m), basis.elem.order, tb.X.tobytes(), tb.W.tobytes())
+
+    def same_space(self, basis: Basis) -> bool:
+        tb_x, tb_w = basis.X, basis.W
+        return self._space_key == (id(basis.mesh), basis.elem.order, tb_x.tobytes(), tb_w.tobytes())
+
+    def symbolic(self) -> int:
+        nnz = C.c_int64()
+        L.check(self.lib.fw_symbolic(self._h, C.byref(nnz)))
+        self.nnz_structural = nnz.value
+        return nnz.value
+
+    # ---------------------------------------------------------------- assembly
+    def assemble(self, eps_kind: int, epsilon_r: np.ndarray, k0: float, mu_r: float = 1.0, radius: float = np.inf):
+        cx = np.iscomplexobj(epsilon_r)
+        eps = L.as_c128(epsilon_r) if cx else L.as_f64(epsilon_r)
+        ne = self.basis.mesh.nelements
+        expect = ne if eps_kind == 0 else 3 * ne
+        if eps.size != expect:
+            raise ValueError(f"epsilon_r has {eps.size} dofs, expected {expect}")
+        L.check(self.lib.fw_assemble_waveguide(self._h, eps_kind, int(cx), L.ptr(eps), C.c_double(k0),
+                                               C.c_double(mu_r), C.c_double(radius)))
+
+    def matrix(self, which: int) -> sp.csr_matrix:
+        nnz, cx = C.c_int64(), C.c_int32()
+        L.check(self.lib.fw_matrix_nnz(self._h, which, C.byref(nnz), C.byref(cx)))
+        indptr = np.empty(self.n + 1, dtype=np.int32)
+        indices = np.empty(nnz.value, dtype=np.int32)
+        data = np.empty(nnz.value, dtype=np.complex128 if cx.value else np.float64)
+        L.check(self.lib.fw_matrix_export(self._h, which, L.ptr(indptr), L.ptr(indices), L.ptr(data)))
+        return sp.csr_matrix((data, indices, indptr), shape=(self.n, self.n))
+
+    def spmv(self, which: int, x: np.ndarray) -> np.ndarray:
+        cx = np.iscomplexobj(x)
+        xx = L.as_c128(x) if cx else L.as_f64(x)
+        nnz, mcx = C.c_int64(), C.c_int32()
+        L.check(self.lib.fw_matrix_nnz(self._h, which, C.byref(nnz), C.byref(mcx)))
+        y = np.empty(self.n, dtype=np.complex128 if (cx or mcx.value) else np.float64)
+        L.check(self.lib.fw_matrix_spmv(self._h, which, int(cx), L.ptr(xx), L.ptr(y)))
+        return y
+
+    def coo_to_csr(self, n_rows: int, rows, cols, data) -> sp.csr_matrix:
+        cx = np.iscomplexobj(data)
+        d = L.as_c128(data) if cx else L.as_f64(data)
+        r, c = L.as_i32(rows), L.as_i32(cols)
+        nnz = C.c_int64()
+        L.check(self.lib.fw_coo_to_csr(self._h, n_rows, C.c_int64(d.size), L.ptr(r), L.ptr(c), L.ptr(d), int(cx),
+                                       C.byref(nnz)))
+        indptr = np.empty(n_rows + 1, dtype=np.int32)
+        indices = np.empty(nnz.value, dtype=np.int32)
+        out = np.empty(nnz.value, dtype=d.dtype)
+        L.check(self.lib.fw_coo_to_csr_export(self._h, L.ptr(indptr), L.ptr(indices), L.ptr(out)))
+        return sp.csr_matrix((out, indices, indptr), shape=(n_rows, n_rows))
+
+    # ---------------------------------------------------------------- LU / eigs
+    def lu_factor(self, sigma, dirichlet=None, leaf_elements=0):
+        d = None if dirichlet is None else L.as_i32(dirichlet)
+        L.check(self.lib.fw_lu_factor_shifted(self._h, C.c_double(np.real(sigma)), C.c_double(np.imag(sigma)),
+                                              0 if d is None else d.size, L.ptr(d), leaf_elements))
+
+    def lu_solve(self, b: np.ndarray, refine: int = 1) -> np.ndarray:
+        cx = np.iscomplexobj(b)
+        bb = L.as_c128(b) if cx else L.as_f64(b)
+        x = np.empty_like(bb)
+        L.check(self.lib.fw_lu_solve(self._h, int(cx), L.ptr(bb), L.ptr(x), refine))
+        return x
+
+    def _eigs_params(self, k, sigma, dirichlet, v0, ncv, tol, maxiter, refine, leaf_elements, keep):
+        p = L.FwEigsParams()
+        p.k, p.ncv, p.maxiter, p.tol = int(k), int(ncv), int(maxiter), float(tol)
+        p.sigma_re, p.sigma_im = float(np.real(sigma)), float(np.imag(sigma))
+        if dirichlet is not None and len(dirichlet):
+            d = L.as_i32(dirichlet)
+            keep.append(d)
+            p.n_dirichlet, p.dirichlet = d.size, d.ctypes.data
+        if v0 is not None:
+            v = L.as_f64(np.real(v0))
+            keep.append(v)
+            p.v0 = v.ctypes.data
+        p.refine, p.leaf_elements = int(refine), int(leaf_elements)
+        return p
+
+    def eigs(self, k, sigma, dirichlet=None, v0=None, ncv=0, tol=0.0, maxiter=0, refine=1, leaf_elements=0):
+        keep = []
+        p = self._eigs_params(k, sigma, dirichlet, v0, ncv, tol, maxiter, refine, leaf_elements, keep)
+        lams = np.empty(k, dtype=np.complex128)
+        X = np.empty((k, self.n), dtype=np.complex128)
+        st = L.FwEigsStats()
+        L.check(self.lib.fw_eigs(self._h, C.byref(p), L.ptr(lams), L.ptr(X), C.byref(st)))
+        return lams, X, st.as_dict()
+
+    # ---------------------------------------------------------------- post-processing
+    def postprocess(self, lams, X, k0, omega, mu0):
+        k = len(lams)
+        lams = L.as_c128(lams)
+        X = L.as_c128(X)
+        E = np.empty((k, self.n), dtype=np.complex128)
+        H = np.empty((k, self.n), dtype=np.complex128)
+        powers = np.empty(k, dtype=np.complex128)
+        L.check(self.lib.fw_postprocess_modes(self._h, k, L.ptr(lams), L.ptr(X), C.c_double(k0), C.c_double(omega),
+                                              C.c_double(mu0), L.ptr(E), L.ptr(H), L.ptr(powers)))
+        return E, H, powers
+
+    def hfield(self, E, beta, omega, mu0):
+        E = L.as_c128(E)
+        H = np.empty(self.n, dtype=np.complex128)
+        L.check(self.lib.fw_hfield(self._h, L.ptr(E), C.c_double(np.real(beta)), C.c_double(np.imag(beta)),
+                                   C.c_double(omega), C.c_double(mu0), L.ptr(H)))
+        return H
+
+    def functional(self, kind, fields, aux=None, aux_kind=0, elements=None, option=0):
+        fs = [None if f is None else L.as_c128(f) for f in fields] + [None] * (4 - len(fields))
+        a = None
+        acx = 0
+        if aux is not None:
+            acx = int(np.iscomplexobj(aux))
+            a = L.as_c128(aux) if acx else L.as_f64(aux)
+        el = None if elements is None else L.as_i32(elements)
+        out = np.zeros(3, dtype=np.complex128)
+        L.check(self.lib.fw_functional(self._h, kind, L.ptr(fs[0]), L.ptr(fs[1]), L.ptr(fs[2]), L.ptr(fs[3]),
+                                       aux_kind, acx, L.ptr(a), 0 if el is None else el.size, L.ptr(el), option,
+                                       L.ptr(out)))
+        return out
+
+    def compute_modes(self, eps_kind, epsilon_r, wavelength, k, sigma, mu_r=1.0, radius=np.inf, dirichlet=None,
+                      v0=None, ncv=0, tol=0.0, maxiter=0, refine=1, leaf_elements=0, reuse_symbolic=False):
+        keep = []
+        cx = np.iscomplexobj(epsilon_r)
+        eps = L.as_c128(epsilon_r) if cx else L.as_f64(epsilon_r)
+        p = L.FwModesParams()
+        p.wavelength, p.mu_r, p.radius = float(wavelength), float(mu_r), float(radius)
+        p.eps_kind, p.eps_is_complex, p.eps = int(eps_kind), int(cx), eps.ctypes.data
+        p.eigs = self._eigs_params(k, sigma, dirichlet, v0, ncv, tol, maxiter, refine, leaf_elements, keep)
+        p.reuse_symbolic = int(reuse_symbolic)
+        lams = np.empty(k, dtype=np.complex128)
+        E = np.empty((k, self.n), dtype=np.complex128)
+        H = np.empty((k, self.n), dtype=np.complex128)
+        powers = np.empty(k, dtype=np.complex128)
+        st = L.FwEigsStats()
+        L.check(self.lib.fw_compute_modes(self._h, C.byref(p), L.ptr(lams), L.ptr(E), L.ptr(H), L.ptr(powers),
+                                          C.byref(st)))
+        return lams, E, H, powers, st.as_dict()
+
+    def timings(self) -> dict:
+        t = L.FwTimings()
+        L.check(self.lib.fw_get_timings(self._h, C.byref(t)))
+        return t.as_dict()

@@ -1,0 +1,523 @@
+// extern "C" boundary of libfemwell_b200 (declarations + reference citations: include/femwell_b200.h).
+#include "handle.h"
+#include "lu.h"
+#include "solver.h"
+
+using namespace fw;
+
+static thread_local std::string g_err;
+
+#define FW_API_BEGIN try {
+#define FW_API_END                         \
+  }                                        \
+  catch (const fw::Error& e) {             \
+    g_err = e.what();                      \
+    return e.code;                         \
+  }                                        \
+  catch (const std::exception& e) {        \
+    g_err = e.what();                      \
+    return FW_ERR_INTERNAL;                \
+  }                                        \
+  return FW_OK;
+
+struct fw_handle {
+  Handle h;
+};
+
+namespace fw {
+Handle::Handle() {}
+Handle::~Handle() {
+  lu.reset();
+  if (stream) cudaStreamDestroy(stream);
+}
+}  // namespace fw
+
+static Values& pick(Handle& h, int which) {
+  switch (which) {
+    case FW_MAT_A:
+      return h.A;
+    case FW_MAT_B:
+      return h.B;
+    case FW_MAT_MASS:
+      return h.Mass;
+    case FW_MAT_C0:
+      return h.C0;
+    case FW_MAT_C1:
+      return h.C1;
+  }
+  throw Error(FW_ERR_INVALID, "unknown matrix id");
+}
+
+extern "C" {
+
+const char* fw_last_error(void) { return g_err.c_str(); }
+int fw_version(void) { return 100; }
+
+int fw_create(fw_handle** out, int device) {
+  FW_API_BEGIN
+  FW_REQUIRE(out != nullptr, "out is NULL");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw Error(FW_ERR_CUDA, std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                                 " -- libfemwell_b200 has no CPU fallback");
+  FW_REQUIRE(device >= 0 && device < count, "bad device index");
+  FW_CHECK_CUDA(cudaSetDevice(device));
+  std::unique_ptr<fw_handle> hh(new fw_handle());
+  hh->h.device = device;
+  FW_CHECK_CUDA(cudaStreamCreateWithFlags(&hh->h.stream, cudaStreamNonBlocking));
+  *out = hh.release();
+  FW_API_END
+}
+
+int fw_destroy(fw_handle* h) {
+  FW_API_BEGIN
+  if (h) {
+    cudaSetDevice(h->h.device);
+    delete h;
+  }
+  FW_API_END
+}
+
+int fw_synchronize(fw_handle* h) {
+  FW_API_BEGIN
+  FW_REQUIRE(h, "handle is NULL");
+  FW_CHECK_CUDA(cudaSetDevice(h->h.device));
+  FW_CHECK_CUDA(cudaStreamSynchronize(h->h.stream));
+  FW_API_END
+}
+
+int fw_set_space(fw_handle* hh, const fw_space* s) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && s, "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  FW_REQUIRE(s->order == 1 || s->order == 2, "Only order 1 and 2 implemented by now.");
+  const int nb = s->order == 1 ? 6 : 14;
+  FW_REQUIRE(s->nbfun == nb, "nbfun does not match order");
+  FW_REQUIRE(s->nqp >= 1 && s->nqp <= MAXQ, "nqp out of range (1..12)");
+  FW_REQUIRE(s->n_vertices > 0 && s->n_elements > 0 && s->n_dofs > 0, "empty mesh");
+  FW_REQUIRE(s->p && s->t && s->element_dofs && s->kind && s->vec && s->sc && s->X && s->W, "NULL array");
+  Space& sp = h.sp;
+  Timer tu(h.stream);
+  sp.order = s->order;
+  sp.nv = s->n_vertices;
+  sp.ne = s->n_elements;
+  sp.n = s->n_dofs;
+  sp.nb = nb;
+  sp.nq = s->nqp;
+  sp.nt = 0;
+  for (int l = 0; l < nb; ++l) {
+    sp.kind[l] = s->kind[l];
+    const int expect = nb == 6 ? (l < 3 ? 1 : 0) : (l < 3 ? 1 : (l >= 12 ? 0 : (((l - 3) % 3) == 2 ? 1 : 0)));
+    FW_REQUIRE(sp.kind[l] == expect, "local dof layout must be entity-major (vertex, facet, interior)");
+    sp.nt += sp.kind[l] == 0;
+  }
+  sp.nz = nb - sp.nt;
+  sp.vec.assign(s->vec, s->vec + (size_t)nb * 2 * sp.nq);
+  sp.sc.assign(s->sc, s->sc + (size_t)nb * sp.nq);
+  sp.X.assign(s->X, s->X + (size_t)2 * sp.nq);
+  sp.W.assign(s->W, s->W + (size_t)sp.nq);
+  sp.h_p.assign(s->p, s->p + (size_t)2 * sp.nv);
+  sp.h_t.assign(s->t, s->t + (size_t)3 * sp.ne);
+  sp.h_edofs.assign(s->element_dofs, s->element_dofs + (size_t)nb * sp.ne);
+  // validate indices on the host (cheap, avoids device faults on bad input)
+  for (size_t i = 0; i < sp.h_t.size(); ++i) FW_REQUIRE(sp.h_t[i] >= 0 && sp.h_t[i] < sp.nv, "t out of range");
+  std::vector<uint8_t> isz((size_t)sp.n, 0);
+  for (int l = 0; l < nb; ++l)
+    for (int e = 0; e < sp.ne; ++e) {
+      int d = sp.h_edofs[(size_t)l * sp.ne + e];
+      FW_REQUIRE(d >= 0 && d < sp.n, "element_dofs out of range");
+      if (sp.kind[l] == 1) isz[d] = 1;
+    }
+  sp.p.upload(sp.h_p.data(), sp.h_p.size(), h.stream);
+  sp.t.upload(sp.h_t.data(), sp.h_t.size(), h.stream);
+  sp.edofs.upload(sp.h_edofs.data(), sp.h_edofs.size(), h.stream);
+  sp.is_z.upload(isz.data(), isz.size(), h.stream);
+  FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
+  sp.valid = true;
+  h.has_symbolic = false;
+  h.A.valid = h.B.valid = h.Mass.valid = h.C0.valid = h.C1.valid = false;
+  h.lu.reset();
+  h.tim = fw_timings{};
+  h.tim.upload_ms = tu.stop();
+  FW_API_END
+}
+
+int fw_symbolic(fw_handle* hh, int64_t* nnz) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh, "handle is NULL");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  Timer t(h.stream);
+  symbolic_space(h);
+  h.tim.symbolic_ms = t.stop();
+  if (nnz) *nnz = h.pat.nnz;
+  FW_API_END
+}
+
+int fw_assemble_waveguide(fw_handle* hh, int32_t eps_kind, int32_t eps_is_complex, const void* eps, double k0,
+                          double mu_r, double radius) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh, "handle is NULL");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  assemble_waveguide(h, eps_kind, eps_is_complex != 0, eps, k0, mu_r, radius);
+  FW_API_END
+}
+
+int fw_matrix_nnz(fw_handle* hh, int32_t which, int64_t* nnz, int32_t* is_complex) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && nnz, "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  if (which >= FW_MAT_MASS) assemble_aux(h);
+  Values& v = pick(h, which);
+  FW_REQUIRE(v.valid, "matrix has not been assembled");
+  *nnz = count_kept(h, h.pat, v);
+  if (is_complex) *is_complex = v.is_complex;
+  FW_API_END
+}
+
+int fw_matrix_export(fw_handle* hh, int32_t which, int32_t* indptr, int32_t* indices, void* data) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && indptr && indices && data, "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  if (which >= FW_MAT_MASS) assemble_aux(h);
+  Values& v = pick(h, which);
+  FW_REQUIRE(v.valid, "matrix has not been assembled");
+  export_compacted(h, h.pat, v, indptr, indices, data);
+  FW_API_END
+}
+
+int fw_coo_to_csr(fw_handle* hh, int32_t n_rows, int64_t n_entries, const int32_t* rows, const int32_t* cols,
+                  const void* data, int32_t is_complex, int64_t* nnz) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && nnz, "NULL argument");
+  FW_REQUIRE(n_rows > 0 && n_entries >= 0, "bad sizes");
+  FW_REQUIRE(n_entries == 0 || (rows && cols && data), "NULL array");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  for (int64_t i = 0; i < n_entries; ++i)
+    FW_REQUIRE(rows[i] >= 0 && rows[i] < n_rows && cols[i] >= 0 && cols[i] < n_rows, "COO index out of range");
+  coo_to_csr(h, n_rows, n_entries, rows, cols, data, is_complex != 0);
+  *nnz = h.coo_pat.nnz;
+  FW_API_END
+}
+
+int fw_coo_to_csr_export(fw_handle* hh, int32_t* indptr, int32_t* indices, void* data) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && indptr && indices && data, "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  FW_REQUIRE(h.coo_val.valid, "fw_coo_to_csr has not been called");
+  export_compacted(h, h.coo_pat, h.coo_val, indptr, indices, data);
+  FW_API_END
+}
+
+int fw_matrix_spmv(fw_handle* hh, int32_t which, int32_t x_is_complex, const void* x, void* y) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && x && y, "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  if (which >= FW_MAT_MASS) assemble_aux(h);
+  Values& v = pick(h, which);
+  FW_REQUIRE(v.valid, "matrix has not been assembled");
+  const int n = h.sp.n;
+  cudaStream_t s = h.stream;
+  const bool out_complex = v.is_complex || x_is_complex;
+  DevBuf<double> dx, dy;
+  if (out_complex && !x_is_complex) {
+    // promote x to complex on the host side of the copy
+    std::vector<double> xc((size_t)2 * n, 0.0);
+    for (int i = 0; i < n; ++i) xc[2 * (size_t)i] = ((const double*)x)[i];
+    dx.upload(xc.data(), xc.size(), s);
+    FW_CHECK_CUDA(cudaStreamSynchronize(s));
+  } else {
+    dx.upload((const double*)x, (size_t)n * (x_is_complex ? 2 : 1), s);
+  }
+  dy.alloc((size_t)n * (out_complex ? 2 : 1));
+  if (!out_complex)
+    spmv<double, double>(n, h.pat.indptr.p, h.pat.indices.p, v.v.p, dx.p, dy.p, s);
+  else if (!v.is_complex)
+    spmv<double, cplx>(n, h.pat.indptr.p, h.pat.indices.p, v.v.p, (const cplx*)dx.p, (cplx*)dy.p, s);
+  else
+    spmv<cplx, cplx>(n, h.pat.indptr.p, h.pat.indices.p, (const cplx*)v.v.p, (const cplx*)dx.p, (cplx*)dy.p, s);
+  dy.download((double*)y, (size_t)n * (out_complex ? 2 : 1), s);
+  FW_CHECK_CUDA(cudaStreamSynchronize(s));
+  FW_API_END
+}
+
+int fw_eigs(fw_handle* hh, const fw_eigs_params* prm, double* lams, double* X, fw_eigs_stats* st) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && prm && lams && X, "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  DevBuf<double> Xd;
+  eigs_shift_invert(h, *prm, (std::complex<double>*)lams, Xd, st);
+  Xd.download(X, (size_t)prm->k * h.sp.n * 2, h.stream);
+  FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
+  FW_API_END
+}
+
+int fw_lu_factor_shifted(fw_handle* hh, double sigma_re, double sigma_im, int32_t n_dirichlet,
+                         const int32_t* dirichlet, int32_t leaf_elements) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh, "handle is NULL");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  FW_REQUIRE(h.A.valid && h.B.valid, "assemble A and B first");
+  std::vector<uint8_t> active((size_t)h.sp.n, 1);
+  for (int i = 0; i < n_dirichlet; ++i) {
+    FW_REQUIRE(dirichlet[i] >= 0 && dirichlet[i] < h.sp.n, "dirichlet dof out of range");
+    active[dirichlet[i]] = 0;
+  }
+  {
+    Timer t(h.stream);
+    lu_analyse(h, active, leaf_elements);
+    h.tim.lu_symbolic_ms = t.stop();
+  }
+  {
+    Timer t(h.stream);
+    lu_factor(h, -1.0, 0.0, sigma_re, sigma_im, h.A.is_complex || sigma_im != 0.0);
+    h.tim.lu_factor_ms = t.stop();
+  }
+  h.lu_sigma_re = sigma_re;
+  h.lu_sigma_im = sigma_im;
+  FW_API_END
+}
+
+int fw_lu_solve(fw_handle* hh, int32_t rhs_is_complex, const void* b, void* x, int32_t refine) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && b && x, "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  FW_REQUIRE(h.lu && h.lu->factored, "fw_lu_factor_shifted must be called first");
+  (void)refine;
+  const int n = h.sp.n;
+  cudaStream_t s = h.stream;
+  const bool lu_c = h.lu->is_complex;
+  DevBuf<double> db, dx;
+  if (lu_c) {
+    std::vector<double> tmp((size_t)2 * n);
+    if (rhs_is_complex)
+      memcpy(tmp.data(), b, sizeof(double) * 2 * n);
+    else
+      for (int i = 0; i < n; ++i) tmp[2 * (size_t)i] = ((const double*)b)[i], tmp[2 * (size_t)i + 1] = 0.0;
+    db.upload(tmp.data(), tmp.size(), s);
+    dx.alloc((size_t)2 * n);
+    lu_solve_dev(h, db.p, dx.p, 1);
+    std::vector<double> out((size_t)2 * n);
+    dx.download(out.data(), out.size(), s);
+    FW_CHECK_CUDA(cudaStreamSynchronize(s));
+    if (rhs_is_complex)
+      memcpy(x, out.data(), sizeof(double) * 2 * n);
+    else
+      for (int i = 0; i < n; ++i) ((double*)x)[i] = out[2 * (size_t)i];
+  } else if (!rhs_is_complex) {
+    db.upload((const double*)b, (size_t)n, s);
+    dx.alloc((size_t)n);
+    lu_solve_dev(h, db.p, dx.p, 1);
+    dx.download((double*)x, (size_t)n, s);
+    FW_CHECK_CUDA(cudaStreamSynchronize(s));
+  } else {
+    // real factors, complex rhs: solve real and imaginary parts as two right-hand sides
+    std::vector<double> tmp((size_t)2 * n);
+    for (int i = 0; i < n; ++i) {
+      tmp[i] = ((const double*)b)[2 * (size_t)i];
+      tmp[(size_t)n + i] = ((const double*)b)[2 * (size_t)i + 1];
+    }
+    db.upload(tmp.data(), tmp.size(), s);
+    dx.alloc((size_t)2 * n);
+    lu_solve_dev(h, db.p, dx.p, 2);
+    dx.download(tmp.data(), tmp.size(), s);
+    FW_CHECK_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < n; ++i) {
+      ((double*)x)[2 * (size_t)i] = tmp[i];
+      ((double*)x)[2 * (size_t)i + 1] = tmp[(size_t)n + i];
+    }
+  }
+  FW_API_END
+}
+
+int fw_postprocess_modes(fw_handle* hh, int32_t k, const double* lams, const double* X, double k0, double omega,
+                         double mu0, double* E, double* H, double* powers) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && lams && X && E && H && powers && k >= 1, "bad argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  FW_REQUIRE(h.sp.valid && h.has_symbolic, "space/symbolic missing");
+  const size_t cnt = (size_t)k * h.sp.n * 2;
+  DevBuf<double> dE, dH;
+  dE.upload(X, cnt, h.stream);
+  dH.alloc(cnt);
+  Timer t(h.stream);
+  postprocess_modes_dev(h, k, (const std::complex<double>*)lams, dE.p, k0, omega, mu0, dE.p, dH.p,
+                        (std::complex<double>*)powers);
+  h.tim.postprocess_ms = t.stop();
+  dE.download(E, cnt, h.stream);
+  dH.download(H, cnt, h.stream);
+  FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
+  FW_API_END
+}
+
+int fw_hfield(fw_handle* hh, const double* E, double beta_re, double beta_im, double omega, double mu0, double* H) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && E && H, "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  FW_REQUIRE(h.sp.valid && h.has_symbolic, "space/symbolic missing");
+  const size_t cnt = (size_t)h.sp.n * 2;
+  DevBuf<double> dE, dH;
+  dE.upload(E, cnt, h.stream);
+  dH.alloc(cnt);
+  hfield_dev(h, (const cplx*)dE.p, cplx{beta_re, beta_im}, omega, mu0, (cplx*)dH.p);
+  dH.download(H, cnt, h.stream);
+  FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
+  FW_API_END
+}
+
+int fw_functional(fw_handle* hh, int32_t kind, const double* f0, const double* f1, const double* f2,
+                  const double* f3, int32_t aux_kind, int32_t aux_is_complex, const void* aux, int32_t n_sel,
+                  const int32_t* elements, int32_t option, double* out) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && f0 && out, "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  FW_REQUIRE(h.sp.valid, "space missing");
+  const Space& sp = h.sp;
+  cudaStream_t s = h.stream;
+  const size_t cnt = (size_t)sp.n * 2;
+  const double* hf[4] = {f0, f1, f2, f3};
+  DevBuf<double> df[4];
+  const cplx* dp[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < 4; ++i)
+    if (hf[i]) {
+      // identical host pointers (e.g. the self overlap) share one device copy
+      int same = -1;
+      for (int j = 0; j < i; ++j)
+        if (hf[j] == hf[i]) same = j;
+      if (same >= 0) {
+        dp[i] = dp[same];
+      } else {
+        df[i].upload(hf[i], cnt, s);
+        dp[i] = (const cplx*)df[i].p;
+      }
+    }
+  DevBuf<double> daux;
+  if (aux) {
+    const size_t na = (aux_kind == FW_EPS_P0 ? (size_t)sp.ne : (size_t)3 * sp.ne) * (aux_is_complex ? 2 : 1);
+    daux.upload((const double*)aux, na, s);
+  }
+  DevBuf<int> dsel;
+  if (elements) {
+    for (int i = 0; i < n_sel; ++i) FW_REQUIRE(elements[i] >= 0 && elements[i] < sp.ne, "element index out of range");
+    dsel.upload(elements, (size_t)n_sel, s);
+  }
+  std::complex<double> o3[3];
+  functional_dev(h, kind, dp[0], dp[1], dp[2], dp[3], aux_kind, aux_is_complex != 0, aux ? daux.p : nullptr, n_sel,
+                 elements ? dsel.p : nullptr, option, o3);
+  for (int k = 0; k < 3; ++k) out[2 * k] = o3[k].real(), out[2 * k + 1] = o3[k].imag();
+  FW_API_END
+}
+
+int fw_compute_modes(fw_handle* hh, const fw_modes_params* prm, double* lams, double* E, double* H, double* powers,
+                     fw_eigs_stats* st) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && prm && lams && E && H && powers, "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  FW_REQUIRE(h.sp.valid, "fw_set_space must be called first");
+  cudaStream_t s = h.stream;
+  const double keep_upload = h.tim.upload_ms;
+  const double keep_symbolic = h.tim.symbolic_ms;
+  h.tim = fw_timings{};
+  h.tim.upload_ms = keep_upload;
+  h.tim.symbolic_ms = keep_symbolic;
+  Timer total(s);
+  if (!(prm->reuse_symbolic && h.has_symbolic)) {
+    Timer t(s);
+    symbolic_space(h);
+    h.tim.symbolic_ms = t.stop();
+  }
+  const double k0 = 2.0 * M_PI / prm->wavelength;
+  assemble_waveguide(h, prm->eps_kind, prm->eps_is_complex != 0, prm->eps, k0, prm->mu_r, prm->radius);
+  DevBuf<double> Xd, Hd;
+  eigs_shift_invert(h, prm->eigs, (std::complex<double>*)lams, Xd, st);
+  const int k = prm->eigs.k;
+  const size_t cnt = (size_t)k * h.sp.n * 2;
+  Hd.alloc(cnt);
+  {
+    Timer t(s);
+    const double c0 = 299792458.0, mu0 = 1.25663706212e-06;
+    postprocess_modes_dev(h, k, (const std::complex<double>*)lams, Xd.p, k0, k0 * c0, mu0, Xd.p, Hd.p,
+                          (std::complex<double>*)powers);
+    h.tim.postprocess_ms = t.stop();
+  }
+  Xd.download(E, cnt, s);
+  Hd.download(H, cnt, s);
+  FW_CHECK_CUDA(cudaStreamSynchronize(s));
+  h.tim.total_ms = total.stop();
+  FW_API_END
+}
+
+int fw_host_dense_eig(int32_t n, const double* a, double* w, double* v) {
+  FW_API_BEGIN
+  FW_REQUIRE(n >= 1 && a && w && v, "bad argument");
+  if (!dense_eig(n, (const std::complex<double>*)a, (std::complex<double>*)w, (std::complex<double>*)v))
+    throw Error(FW_ERR_NOCONV, "QR iteration failed");
+  FW_API_END
+}
+
+// host-only: analysis phase of the sparse LU on caller-provided element connectivity (CPU tests)
+static thread_local std::unique_ptr<LUSymbolic> g_dbg_sym;
+int fw_debug_lu_symbolic(int32_t n, int32_t nb, int32_t ne, const int32_t* edofs, const double* cx, const double* cy,
+                         const uint8_t* active, int32_t leaf_elements, int64_t* sizes /*[8]*/) {
+  FW_API_BEGIN
+  FW_REQUIRE(edofs && cx && cy && active && sizes, "NULL argument");
+  g_dbg_sym.reset(new LUSymbolic());
+  lu_symbolic_build(*g_dbg_sym, n, nb, ne, edofs, cx, cy, active, leaf_elements);
+  const LUSymbolic& S = *g_dbg_sym;
+  sizes[0] = S.n_active, sizes[1] = S.n_nodes, sizes[2] = S.n_levels, sizes[3] = (int64_t)S.blist.size();
+  sizes[4] = S.factor_entries, sizes[5] = S.work_entries, sizes[6] = S.max_m, sizes[7] = S.max_ns;
+  FW_API_END
+}
+// which: 0 perm, 1 iperm, 2 node_of, 3 parent, 4 child0, 5 child1, 6 depth, 7 m, 8 ns, 9 own_start,
+//        10 blist, 11 rel, 12 level_start, 13 level_nodes (int32) ; 20 front_off, 21 blist_off (int64)
+int fw_debug_lu_symbolic_get(int32_t which, void* out) {
+  FW_API_BEGIN
+  FW_REQUIRE(g_dbg_sym && out, "fw_debug_lu_symbolic must be called first");
+  const LUSymbolic& S = *g_dbg_sym;
+  auto cp = [&](const std::vector<int>& v) { memcpy(out, v.data(), v.size() * sizeof(int)); };
+  auto cp64 = [&](const std::vector<int64_t>& v) { memcpy(out, v.data(), v.size() * sizeof(int64_t)); };
+  switch (which) {
+    case 0: cp(S.perm); break;
+    case 1: cp(S.iperm); break;
+    case 2: cp(S.node_of); break;
+    case 3: cp(S.parent); break;
+    case 4: cp(S.child0); break;
+    case 5: cp(S.child1); break;
+    case 6: cp(S.depth); break;
+    case 7: cp(S.m); break;
+    case 8: cp(S.ns); break;
+    case 9: cp(S.own_start); break;
+    case 10: cp(S.blist); break;
+    case 11: cp(S.rel); break;
+    case 12: cp(S.level_start); break;
+    case 13: cp(S.level_nodes); break;
+    case 20: cp64(S.front_off); break;
+    case 21: cp64(S.blist_off); break;
+    default: throw Error(FW_ERR_INVALID, "unknown array id");
+  }
+  FW_API_END
+}
+
+int fw_get_timings(fw_handle* hh, fw_timings* t) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && t, "NULL argument");
+  *t = hh->h.tim;
+  FW_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,637 @@
+// Shift-invert Arnoldi with thick (Krylov-Schur style) restarts on OP = (K - sigma M)^-1 M,
+// K = -A, M = -B.  Replaces scipy.sparse.linalg.eigs(K, M=M, k, sigma) -- ARPACK mode 3 --
+// as called through skfem's solver_eigen_scipy (femwell/maxwell/waveguide.py:611-625;
+// scipy arpack.py:1184-1442).  Hand-written kernels: masked SpMV (K4), CGS2 multi-dot /
+// multi-axpy (K5), basis update V <- V Q and Ritz vector extraction (K6).
+#include <algorithm>
+#include <complex>
+
+#include "lu.h"
+#include "solver.h"
+
+namespace fw {
+
+using cd = std::complex<double>;
+constexpr int MAXV = 128;
+
+// ------------------------------------------------------------------------------ operator kernels
+template <class V, class S>
+__device__ inline S cvt_(V v);
+template <>
+__device__ inline double cvt_<double, double>(double v) { return v; }
+template <>
+__device__ inline cplx cvt_<double, cplx>(double v) { return {v, 0.0}; }
+template <>
+__device__ inline cplx cvt_<cplx, cplx>(cplx v) { return v; }
+
+__device__ inline double shfl_xor_(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+__device__ inline cplx shfl_xor_(cplx v, int o) {
+  return {__shfl_xor_sync(0xffffffffu, v.re, o), __shfl_xor_sync(0xffffffffu, v.im, o)};
+}
+
+template <class V, class S>
+__global__ void __launch_bounds__(256) k_op_apply(int n, const int* __restrict__ indptr,
+                                                  const int* __restrict__ indices, const V* __restrict__ A,
+                                                  const V* __restrict__ B, S alphaA, S alphaB, bool useA,
+                                                  const uint8_t* __restrict__ active, const S* __restrict__ x,
+                                                  S* __restrict__ y) {
+  constexpr int TPR = 8;
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = (int)(gt / TPR), l = (int)(gt % TPR);
+  S accA = scalar_traits<S>::zero(), accB = scalar_traits<S>::zero();
+  const bool live = row < n && active[row];
+  if (live) {
+    const int a = indptr[row], b = indptr[row + 1];
+    for (int k = a + l; k < b; k += TPR) {
+      const int c = indices[k];
+      if (!active[c]) continue;
+      const S xv = x[c];
+      if (useA) fma_(accA, cvt_<V, S>(A[k]), xv);
+      fma_(accB, cvt_<V, S>(B[k]), xv);
+    }
+  }
+#pragma unroll
+  for (int o = TPR / 2; o > 0; o >>= 1) {
+    accA = accA + shfl_xor_(accA, o);
+    accB = accB + shfl_xor_(accB, o);
+  }
+  if (l == 0 && row < n) y[row] = live ? (alphaA * accA + alphaB * accB) : scalar_traits<S>::zero();
+}
+
+template <class V, class S>
+static void op_apply_impl(Handle& h, const uint8_t* active, S alphaA, S alphaB, bool useA, const S* x, S* y) {
+  const Pattern& pat = h.pat;
+  k_op_apply<V, S><<<cdiv((int64_t)pat.n * 8, 256), 256, 0, h.stream>>>(
+      pat.n, pat.indptr.p, pat.indices.p, (const V*)h.A.v.p, (const V*)h.B.v.p, alphaA, alphaB, useA, active, x, y);
+  FW_CHECK_CUDA(cudaGetLastError());
+  h.tim.kernel_launches += 1;
+}
+
+// ------------------------------------------------------------------------------ CGS2 kernels
+// partial[b*nvec + i] = sum over the rows of block b of conj(V[i][r]) * w[r]
+template <class T>
+__global__ void __launch_bounds__(256) k_multidot(const T* __restrict__ V, int nvec, int64_t ld,
+                                                  const T* __restrict__ w, int n, T* __restrict__ partial) {
+  __shared__ T part[8][MAXV];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int64_t base = (int64_t)blockIdx.x * 1024;
+  T wr[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int64_t r = base + k * 256 + t;
+    wr[k] = r < n ? w[r] : scalar_traits<T>::zero();
+  }
+  for (int i = 0; i < nvec; ++i) {
+    const T* vi = V + (int64_t)i * ld;
+    T s = scalar_traits<T>::zero();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int64_t r = base + k * 256 + t;
+      if (r < n) fma_(s, conj_(vi[r]), wr[k]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = s + shfl_xor_(s, o);
+    if (lane == 0) part[warp][i] = s;
+  }
+  __syncthreads();
+  for (int i = t; i < nvec; i += 256) {
+    T s = part[0][i];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) s = s + part[q][i];
+    partial[(int64_t)blockIdx.x * nvec + i] = s;
+  }
+}
+
+// out[i] = sum_b partial[b*nvec + i]   (one block per i, fixed order => deterministic)
+template <class T>
+__global__ void __launch_bounds__(256) k_reduce_partials(const T* __restrict__ partial, int nblocks, int nvec,
+                                                         T* __restrict__ out) {
+  __shared__ T sh[256];
+  const int i = blockIdx.x, t = threadIdx.x;
+  T s = scalar_traits<T>::zero();
+  for (int b = t; b < nblocks; b += 256) s = s + partial[(int64_t)b * nvec + i];
+  sh[t] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) sh[t] = sh[t] + sh[t + o];
+    __syncthreads();
+  }
+  if (t == 0) out[i] = sh[0];
+}
+
+// w[r] -= sum_i V[i][r] * hc[i] ; optionally accumulates |w|^2 per block into nrm_partial
+template <class T>
+__global__ void __launch_bounds__(256) k_multiaxpy(T* __restrict__ w, const T* __restrict__ V, int nvec, int64_t ld,
+                                                   int n, const T* __restrict__ hc, double* __restrict__ nrm_partial) {
+  __shared__ T sh[MAXV];
+  __shared__ double red[8];
+  const int t = threadIdx.x;
+  for (int i = t; i < nvec; i += 256) sh[i] = hc[i];
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * 1024;
+  double nrm = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int64_t r = base + k * 256 + t;
+    if (r < n) {
+      T acc = w[r];
+      for (int i = 0; i < nvec; ++i) fnma_(acc, V[(int64_t)i * ld + r], sh[i]);
+      w[r] = acc;
+      nrm += abs2_(acc);
+    }
+  }
+  if (nrm_partial) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    if ((t & 31) == 0) red[t >> 5] = nrm;
+    __syncthreads();
+    if (t == 0) {
+      double s = 0;
+      for (int q = 0; q < 8; ++q) s += red[q];
+      nrm_partial[blockIdx.x] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_reduce_double(const double* __restrict__ partial, int nblocks,
+                                                       double* __restrict__ out) {
+  __shared__ double sh[256];
+  const int t = threadIdx.x;
+  double s = 0;
+  for (int b = t; b < nblocks; b += 256) s += partial[b];
+  sh[t] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) sh[t] += sh[t + o];
+    __syncthreads();
+  }
+  if (t == 0) out[0] = sh[0];
+}
+
+template <class T>
+__global__ void k_scale_copy(const T* __restrict__ src, T* __restrict__ dst, int n, double scale) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * scale;
+}
+template <class T>
+__global__ void k_axpy1(T* __restrict__ y, const T* __restrict__ x, int n, double a) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = y[i] + x[i] * a;
+}
+template <class T>
+__global__ void k_sub(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] - b[i];
+}
+template <class T>
+__global__ void k_sqnorm_partial(const T* __restrict__ v, int n, double* __restrict__ partial) {
+  __shared__ double red[8];
+  const int t = threadIdx.x;
+  const int64_t base = (int64_t)blockIdx.x * 1024;
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int64_t r = base + k * 256 + t;
+    if (r < n) s += abs2_(v[r]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((t & 31) == 0) red[t >> 5] = s;
+  __syncthreads();
+  if (t == 0) {
+    double q = 0;
+    for (int i = 0; i < 8; ++i) q += red[i];
+    partial[blockIdx.x] = q;
+  }
+}
+
+// V[0..p) <- V[0..m) Q (Q: m x p column-major) ; V[p] <- V[m].  One thread per row.
+template <class T>
+__global__ void __launch_bounds__(128) k_basis_update(T* __restrict__ V, int64_t ld, int n, int m, int p,
+                                                      const T* __restrict__ Q) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  T v[MAXV];
+  for (int l = 0; l < m; ++l) v[l] = V[(int64_t)l * ld + r];
+  const T last = V[(int64_t)m * ld + r];
+  for (int i = 0; i < p; ++i) {
+    T acc = scalar_traits<T>::zero();
+    for (int l = 0; l < m; ++l) fma_(acc, v[l], Q[(size_t)i * m + l]);
+    V[(int64_t)i * ld + r] = acc;
+  }
+  V[(int64_t)p * ld + r] = last;
+}
+
+__device__ inline cplx mulc_(double a, cplx b) { return {a * b.re, a * b.im}; }
+__device__ inline cplx mulc_(cplx a, cplx b) { return a * b; }
+
+// X[i][r] = sum_l V[l][r] * Y[l + i*m]   (Y complex, X complex)
+template <class T>
+__global__ void __launch_bounds__(128) k_ritz_vectors(const T* __restrict__ V, int64_t ld, int n, int m, int k,
+                                                      const cplx* __restrict__ Y, cplx* __restrict__ X) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  for (int i = 0; i < k; ++i) {
+    cplx acc{0.0, 0.0};
+    for (int l = 0; l < m; ++l) acc += mulc_(V[(int64_t)l * ld + r], Y[(size_t)i * m + l]);
+    X[(int64_t)i * n + r] = acc;
+  }
+}
+
+__global__ void k_mask_real_to(const double* __restrict__ src, const uint8_t* __restrict__ active, int n,
+                               double* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = active[i] ? src[i] : 0.0;
+}
+__global__ void k_mask_real_to(const double* __restrict__ src, const uint8_t* __restrict__ active, int n,
+                               cplx* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = cplx{active[i] ? src[i] : 0.0, 0.0};
+}
+
+// ------------------------------------------------------------------------------ host helpers
+namespace {
+
+template <class T>
+struct HostScalar;
+template <>
+struct HostScalar<double> {
+  static cd to_cd(double v) { return cd(v, 0.0); }
+  static double from_cd(cd v) { return v.real(); }
+};
+template <>
+struct HostScalar<cplx> {
+  static cd to_cd(cplx v) { return cd(v.re, v.im); }
+  static cplx from_cd(cd v) { return cplx{v.real(), v.imag()}; }
+};
+
+struct Work {
+  DevBuf<double> V, w, t1, t2, partial, hdev, nrmp, nrm, Qd, Yd;
+};
+
+template <class T>
+double dev_norm(Handle& h, const T* v, int n, Work& W) {
+  const int nb = cdiv(n, 1024);
+  W.nrmp.alloc((size_t)nb);
+  W.nrm.alloc(1);
+  k_sqnorm_partial<T><<<nb, 256, 0, h.stream>>>(v, n, W.nrmp.p);
+  k_reduce_double<<<1, 256, 0, h.stream>>>(W.nrmp.p, nb, W.nrm.p);
+  double r = 0;
+  W.nrm.download(&r, 1, h.stream);
+  FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
+  h.tim.kernel_launches += 2;
+  return std::sqrt(r);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------ the solver
+template <class T, class V>
+static void eigs_typed(Handle& h, const fw_eigs_params& prm, const std::vector<uint8_t>& active_host, cd sigma,
+                       cd* lams, DevBuf<double>& X_dev, fw_eigs_stats* st) {
+  using HS = HostScalar<T>;
+  constexpr size_t wsc = sizeof(T) / sizeof(double);
+  cudaStream_t s = h.stream;
+  LU& lu = *h.lu;
+  const int n = h.sp.n;
+  const int k = prm.k;
+  int m = prm.ncv > 0 ? prm.ncv : std::max(2 * k + 1, 20);
+  const int n_active = lu.sym.n_active;
+  m = std::min(m, std::min(n_active - 1, MAXV - 2));
+  FW_REQUIRE(k >= 1 && k < m, "need 1 <= k < ncv <= n_active - 1");
+  const int maxrestart = prm.maxiter > 0 ? prm.maxiter : 300;
+  const double tol = prm.tol > 0 ? prm.tol : 1e-14;
+  const int refine = prm.refine < 0 ? 0 : prm.refine;
+
+  DevBuf<uint8_t> act;
+  act.upload(active_host.data(), active_host.size(), s);
+  Work W;
+  W.V.alloc((size_t)(m + 1) * n * wsc);
+  W.w.alloc((size_t)n * wsc);
+  W.t1.alloc((size_t)n * wsc);
+  W.t2.alloc((size_t)n * wsc);
+  const int nblk = cdiv(n, 1024);
+  W.partial.alloc((size_t)nblk * MAXV * wsc);
+  W.hdev.alloc((size_t)2 * MAXV * wsc);
+  W.nrmp.alloc((size_t)nblk);
+  W.nrm.alloc(1);
+  T* Vb = (T*)W.V.p;
+  T* w = (T*)W.w.p;
+  T* t1 = (T*)W.t1.p;
+  T* t2 = (T*)W.t2.p;
+  const int64_t ld = n;
+  int n_op = 0;
+  double solve_ms = 0;
+  const T sigT = HS::from_cd(sigma);
+  const T minus1 = HS::from_cd(cd(-1.0, 0.0));
+  const T zeroT = HS::from_cd(cd(0.0, 0.0));
+
+  // y = OP x = (K - sigma M)^-1 M x, with `refine` steps of iterative refinement on the solve
+  auto apply_op = [&](const T* x, T* y) {
+    // t1 = M x = -(B x)
+    op_apply_impl<V, T>(h, act.p, zeroT, minus1, false, x, t1);
+    Timer ts(s);
+    lu_solve_dev(h, t1, y, 1);
+    for (int it = 0; it < refine; ++it) {
+      // r = t1 - (K - sigma M) y = t1 - (-A + sigma B) y
+      op_apply_impl<V, T>(h, act.p, minus1, sigT, true, y, t2);
+      k_sub<T><<<cdiv(n, 256), 256, 0, s>>>(t1, t2, t2, n);
+      lu_solve_dev(h, t2, t2, 1);
+      k_axpy1<T><<<cdiv(n, 256), 256, 0, s>>>(y, t2, n, 1.0);
+      h.tim.kernel_launches += 2;
+    }
+    solve_ms += ts.stop();
+    ++n_op;
+  };
+
+  // ---- start vector (ARPACK forces it into range(OP) with one application)
+  {
+    std::vector<double> v0((size_t)n);
+    if (prm.v0) {
+      std::copy(prm.v0, prm.v0 + n, v0.begin());
+    } else {
+      uint64_t z = 0x9E3779B97F4A7C15ull;
+      for (int i = 0; i < n; ++i) {
+        z += 0x9E3779B97F4A7C15ull;
+        uint64_t x = z;
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        x ^= x >> 31;
+        v0[i] = (double)(x >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+      }
+    }
+    DevBuf<double> v0d;
+    v0d.upload(v0.data(), v0.size(), s);
+    k_mask_real_to<<<cdiv(n, 256), 256, 0, s>>>(v0d.p, act.p, n, w);
+    FW_CHECK_CUDA(cudaStreamSynchronize(s));
+    apply_op(w, Vb);
+    double nv = dev_norm<T>(h, Vb, n, W);
+    FW_REQUIRE(nv > 0 && std::isfinite(nv), "start vector has no component in range(OP)");
+    k_scale_copy<T><<<cdiv(n, 256), 256, 0, s>>>(Vb, Vb, n, 1.0 / nv);
+  }
+
+  std::vector<cd> H((size_t)(m + 1) * m, cd(0));  // column-major, (m+1) x m
+  auto Hat = [&](int i, int j) -> cd& { return H[(size_t)j * (m + 1) + i]; };
+  std::vector<cd> theta(m), Y((size_t)m * m), Hm((size_t)m * m);
+  std::vector<int> order(m);
+  std::vector<double> resid(m);
+  std::vector<T> hbuf(2 * MAXV);
+  int j0 = 0, restarts = 0, iterations = 0, nconv = 0, m_eff = m;
+  bool done = false;
+
+  while (!done) {
+    for (int j = j0; j < m_eff; ++j) {
+      apply_op(Vb + (int64_t)j * ld, w);
+      const int nvec = j + 1;
+      T* h1 = (T*)W.hdev.p;
+      T* h2 = h1 + MAXV;
+      // CGS2: two passes of (h = V^H w ; w -= V h)
+      k_multidot<T><<<nblk, 256, 0, s>>>(Vb, nvec, ld, w, n, (T*)W.partial.p);
+      k_reduce_partials<T><<<nvec, 256, 0, s>>>((const T*)W.partial.p, nblk, nvec, h1);
+      k_multiaxpy<T><<<nblk, 256, 0, s>>>(w, Vb, nvec, ld, n, h1, nullptr);
+      k_multidot<T><<<nblk, 256, 0, s>>>(Vb, nvec, ld, w, n, (T*)W.partial.p);
+      k_reduce_partials<T><<<nvec, 256, 0, s>>>((const T*)W.partial.p, nblk, nvec, h2);
+      k_multiaxpy<T><<<nblk, 256, 0, s>>>(w, Vb, nvec, ld, n, h2, W.nrmp.p);
+      k_reduce_double<<<1, 256, 0, s>>>(W.nrmp.p, nblk, W.nrm.p);
+      h.tim.kernel_launches += 7;
+      double nrm2 = 0;
+      FW_CHECK_CUDA(cudaMemcpyAsync(hbuf.data(), W.hdev.p, (size_t)2 * MAXV * sizeof(T), cudaMemcpyDeviceToHost, s));
+      W.nrm.download(&nrm2, 1, s);
+      FW_CHECK_CUDA(cudaStreamSynchronize(s));
+      double hn = 0;
+      for (int i = 0; i < nvec; ++i) {
+        cd hv = HS::to_cd(hbuf[i]) + HS::to_cd(hbuf[MAXV + i]);
+        Hat(i, j) += hv;  // += : after a restart column j0.. are fresh zeros
+        hn += std::norm(hv);
+      }
+      const double beta = std::sqrt(nrm2);
+      FW_REQUIRE(std::isfinite(beta), "Arnoldi produced a non-finite vector (factorisation failed?)");
+      Hat(j + 1, j) = beta;
+      ++iterations;
+      if (beta <= 1e-14 * std::sqrt(hn) || beta == 0.0) {
+        // invariant subspace: the Ritz pairs of the leading (j+1) block are exact
+        m_eff = j + 1;
+        Hat(j + 1, j) = 0.0;
+        break;
+      }
+      k_scale_copy<T><<<cdiv(n, 256), 256, 0, s>>>(w, Vb + (int64_t)(j + 1) * ld, n, 1.0 / beta);
+      h.tim.kernel_launches += 1;
+    }
+    // ---- Ritz pairs of the m_eff x m_eff projected matrix
+    const int me = m_eff;
+    for (int j = 0; j < me; ++j)
+      for (int i = 0; i < me; ++i) Hm[(size_t)j * me + i] = Hat(i, j);
+    if (!dense_eig(me, Hm.data(), theta.data(), Y.data()))
+      throw Error(FW_ERR_NOCONV, "QR iteration on the projected matrix failed");
+    for (int i = 0; i < me; ++i) {
+      order[i] = i;
+      cd r = 0;
+      for (int l = 0; l < me; ++l) r += Hat(me, l) * Y[(size_t)i * me + l];
+      resid[i] = std::abs(r);
+    }
+    std::sort(order.begin(), order.begin() + me, [&](int a, int b) {
+      double aa = std::abs(theta[a]), bb = std::abs(theta[b]);
+      if (aa != bb) return aa > bb;
+      return theta[a].imag() > theta[b].imag();
+    });
+    nconv = 0;
+    const double eps23 = 3.666852862501036e-11;  // eps^(2/3), ARPACK's floor for the Ritz value scale
+    const int kk = std::min(k, me);
+    for (int i = 0; i < kk; ++i)
+      if (resid[order[i]] <= tol * std::max(eps23, std::abs(theta[order[i]]))) ++nconv;
+    if (nconv >= kk || me < m || restarts >= maxrestart) {
+      done = true;
+      break;
+    }
+    // ---- thick restart: keep p Ritz directions, V <- V Q, H <- Q^H H Q, last row b^T Q
+    ++restarts;
+    int p = std::min(me - 1, k + std::max(1, (me - k) / 2));
+    std::vector<std::vector<cd>> basis;
+    const bool real_arith = !scalar_traits<T>::is_complex;
+    std::vector<char> used(me, 0);
+    for (int ii = 0; ii < me && (int)basis.size() < p; ++ii) {
+      const int i = order[ii];
+      if (used[i]) continue;
+      used[i] = 1;
+      std::vector<cd> y(Y.begin() + (size_t)i * me, Y.begin() + (size_t)(i + 1) * me);
+      if (!real_arith) {
+        basis.push_back(y);
+        continue;
+      }
+      const bool is_real = std::abs(theta[i].imag()) <= 1e-12 * std::abs(theta[i]);
+      if (is_real) {
+        int big = 0;
+        for (int l = 1; l < me; ++l)
+          if (std::abs(y[l]) > std::abs(y[big])) big = l;
+        cd ph = std::conj(y[big]) / std::abs(y[big]);
+        for (auto& v : y) v = cd((v * ph).real(), 0.0);
+        basis.push_back(y);
+      } else {
+        // complex pair: keep Re and Im, and mark the conjugate partner as used
+        int partner = -1;
+        double best = 1e300;
+        for (int l = 0; l < me; ++l)
+          if (!used[l]) {
+            double dd = std::abs(theta[l] - std::conj(theta[i]));
+            if (dd < best) best = dd, partner = l;
+          }
+        if (partner >= 0 && best <= 1e-8 * std::abs(theta[i])) used[partner] = 1;
+        std::vector<cd> yr(me), yi(me);
+        for (int l = 0; l < me; ++l) yr[l] = cd(y[l].real(), 0.0), yi[l] = cd(y[l].imag(), 0.0);
+        basis.push_back(yr);
+        basis.push_back(yi);
+      }
+    }
+    // orthonormalise (MGS, two sweeps), dropping dependent directions
+    std::vector<std::vector<cd>> Q;
+    for (auto& b : basis) {
+      std::vector<cd> v = b;
+      for (int sweep = 0; sweep < 2; ++sweep)
+        for (auto& q : Q) {
+          cd d = 0;
+          for (int l = 0; l < me; ++l) d += std::conj(q[l]) * v[l];
+          for (int l = 0; l < me; ++l) v[l] -= d * q[l];
+        }
+      double nv = 0;
+      for (auto& x : v) nv += std::norm(x);
+      nv = std::sqrt(nv);
+      if (nv < 1e-10) continue;
+      for (auto& x : v) x /= nv;
+      Q.push_back(v);
+    }
+    p = (int)Q.size();
+    if (p >= me) p = me - 1, Q.resize(p);
+    // new projected matrix
+    std::vector<cd> HQ((size_t)me * p, cd(0));
+    for (int c = 0; c < p; ++c)
+      for (int l = 0; l < me; ++l) {
+        const cd q = Q[c][l];
+        if (q == cd(0)) continue;
+        for (int i = 0; i < me; ++i) HQ[(size_t)c * me + i] += Hat(i, l) * q;
+      }
+    std::vector<cd> Hn((size_t)(p + 1) * p, cd(0));
+    for (int c = 0; c < p; ++c) {
+      for (int r = 0; r < p; ++r) {
+        cd sacc = 0;
+        for (int l = 0; l < me; ++l) sacc += std::conj(Q[r][l]) * HQ[(size_t)c * me + l];
+        Hn[(size_t)c * (p + 1) + r] = sacc;
+      }
+      cd bacc = 0;
+      for (int l = 0; l < me; ++l) bacc += Hat(me, l) * Q[c][l];
+      Hn[(size_t)c * (p + 1) + p] = bacc;
+    }
+    std::fill(H.begin(), H.end(), cd(0));
+    for (int c = 0; c < p; ++c)
+      for (int r = 0; r <= p; ++r) Hat(r, c) = Hn[(size_t)c * (p + 1) + r];
+    // device basis update
+    std::vector<T> Qh((size_t)me * p);
+    for (int c = 0; c < p; ++c)
+      for (int l = 0; l < me; ++l) Qh[(size_t)c * me + l] = HS::from_cd(Q[c][l]);
+    W.Qd.upload((const double*)Qh.data(), Qh.size() * wsc, s);
+    k_basis_update<T><<<cdiv(n, 128), 128, 0, s>>>(Vb, ld, n, me, p, (const T*)W.Qd.p);
+    FW_CHECK_CUDA(cudaStreamSynchronize(s));
+    h.tim.kernel_launches += 1;
+    j0 = p;
+  }
+
+  // ---- extract the k wanted Ritz pairs
+  const int me = m_eff;
+  const int kk = std::min(k, me);
+  if (nconv < kk || kk < k) {
+    if (st) {
+      st->nconv = nconv;
+      st->iterations = iterations;
+      st->restarts = restarts;
+      st->n_op = n_op;
+    }
+    throw Error(FW_ERR_NOCONV, "ARPACK-style error: no convergence (" + std::to_string(nconv) + "/" +
+                                   std::to_string(k) + " eigenvalues converged after " + std::to_string(restarts) +
+                                   " restarts)");
+  }
+  std::vector<cplx> Yh((size_t)me * k);
+  double maxres = 0;
+  for (int i = 0; i < k; ++i) {
+    const int o = order[i];
+    lams[i] = sigma + 1.0 / theta[o];
+    maxres = std::max(maxres, resid[o] / std::abs(theta[o]));
+    for (int l = 0; l < me; ++l) Yh[(size_t)i * me + l] = cplx{Y[(size_t)o * me + l].real(), Y[(size_t)o * me + l].imag()};
+  }
+  W.Yd.upload((const double*)Yh.data(), Yh.size() * 2, s);
+  X_dev.alloc((size_t)k * n * 2);
+  k_ritz_vectors<T><<<cdiv(n, 128), 128, 0, s>>>(Vb, ld, n, me, k, (const cplx*)W.Yd.p, (cplx*)X_dev.p);
+  h.tim.kernel_launches += 1;
+  for (int i = 0; i < k; ++i) {
+    cplx* xi = (cplx*)X_dev.p + (int64_t)i * n;
+    double nv = dev_norm<cplx>(h, xi, n, W);
+    if (nv > 0) k_scale_copy<cplx><<<cdiv(n, 256), 256, 0, s>>>(xi, xi, n, 1.0 / nv);
+  }
+  FW_CHECK_CUDA(cudaStreamSynchronize(s));
+  if (st) {
+    st->nconv = nconv;
+    st->iterations = iterations;
+    st->restarts = restarts;
+    st->n_op = n_op;
+    st->t_solve_ms_total = solve_ms;
+    st->max_residual = maxres;
+  }
+}
+
+void eigs_shift_invert(Handle& h, const fw_eigs_params& prm, cd* lams, DevBuf<double>& X_dev, fw_eigs_stats* st) {
+  FW_REQUIRE(h.sp.valid && h.has_symbolic && h.A.valid && h.B.valid, "assemble A and B first");
+  FW_REQUIRE(prm.k >= 1, "k must be >= 1");
+  const int n = h.sp.n;
+  std::vector<uint8_t> active((size_t)n, 1);
+  for (int i = 0; i < prm.n_dirichlet; ++i) {
+    int d = prm.dirichlet[i];
+    FW_REQUIRE(d >= 0 && d < n, "dirichlet dof out of range");
+    active[d] = 0;
+  }
+  cudaStream_t s = h.stream;
+  if (st) memset(st, 0, sizeof(*st));
+  {
+    Timer t(s);
+    lu_analyse(h, active, prm.leaf_elements);
+    double ms = t.stop();
+    h.tim.lu_symbolic_ms = ms;
+    if (st) st->t_symbolic_ms = ms;
+  }
+  const cd sigma(prm.sigma_re, prm.sigma_im);
+  const bool cplx_arith = h.A.is_complex || prm.sigma_im != 0.0;
+  {
+    Timer t(s);
+    // K - sigma M = -A + sigma B
+    lu_factor(h, -1.0, 0.0, prm.sigma_re, prm.sigma_im, cplx_arith);
+    double ms = t.stop();
+    h.tim.lu_factor_ms = ms;
+    if (st) st->t_factor_ms = ms;
+  }
+  if (st) {
+    st->pivots_perturbed = h.lu->perturbed;
+    st->lu_levels = h.lu->sym.n_levels;
+    st->lu_fronts = h.lu->sym.n_nodes;
+    st->lu_factor_entries = h.lu->sym.factor_entries;
+  }
+  fw_eigs_stats tmp{};
+  {
+    Timer t(s);
+    if (!cplx_arith)
+      eigs_typed<double, double>(h, prm, active, sigma, lams, X_dev, &tmp);
+    else if (!h.A.is_complex)
+      eigs_typed<cplx, double>(h, prm, active, sigma, lams, X_dev, &tmp);
+    else
+      eigs_typed<cplx, cplx>(h, prm, active, sigma, lams, X_dev, &tmp);
+    double ms = t.stop();
+    h.tim.arnoldi_ms = ms;
+    if (st) st->t_arnoldi_ms = ms;
+  }
+  if (st) {
+    st->nconv = tmp.nconv;
+    st->iterations = tmp.iterations;
+    st->restarts = tmp.restarts;
+    st->n_op = tmp.n_op;
+    st->t_solve_ms_total = tmp.t_solve_ms_total;
+    st->max_residual = tmp.max_residual;
+  }
+}
+
+}  // namespace fw

@@ -1,0 +1,84 @@
+// The library handle: one device, one stream, all resident state of the waveguide path.
+#pragma once
+#include "common.h"
+
+namespace fw {
+
+struct LU;  // sparse multifrontal factorisation (lu.h)
+
+// structural CSR pattern + the sorted-COO bookkeeping that produced it
+struct Pattern {
+  int n = 0;              // rows
+  int64_t n_coo = 0;      // COO entries that were sorted
+  int64_t nnz = 0;        // distinct (row, col)
+  DevBuf<int> indptr;     // [n+1]
+  DevBuf<int> indices;    // [nnz]
+  DevBuf<uint32_t> perm;  // [n_coo]  source COO index of sorted position
+  DevBuf<uint32_t> seg;   // [nnz+1]  first sorted position of every CSR slot
+};
+
+// values on a Pattern (+ "any non-zero contribution" flags for eliminate_zeros parity)
+struct Values {
+  bool is_complex = false;
+  bool valid = false;
+  DevBuf<double> v;       // nnz (f64) or 2*nnz (c128)
+  DevBuf<uint8_t> flag;   // nnz
+  int64_t nnz_kept = -1;  // after eliminate_zeros
+};
+
+struct Space {
+  int order = 0, nv = 0, ne = 0, n = 0, nb = 0, nq = 0, nt = 0, nz = 0;
+  int kind[MAXNB];
+  std::vector<double> vec, sc, X, W;
+  std::vector<double> h_p;
+  std::vector<int> h_t, h_edofs;
+  DevBuf<double> p;
+  DevBuf<int> t, edofs;
+  DevBuf<uint8_t> is_z;  // [n] 1 for Lagrange (E_z) dofs
+  bool valid = false;
+};
+
+struct Handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  Space sp;
+  Pattern pat;
+  bool has_symbolic = false;
+  Values A, B, Mass, C0, C1;
+  DevBuf<double> blocks;  // scratch: local element blocks (SoA [entry][Ne])
+  // generic COO->CSR result
+  Pattern coo_pat;
+  Values coo_val;
+  // compacted export scratch
+  DevBuf<uint32_t> scan_tmp, scan_tmp2;
+  std::unique_ptr<LU> lu;
+  double lu_sigma_re = 0, lu_sigma_im = 0;
+  fw_timings tim{};
+  Handle();
+  ~Handle();
+};
+
+// ---- scan / sort / COO->CSR (sort.cu)
+void exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, DevBuf<uint32_t>& tmp, cudaStream_t s);
+void build_pattern_from_keys(Pattern& pat, DevBuf<uint64_t>& keys, DevBuf<uint32_t>& payload, int64_t n_coo,
+                             int n_rows, int col_bits, Handle& h);
+void symbolic_space(Handle& h);
+template <class S>
+void reduce_onto_pattern(const Pattern& pat, const S* coo_vals, const int* lut, int lut_n, int64_t stride,
+                         S* out, uint8_t* flag, cudaStream_t s);
+int64_t count_kept(Handle& h, const Pattern& pat, Values& val);
+void export_compacted(Handle& h, const Pattern& pat, Values& val, int* indptr, int* indices, void* data);
+void coo_to_csr(Handle& h, int n_rows, int64_t n_entries, const int* rows, const int* cols, const void* data,
+                bool is_complex);
+
+// ---- element kernels (assemble.cu)
+void upload_tables(Handle& h);
+void assemble_waveguide(Handle& h, int eps_kind, bool eps_complex, const void* eps_host, double k0, double mu_r,
+                        double radius);
+void assemble_aux(Handle& h);  // Mass, C0, C1 (geometry only, f64)
+
+// ---- CSR kernels (csr.cu)
+template <class MT, class VT>
+void spmv(int n, const int* indptr, const int* indices, const MT* vals, const VT* x, VT* y, cudaStream_t s);
+
+}  // namespace fw

@@ -1,0 +1,62 @@
+// Sparse multifrontal LU of the shifted pencil (K - sigma M) -- stands in for the cuDSS call
+// named by the north star (cuDSS is not present in this image).  Replaces
+// scipy's splu(OP) + OP.solve inside eigs mode 3 (scipy arpack.py:1006-1019, 1179-1181).
+//
+// Analysis (host, lu_symbolic.cpp): element-based geometric nested dissection (kd-tree over
+// element centroids; a dof belongs to the lowest tree node that contains all its elements),
+// postorder numbering, front index sets, extend-add maps.
+// Numeric (device, lu_numeric.cu): level-by-level batched dense partial LU of the fronts with
+// windowed partial pivoting, hand-written FP64/C128 TRSM + GEMM kernels, and level-batched
+// forward/backward substitution.
+#pragma once
+#include "handle.h"
+
+namespace fw {
+
+struct LUSymbolic {
+  int n = 0;         // total dofs
+  int n_active = 0;  // dofs that take part in the factorisation (not Dirichlet)
+  int n_nodes = 0, n_levels = 0;
+  int64_t factor_entries = 0;  // sum m^2
+  int64_t work_entries = 0;    // sum m
+  int max_m = 0, max_ns = 0;
+  std::vector<int> perm;      // [n_active] new -> old dof
+  std::vector<int> iperm;     // [n] old -> new (or -1)
+  std::vector<int> node_of;   // [n_active] owning node of a new index
+  // per node
+  std::vector<int> parent, child0, child1, depth, m, ns, own_start;
+  std::vector<int64_t> front_off;  // offset of the m x m front in the factor arena
+  std::vector<int64_t> work_off;   // offset of the length-m work vector
+  std::vector<int64_t> blist_off;  // offset into blist/rel (length m - ns)
+  std::vector<int> blist;          // boundary indices (new numbering, ascending)
+  std::vector<int> rel;            // position of each boundary index in the parent's front
+  // levels (by depth, deepest first when iterated backwards)
+  std::vector<int> level_start;    // [n_levels + 1]
+  std::vector<int> level_nodes;    // nodes sorted by depth
+  std::vector<int> level_max_ns, level_max_m, level_max_nb;
+};
+
+// centroids: [2, ne]; edofs: [nb, ne]; active: [n] (1 = in the system)
+void lu_symbolic_build(LUSymbolic& S, int n, int nb, int ne, const int* edofs, const double* cx, const double* cy,
+                       const uint8_t* active, int leaf_elements);
+
+struct LUDevice;  // device-side mirrors (lu_numeric.cu)
+
+struct LU {
+  LUSymbolic sym;
+  bool is_complex = false;
+  bool factored = false;
+  int perturbed = 0;
+  std::unique_ptr<LUDevice> dev;
+  LU();
+  ~LU();
+};
+
+// factor OP = alphaA * A + alphaB * B (values on the structural pattern h.pat)
+void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements);
+void lu_factor(Handle& h, double alphaA_re, double alphaA_im, double alphaB_re, double alphaB_im, bool complex_arith);
+// solve OP x = b for nrhs right-hand sides given in ORIGINAL dof order on the device
+// (b, x: [nrhs][n] of the LU scalar type; x[inactive] = 0).  b and x may alias.
+void lu_solve_dev(Handle& h, const void* b, void* x, int nrhs);
+
+}  // namespace fw

@@ -1,0 +1,26 @@
+// Shift-invert Arnoldi (thick restart) + post-processing entry points.
+#pragma once
+#include <complex>
+
+#include "handle.h"
+
+namespace fw {
+
+bool dense_eig(int n, const std::complex<double>* a, std::complex<double>* w, std::complex<double>* v);
+
+// device result: lams (host) and X_dev [k][n] c128 on the device (unit 2-norm Ritz vectors)
+void eigs_shift_invert(Handle& h, const fw_eigs_params& prm, std::complex<double>* lams, DevBuf<double>& X_dev,
+                       fw_eigs_stats* st);
+
+// y = (alphaA*A + alphaB*B) x with Dirichlet rows/cols masked (identity rows give 0 here)
+template <class V, class S>
+void op_apply(Handle& h, const uint8_t* active, S alphaA, S alphaB, const S* x, S* y);
+
+void postprocess_modes_dev(Handle& h, int k, const std::complex<double>* lams, const double* X_dev, double k0,
+                           double omega, double mu0, double* E_dev, double* H_dev, std::complex<double>* powers);
+void hfield_dev(Handle& h, const cplx* E_dev, cplx beta, double omega, double mu0, cplx* H_dev);
+void functional_dev(Handle& h, int kind, const cplx* f0, const cplx* f1, const cplx* f2, const cplx* f3, int aux_kind,
+                    bool aux_complex, const void* aux_dev, int n_sel, const int* elements_dev, int option,
+                    std::complex<double>* out3);
+
+}  // namespace fw

@@ -1,0 +1,257 @@
+"""Waveguide eigenmode solver -- B200-native drop-in for ``femwell.maxwell.waveguide``.
+
+Same public API as the reference (``/root/reference/femwell/maxwell/waveguide.py``):
+``compute_modes(basis_epsilon_r, epsilon_r, wavelength, *, mu_r, num_modes, order,
+metallic_boundaries, radius, n_guess, solver)`` returning ``Modes`` of ``Mode`` (:528-654), and the
+``Mode`` scalar post-processing (:54-72, :112-258), ``calculate_hfield`` (:657-677),
+``calculate_overlap`` same-basis branch (:699-736).
+
+All arithmetic runs in libfemwell_b200 (hand-written sm_100a CUDA behind the C ABI of
+``include/femwell_b200.h``); this module only validates arguments, moves numpy arrays across the
+boundary and wraps the results in the unchanged dataclasses.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from functools import cached_property
+from typing import List, Optional
+
+import numpy as np
+
+from ..basis import Basis
+from ..context import (FUN_CONFINEMENT, FUN_COUPLING, FUN_E2_E4, FUN_EX2_EY2, FUN_EX2_EY2_EALL, FUN_OVERLAP,
+                       Context)
+from ..element import (ElementTriN1, ElementTriN2, ElementTriP1, ElementTriP2, eps_kind_of)
+
+speed_of_light = 299792458.0
+epsilon_0 = 8.8541878128e-12
+mu_0 = 1.25663706212e-06
+
+_contexts = {}
+
+
+def get_context(device: Optional[int] = None) -> Context:
+    """One library handle per (process, device)."""
+    if device is None:
+        import os
+
+        device = int(os.environ.get("FEMWELL_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                device = device % torch.cuda.device_count()
+        except Exception:
+            pass
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]
+
+
+def _bind(basis: Basis, device=None) -> Context:
+    ctx = get_context(device)
+    if not ctx.same_space(basis) or ctx.nnz_structural is None:
+        ctx.set_space(basis)
+        ctx.symbolic()
+    return ctx
+
+
+@dataclass(frozen=True)
+class Mode:
+    frequency: float
+    """Frequency of the light"""
+    k: float
+    """Propagation constant of the mode"""
+    basis_epsilon_r: Basis
+    """Basis used for epsilon_r"""
+    epsilon_r: np.ndarray
+    """Epsilon_r with which the mode was calculated"""
+    basis: Basis
+    """Basis on which the mode was calculated and E/H are defined"""
+    E: np.ndarray
+    """Electric field of the mode"""
+    H: np.ndarray
+    """Magnetic field of the mode"""
+
+    @property
+    def omega(self):
+        return 2 * np.pi * self.frequency
+
+    @property
+    def k0(self):
+        return self.omega / speed_of_light
+
+    @property
+    def wavelength(self):
+        return speed_of_light / self.frequency
+
+    @property
+    def n_eff(self):
+        return self.k / self.k0
+
+    def _sel(self, elements):
+        return None if elements is None else self.basis.mesh.normalize_elements(elements)
+
+    @cached_property
+    def te_fraction(self):
+        """waveguide.py:112-127"""
+        o = _bind(self.basis).functional(FUN_EX2_EY2, [self.E], elements=self.basis.tind)
+        return (o[0] / (o[0] + o[1])).real
+
+    @cached_property
+    def tm_fraction(self):
+        return 1 - self.te_fraction
+
+    @cached_property
+    def transversality(self):
+        """waveguide.py:135-159"""
+        o = _bind(self.basis).functional(FUN_EX2_EY2_EALL, [self.E], elements=self.basis.tind)
+        return ((o[0] + o[1]) / o[2]).real
+
+    def __repr__(self) -> str:
+        return f"{self.__class__.__name__}(k: {self.k}, n_eff:{self.n_eff})"
+
+    def calculate_overlap(self, mode, elements=None):
+        return calculate_overlap(self.basis, self.E, self.H, mode.basis, mode.E, mode.H)
+
+    def calculate_coupling_coefficient(self, mode, delta_epsilon):
+        """waveguide.py:167-179"""
+        o = _bind(self.basis).functional(FUN_COUPLING, [self.E, mode.E], aux=np.asarray(delta_epsilon),
+                                         aux_kind=eps_kind_of(self.basis_epsilon_r.elem), elements=self.basis.tind)
+        return o[0]
+
+    def calculate_effective_area(self, field="xy"):
+        """waveguide.py:181-213"""
+        opt = {"xy": 0, "x": 1}.get(field, 2)
+        o = _bind(self.basis).functional(FUN_E2_E4, [self.E], option=opt, elements=self.basis.tind)
+        return np.real(o[0] ** 2 / o[1])
+
+    def calculate_propagation_loss(self, distance):
+        return -20 / np.log(10) * self.k0 * np.imag(self.n_eff) * distance
+
+    def calculate_power(self, elements=None):
+        """waveguide.py:218-223"""
+        if elements is None or (hasattr(elements, "__len__") and len(elements) == 0):
+            basis = self.basis
+        else:
+            basis = self.basis.with_elements(elements)
+        return calculate_overlap(basis, self.E, self.H, basis, self.E, self.H)
+
+    def calculate_confinement_factor(self, elements):
+        """waveguide.py:225-249"""
+        sel = self.basis.mesh.normalize_elements(elements)
+        o = _bind(self.basis).functional(FUN_CONFINEMENT, [self.E], aux=np.asarray(self.epsilon_r),
+                                         aux_kind=eps_kind_of(self.basis_epsilon_r.elem), elements=sel)
+        return speed_of_light * epsilon_0 * o[0]
+
+    def calculate_pertubated_neff(self, delta_epsilon):
+        return self.n_eff + self.calculate_coupling_coefficient(self, delta_epsilon) * epsilon_0 * speed_of_light * 0.5
+
+
+@dataclass(frozen=True)
+class Modes:
+    modes: List
+    stats: dict = field(default_factory=dict, compare=False, repr=False)
+
+    def __getitem__(self, idx) -> Mode:
+        return self.modes[idx]
+
+    def __len__(self) -> int:
+        return len(self.modes)
+
+    def __repr__(self) -> str:
+        modes = "\n\t" + "\n\t".join(repr(mode) for mode in self.modes) + "\n"
+        return f"{self.__class__.__name__}(modes=({modes}))"
+
+    def sorted(self, key):
+        return Modes(modes=sorted(self.modes, key=key))
+
+    @property
+    def n_effs(self):
+        return np.array([mode.n_eff for mode in self.modes])
+
+
+def _mode_element(order):
+    if order == 1:
+        return ElementTriN1() * ElementTriP1()
+    if order == 2:
+        return ElementTriN2() * ElementTriP2()
+    raise AssertionError("Only order 1 and 2 implemented by now.")
+
+
+def compute_modes(
+    basis_epsilon_r,
+    epsilon_r,
+    wavelength,
+    *,
+    mu_r=1,
+    num_modes=1,
+    order=1,
+    metallic_boundaries=False,
+    radius=np.inf,
+    n_guess=None,
+    solver="b200",
+    solver_options=None,
+) -> Modes:
+    """Computes the modes of a waveguide (reference signature, waveguide.py:528-540).
+
+    ``solver`` must be ``"b200"``; ``solver_options`` (dict, optional): ``v0``, ``ncv``, ``tol``,
+    ``maxiter``, ``refine``, ``leaf_elements``, ``reuse_symbolic``, ``device``.
+    """
+    if solver != "b200":
+        raise ValueError("`solver` must be `b200` in femwell_b200 (use femwell itself for `scipy`/`slepc`)")
+    opts = dict(solver_options or {})
+    k0 = 2 * np.pi / wavelength
+    element = _mode_element(order)
+    basis = basis_epsilon_r.with_element(element)
+    basis_epsilon_r = basis.with_element(basis_epsilon_r.elem)  # adjust quadrature (waveguide.py:575)
+    epsilon_r = np.asarray(epsilon_r)
+    eps_kind = eps_kind_of(basis_epsilon_r.elem)
+
+    if n_guess:
+        sigma = k0**2 * n_guess**2
+    else:
+        sigma = k0**2 * np.max(epsilon_r) * 1.1
+
+    dirichlet = None
+    if metallic_boundaries:
+        dirichlet = basis.get_dofs(None if metallic_boundaries is True else metallic_boundaries)
+
+    device = opts.pop("device", None)
+    ctx = get_context(device)
+    reuse = ctx.same_space(basis) and ctx.nnz_structural is not None
+    if not reuse:
+        ctx.set_space(basis)
+    lams, E, H, powers, stats = ctx.compute_modes(
+        eps_kind, epsilon_r, wavelength, num_modes, sigma, mu_r=float(mu_r), radius=float(radius),
+        dirichlet=dirichlet, reuse_symbolic=reuse, **opts)
+    ctx.nnz_structural = ctx.nnz_structural or -1
+    stats["timings"] = ctx.timings()
+    return Modes(
+        modes=[
+            Mode(
+                frequency=speed_of_light / wavelength,
+                k=np.sqrt(lams[i]),
+                basis_epsilon_r=basis_epsilon_r,
+                epsilon_r=epsilon_r,
+                basis=basis,
+                E=E[i].copy(),
+                H=H[i].copy(),
+            )
+            for i in range(num_modes)
+        ],
+        stats=stats,
+    )
+
+
+def calculate_hfield(basis, xs, beta, omega):
+    """waveguide.py:657-677"""
+    return _bind(basis).hfield(xs, beta, omega, mu_0)
+
+
+def calculate_overlap(basis_i, E_i, H_i, basis_j, E_j, H_j):
+    """Same-basis branch of waveguide.py:699-736 (same mesh & quadrature)."""
+    if not (basis_i.mesh is basis_j.mesh and np.array_equal(basis_i.X, basis_j.X)
+            and np.array_equal(basis_i.W, basis_j.W)):
+        raise NotImplementedError("cross-mesh overlap (waveguide.py:737-759) is a 'next' row (SURVEY.md 8f)")
+    return _bind(basis_i).functional(FUN_OVERLAP, [E_i, H_i, E_j, H_j], elements=basis_i.tind)[0]

@@ -1,0 +1,353 @@
+"""GPU parity suite: CUDA path (through the C ABI) vs the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): matrix entries 1e-12 relative, n_eff 1e-9 relative, normalised
+mode overlaps within 1e-6.  Integer/index work (CSR patterns) is compared bit-exactly.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from common import RECT_CASES, csr_rel_diff, mode_element, rectangle_problem, strip_problem
+from femwell_b200.basis import Basis
+from femwell_b200.element import ElementDG, ElementTriP0, ElementTriP1, ElementVector, triangle_quadrature
+from femwell_b200.mesh import MeshTri
+from oracle import femwell_oracle as fo
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from femwell_b200.context import Context
+
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _oracle_AB(m, b, eps_kind, eps, k0, mu_r=1.0, radius=np.inf):
+    order = b.elem.order
+    return fo.assemble_waveguide(m.p, m.t.astype(np.int64), b.element_dofs.astype(np.int64), order, b.X, b.W,
+                                 fo.interpolate_eps(eps_kind, eps, m.nelements, b.X), k0, mu_r, radius, n=b.N)
+
+
+# ----------------------------------------------------------------------------- K2: COO -> CSR
+@pytest.mark.parametrize("n_rows,n_entries,cplx,seed", [(1, 1, False, 0), (7, 0, False, 1), (50, 400, False, 2),
+                                                        (1000, 20000, True, 3), (100000, 3000000, False, 4),
+                                                        (257, 70000, False, 5)])
+def test_coo_to_csr_matches_scipy(ctx, n_rows, n_entries, cplx, seed):
+    rng = np.random.default_rng(seed)
+    rows = rng.integers(0, n_rows, n_entries).astype(np.int32)
+    cols = rng.integers(0, n_rows, n_entries).astype(np.int32)
+    data = rng.standard_normal(n_entries)
+    if cplx:
+        data = data + 1j * rng.standard_normal(n_entries)
+    if n_entries:
+        data[rng.integers(0, n_entries, n_entries // 10)] = 0  # explicit zeros must be eliminated first
+    ref = sp.coo_matrix((data, (rows, cols)), shape=(n_rows, n_rows))
+    ref.eliminate_zeros()
+    ref = ref.tocsr()
+    got = ctx.coo_to_csr(n_rows, rows, cols, data)
+    assert np.array_equal(got.indptr, ref.indptr)
+    assert np.array_equal(got.indices, ref.indices)
+    np.testing.assert_allclose(got.data, ref.data, rtol=1e-13, atol=1e-13)
+
+
+def test_coo_to_csr_cancelling_duplicates_stay_explicit(ctx):
+    rows = np.array([0, 0, 1], dtype=np.int32)
+    cols = np.array([1, 1, 0], dtype=np.int32)
+    data = np.array([2.0, -2.0, 3.0])
+    got = ctx.coo_to_csr(2, rows, cols, data)
+    assert got.nnz == 2 and got[0, 1] == 0.0 and got[1, 0] == 3.0
+
+
+# ----------------------------------------------------------------------------- K1+K2: assembly
+CASES = [
+    # order, n, jitter, eps_kind, complex, radius, intorder
+    (1, 10, 0.15, 0, False, np.inf, 2),
+    (2, 10, 0.15, 0, False, np.inf, 4),
+    (2, 8, 0.0, 0, False, np.inf, 4),      # structured: accidental exact zeros are eliminated (R8)
+    (2, 9, 0.15, 0, True, np.inf, 4),
+    (2, 9, 0.15, 1, True, 5.0, 4),        # DG-P1 complex eps + bend (config 3 style)
+    (2, 9, 0.15, 2, False, np.inf, 4),    # diagonal anisotropy
+    (2, 9, 0.15, 2, True, 7.5, 6),
+    (1, 9, 0.15, 1, False, 3.0, 5),
+    (2, 7, 0.15, 0, False, np.inf, 2),     # P0-default 3-point rule (R3)
+]
+
+
+def _make_eps(m, eps_kind, cplx, seed=0):
+    rng = np.random.default_rng(seed)
+    ne = m.nelements
+    base = np.full(ne, 1.444**2)
+    base[m.subdomains["core"]] = 3.4777**2
+    if eps_kind == 0:
+        eps = base.copy()
+    elif eps_kind == 1:
+        eps = np.repeat(base, 3) * (1 + 0.05 * rng.uniform(-1, 1, 3 * ne))
+    else:
+        eps = np.repeat(base, 3) * np.tile([1.0, 1.1, 0.9], ne)
+    if cplx:
+        eps = eps.astype(complex) - 1j * rng.uniform(0, 0.5, eps.size)
+    return eps
+
+
+@pytest.mark.parametrize("order,n,jitter,eps_kind,cplx,radius,intorder", CASES)
+def test_assembly_matches_oracle(ctx, order, n, jitter, eps_kind, cplx, radius, intorder):
+    m, _ = strip_problem(n, jitter=jitter)
+    b = Basis(m, ElementTriP0(), intorder=intorder).with_element(mode_element(order))
+    eps = _make_eps(m, eps_kind, cplx)
+    k0 = 2 * np.pi / 1.55
+    A_ref, B_ref = _oracle_AB(m, b, eps_kind, eps, k0, 1.3, radius)
+    ctx.set_space(b)
+    ctx.symbolic()
+    ctx.assemble(eps_kind, eps, k0, 1.3, radius)
+    A, B = ctx.matrix(0), ctx.matrix(1)
+    assert A.dtype == A_ref.dtype and B.dtype == B_ref.dtype
+    dA, sameA = csr_rel_diff(A, A_ref)
+    dB, sameB = csr_rel_diff(B, B_ref)
+    assert sameA and sameB, "CSR sparsity pattern differs from the reference path"
+    assert dA < 1e-12 and dB < 1e-12, (dA, dB)
+
+
+def test_assembly_golden_checksums(ctx):
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "strip_n16.json")))
+    m, eps = strip_problem(g["n"])
+    b = Basis(m, mode_element(2), intorder=4)
+    ctx.set_space(b)
+    ctx.symbolic()
+    ctx.assemble(0, eps, 2 * np.pi / g["wavelength"])
+    A, B = ctx.matrix(0), ctx.matrix(1)
+    assert A.nnz == g["nnzA"] and B.nnz == g["nnzB"]
+    assert abs(abs(A).sum() - g["sumabsA"]) < 1e-11 * g["sumabsA"]
+    assert abs(abs(B).sum() - g["sumabsB"]) < 1e-11 * g["sumabsB"]
+
+
+def test_hfield_operators_match_oracle(ctx):
+    m, eps = strip_problem(8)
+    b = Basis(m, mode_element(2), intorder=4)
+    beta = 7.3 + 0.2j
+    C_ref, M_ref = fo.assemble_hfield_operators(m.p, m.t.astype(np.int64), b.element_dofs.astype(np.int64), 2, b.X,
+                                                b.W, beta, b.N)
+    ctx.set_space(b)
+    ctx.symbolic()
+    Mass, C0, C1 = ctx.matrix(2), ctx.matrix(3), ctx.matrix(4)
+    dM, _ = csr_rel_diff(Mass.astype(complex), M_ref)
+    dC, _ = csr_rel_diff((C0 + 1j * beta * C1).tocsr(), C_ref)
+    assert dM < 1e-12 and dC < 1e-12
+
+
+# ----------------------------------------------------------------------------- K4: SpMV
+@pytest.mark.parametrize("cplx_eps,cplx_x", [(False, False), (False, True), (True, True), (True, False)])
+def test_spmv_matches_scipy(ctx, cplx_eps, cplx_x):
+    m, _ = strip_problem(12)
+    b = Basis(m, mode_element(2), intorder=4)
+    eps = _make_eps(m, 0, cplx_eps)
+    k0 = 2 * np.pi / 1.55
+    ctx.set_space(b)
+    ctx.symbolic()
+    ctx.assemble(0, eps, k0)
+    A = ctx.matrix(0)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(b.N) + (1j * rng.standard_normal(b.N) if cplx_x else 0)
+    y = ctx.spmv(0, x)
+    ref = A @ x
+    assert np.linalg.norm(y - ref) < 1e-13 * np.linalg.norm(ref)
+
+
+# ----------------------------------------------------------------------------- sparse LU
+@pytest.mark.parametrize("order,n,cplx,dirichlet,leaf", [(2, 12, False, False, 0), (2, 24, False, True, 16),
+                                                       (1, 30, False, False, 8), (2, 16, True, False, 0),
+                                                       (2, 40, False, False, 0)])
+def test_lu_solve_matches_scipy(ctx, order, n, cplx, dirichlet, leaf):
+    m, _ = strip_problem(n)
+    b = Basis(m, ElementTriP0(), intorder=4).with_element(mode_element(order))
+    eps = _make_eps(m, 0, cplx)
+    k0 = 2 * np.pi / 1.55
+    ctx.set_space(b)
+    ctx.symbolic()
+    ctx.assemble(0, eps, k0)
+    A, B = ctx.matrix(0), ctx.matrix(1)
+    sigma = k0**2 * np.max(eps.real) * 1.1
+    D = b.get_dofs(None) if dirichlet else None
+    ctx.lu_factor(sigma, D, leaf)
+    act = np.ones(b.N, dtype=bool)
+    if dirichlet:
+        act[D] = False
+    rng = np.random.default_rng(3)
+    for rhs_c in (False, True):
+        rhs = rng.standard_normal(b.N) + (1j * rng.standard_normal(b.N) if rhs_c else 0)
+        rhs = rhs * act
+        x = ctx.lu_solve(rhs)
+        I = np.nonzero(act)[0]
+        OP = (-A + sigma * B).tocsr()[I][:, I]
+        xs = spla.splu(OP.tocsc()).solve(rhs[I].astype(complex))
+        assert np.all(x[~act] == 0)
+        assert np.linalg.norm(OP @ x[I] - rhs[I]) < 1e-11 * np.linalg.norm(rhs)
+        assert np.linalg.norm(x[I] - xs) < 1e-9 * np.linalg.norm(xs)
+
+
+# ----------------------------------------------------------------------------- eigen-solve
+def _match(l_gpu, l_ref):
+    """pair eigenvalues by value"""
+    idx = [int(np.argmin(abs(l_ref - z))) for z in l_gpu]
+    assert sorted(idx) == list(range(len(l_ref))), (l_gpu, l_ref)
+    return idx
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_eigs_rectangle_known_answers_and_oracle(ctx, case):
+    """metallic boundaries; reference literature values (mode_solver_rectangle.py:45) and oracle parity."""
+    from femwell_b200.maxwell.waveguide import compute_modes
+
+    m, eps, bnd, fsel, ref = rectangle_problem(20, case)
+    b0 = Basis(m, ElementTriP0(), intorder=4)
+    modes = compute_modes(b0, eps, 1.5, num_modes=1, order=2, metallic_boundaries=bnd)
+    X, W = triangle_quadrature(4)
+    r = fo.compute_modes(m.p, m.t, 0, eps, 1.5, X, W, num_modes=1, order=2, dirichlet_facets=fsel, with_h=False)
+    assert abs(modes[0].n_eff - r.n_effs[0]) < 1e-9 * abs(r.n_effs[0])
+    assert abs(modes[0].n_eff.real - ref) < 5e-5
+
+
+@pytest.mark.parametrize("order,n,k,cplx", [(2, 16, 2, False), (1, 24, 3, False), (2, 14, 2, True), (2, 20, 6, False)])
+def test_compute_modes_matches_oracle(ctx, order, n, k, cplx):
+    from femwell_b200.maxwell.waveguide import calculate_overlap, compute_modes
+
+    m, eps = strip_problem(n)
+    if cplx:
+        eps = eps.astype(complex)
+        eps[m.subdomains["clad"]] -= 0.05j
+    b0 = Basis(m, ElementTriP0(), intorder=4)
+    modes = compute_modes(b0, eps, 1.55, num_modes=k, order=order)
+    b = modes[0].basis
+    v0 = np.random.default_rng(0).uniform(-1, 1, b.N)
+    r = fo.compute_modes(m.p, m.t, 0, eps, 1.55, b.X, b.W, num_modes=k, order=order, v0=v0)
+    idx = _match(np.array([md.k**2 for md in modes]), r.lams)
+    ed = b.element_dofs.astype(np.int64)
+    for i, md in enumerate(modes):
+        j = idx[i]
+        assert abs(md.n_eff - r.n_effs[j]) < 1e-9 * abs(r.n_effs[j]), (md.n_eff, r.n_effs[j])
+        # normalised overlap with the oracle's mode (phase-free): |<gpu, ref>| = 1 within 1e-6
+        ov = fo.calculate_overlap(m.p, m.t, ed, order, b.X, b.W, md.E, md.H, r.E[:, j], r.H[:, j])
+        assert abs(abs(ov) - 1) < 1e-6, ov
+        # power normalisation through the GPU functional
+        assert abs(md.calculate_power() - 1) < 1e-9
+        assert abs(calculate_overlap(b, md.E, md.H, b, md.E, md.H) - 1) < 1e-9
+    # modes come back nearest-to-sigma first
+    lam = np.array([md.k**2 for md in modes])
+    sig = modes.stats and (2 * np.pi / 1.55) ** 2 * np.max(eps) * 1.1
+    assert np.all(np.diff(abs(lam - sig)) >= -1e-9 * abs(sig))
+
+
+def test_golden_strip_modes(ctx):
+    from femwell_b200.maxwell.waveguide import compute_modes
+
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "strip_n16.json")))
+    m, eps = strip_problem(g["n"])
+    modes = compute_modes(Basis(m, ElementTriP0(), intorder=4), eps, g["wavelength"], num_modes=2, order=2)
+    for i in range(2):
+        assert abs(modes[i].n_eff.real - g["n_eff"][i][0]) < 1e-9 * g["n_eff"][i][0]
+        assert abs(modes[i].te_fraction - g["te_fraction"][i]) < 1e-6
+
+
+def test_bend_with_pml_complex_dgp1(ctx):
+    """config-3 style: DG-P1 complex eps with PML ramp, finite radius, n_guess (bent_waveguide.py:73-119)."""
+    from femwell_b200.maxwell.waveguide import compute_modes
+
+    m = __import__("femwell_b200.mesh", fromlist=["waveguide_mesh"]).waveguide_mesh(
+        14, slab_h=0.11, bbox=(-1.25, 4.25, -1.0, 1.22), extra_x=[2.25])
+    b0 = Basis(m, ElementDG(ElementTriP1()), intorder=4)
+    ne = m.nelements
+    base = np.full(ne, 1.0)
+    for name, nn in {"core": 3.48, "slab": 3.48, "box": 1.48, "clad": 1.0}.items():
+        base[m.subdomains[name]] = nn**2
+    eps = np.repeat(base, 3).astype(complex)
+    xv = m.p[0, m.t].T.reshape(-1)  # DG-P1 dof (e, a) sits on vertex a of element e
+    eps += -10j * np.maximum(0, xv - 2.25) ** 2
+    straight = compute_modes(b0, eps, 1.55, num_modes=1, order=2)
+    bent = compute_modes(b0, eps, 1.55, num_modes=1, order=2, radius=5.0, n_guess=straight[0].n_eff)
+    X, W = b0.X, b0.W
+    r = fo.compute_modes(m.p, m.t, 1, eps, 1.55, X, W, num_modes=1, order=2, radius=5.0,
+                         n_guess=straight[0].n_eff, with_h=False)
+    assert abs(bent[0].n_eff - r.n_effs[0]) < 1e-9 * abs(r.n_effs[0])
+    assert bent[0].n_eff.imag != 0
+
+
+# ----------------------------------------------------------------------------- post-processing
+def test_hfield_and_functionals_match_oracle(ctx):
+    from femwell_b200.maxwell.waveguide import calculate_hfield, compute_modes, speed_of_light
+
+    m, eps = strip_problem(14)
+    b0 = Basis(m, ElementTriP0(), intorder=4)
+    modes = compute_modes(b0, eps, 1.55, num_modes=2, order=2)
+    md, md2 = modes[0], modes[1]
+    b = md.basis
+    ed = b.element_dofs.astype(np.int64)
+    args = (m.p, m.t.astype(np.int64), ed, 2, b.X, b.W)
+    H_ref = fo.calculate_hfield(*args, md.E, md.k, md.k0 * speed_of_light, b.N)
+    H = calculate_hfield(b, md.E, md.k, md.k0 * speed_of_light)
+    assert np.linalg.norm(H - H_ref) < 1e-9 * np.linalg.norm(H_ref)
+    assert np.linalg.norm(md.H - H_ref) < 1e-9 * np.linalg.norm(H_ref)
+    assert abs(md.te_fraction - fo.te_fraction(*args, md.E)) < 1e-12
+    assert abs(md.transversality - fo.transversality(*args, md.E)) < 1e-12
+    for f in ("xy", "x", "y"):
+        ref = fo.effective_area(*args, md.E, f)
+        assert abs(md.calculate_effective_area(f) - ref) < 1e-10 * abs(ref)
+    ov_ref = fo.calculate_overlap(*args, md.E, md.H, md2.E, md2.H)
+    assert abs(md.calculate_overlap(md2) - ov_ref) < 1e-10
+    core = m.subdomains["core"]
+    p_ref = fo.calculate_overlap(*args, md.E, md.H, md.E, md.H, subset=core)
+    assert abs(md.calculate_power(elements="core") - p_ref) < 1e-10
+    assert 0.5 < md.calculate_power(elements="core").real < 1.0
+    deps = np.zeros(m.nelements)
+    deps[core] = 0.01
+    cc_ref = fo.coupling_coefficient(*args, md.E, md2.E, fo.interpolate_eps(0, deps, m.nelements, b.X))
+    cc = md.calculate_coupling_coefficient(md2, deps)
+    assert abs(cc - cc_ref) < 1e-10 * max(1.0, abs(cc_ref))
+    cf_ref = fo.confinement_factor(*args, md.E, fo.interpolate_eps(0, eps[core], core.size, b.X), core)
+    cf = md.calculate_confinement_factor("core")
+    assert abs(cf - cf_ref) < 1e-10 * abs(cf_ref)
+    assert abs(md.calculate_pertubated_neff(deps) - md.n_eff) > 0
+
+
+def test_argument_validation(ctx):
+    from femwell_b200.maxwell.waveguide import compute_modes
+
+    m, eps = strip_problem(6)
+    b0 = Basis(m, ElementTriP0())
+    with pytest.raises(ValueError):
+        compute_modes(b0, eps, 1.55, solver="scipy")
+    with pytest.raises(AssertionError):
+        compute_modes(b0, eps, 1.55, order=3)
+
+
+# ----------------------------------------------------------------------------- size-independent properties at larger size
+def test_large_assembly_properties(ctx):
+    """~180k triangles: linearity in eps, row-sum identities, spmv consistency (no oracle run)."""
+    m, eps = strip_problem(300)
+    b = Basis(m, mode_element(2), intorder=4)
+    k0 = 2 * np.pi / 1.55
+    ctx.set_space(b)
+    nnz = ctx.symbolic()
+    ctx.assemble(0, eps, k0)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(b.N)
+    y1 = ctx.spmv(1, x)
+    ctx.assemble(0, 2 * eps, k0)
+    y2 = ctx.spmv(1, x)
+    # B does not depend on eps
+    assert np.linalg.norm(y1 - y2) == 0
+    # mass matrix integrates the constant: sum over P-block of M = area
+    Mass = ctx.matrix(2)
+    zd = b.split_indices()[1]
+    one_z = np.zeros(b.N)
+    one_z[zd] = 1.0  # sum of all P2 shape functions == 1
+    area = (m.p[0].max() - m.p[0].min()) * (m.p[1].max() - m.p[1].min())
+    assert abs(one_z @ (Mass @ one_z) - area) < 1e-10 * area
+    assert abs(one_z @ ctx.spmv(2, one_z) - area) < 1e-10 * area
+    assert nnz >= Mass.nnz
