@@ -80,7 +80,8 @@ class Context:
         L.check(self.lib.fw_assemble_waveguide(self._h, eps_kind, int(cx), L.ptr(eps), C.c_double(k0),
                                                C.c_double(mu_r), C.c_double(radius)))
 
-    def matrix(self, which: int) -> sp.csr_matrix:
+    def matrix(self, which: int, eliminate_zeros: bool = True) -> sp.csr_matrix:
+        L.check(self.lib.fw_set_option(self._h, 0, int(eliminate_zeros)))
         nnz, cx = C.c_int64(), C.c_int32()
         L.check(self.lib.fw_matrix_nnz(self._h, which, C.byref(nnz), C.byref(cx)))
         indptr = np.empty(self.n + 1, dtype=np.int32)
@@ -118,10 +119,10 @@ class Context:
                                               0 if d is None else d.size, L.ptr(d), leaf_elements))
 
     def lu_solve(self, b: np.ndarray, refine: int = 1) -> np.ndarray:
-        cx = np.iscomplexobj(b)
-        bb = L.as_c128(b) if cx else L.as_f64(b)
+        # always complex across the ABI: the factors may be complex even for a real right-hand side
+        bb = L.as_c128(b)
         x = np.empty_like(bb)
-        L.check(self.lib.fw_lu_solve(self._h, int(cx), L.ptr(bb), L.ptr(x), refine))
+        L.check(self.lib.fw_lu_solve(self._h, 1, L.ptr(bb), L.ptr(x), refine))
         return x
 
     def _eigs_params(self, k, sigma, dirichlet, v0, ncv, tol, maxiter, refine, leaf_elements, keep):

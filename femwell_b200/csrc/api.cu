@@ -144,6 +144,19 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
   FW_API_END
 }
 
+int fw_set_option(fw_handle* hh, int32_t option, int32_t value) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh, "handle is NULL");
+  switch (option) {
+    case FW_OPT_ELIMINATE_ZEROS:
+      hh->h.eliminate_zeros = value != 0;
+      break;
+    default:
+      throw Error(FW_ERR_INVALID, "unknown option");
+  }
+  FW_API_END
+}
+
 int fw_symbolic(fw_handle* hh, int64_t* nnz) {
   FW_API_BEGIN
   FW_REQUIRE(hh, "handle is NULL");
@@ -510,6 +523,14 @@ int fw_debug_lu_symbolic_get(int32_t which, void* out) {
     case 21: cp64(S.blist_off); break;
     default: throw Error(FW_ERR_INVALID, "unknown array id");
   }
+  FW_API_END
+}
+
+int fw_debug_lu_get(fw_handle* hh, int32_t which, void* out) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && out, "NULL argument");
+  FW_CHECK_CUDA(cudaSetDevice(hh->h.device));
+  lu_debug_download(hh->h, which, out);
   FW_API_END
 }
 

@@ -44,6 +44,7 @@ struct Handle {
   Space sp;
   Pattern pat;
   bool has_symbolic = false;
+  bool eliminate_zeros = true;  // export semantics of scipy's coo.eliminate_zeros()
   Values A, B, Mass, C0, C1;
   DevBuf<double> blocks;  // scratch: local element blocks (SoA [entry][Ne])
   // generic COO->CSR result

@@ -58,5 +58,6 @@ void lu_factor(Handle& h, double alphaA_re, double alphaA_im, double alphaB_re, 
 // solve OP x = b for nrhs right-hand sides given in ORIGINAL dof order on the device
 // (b, x: [nrhs][n] of the LU scalar type; x[inactive] = 0).  b and x may alias.
 void lu_solve_dev(Handle& h, const void* b, void* x, int nrhs);
+void lu_debug_download(Handle& h, int which, void* out);
 
 }  // namespace fw

@@ -28,7 +28,7 @@ struct LUDevice {
   DevBuf<int> parent, child0, child1, m, ns, own_start;
   DevBuf<long long> front_off, work_off, blist_off;
   DevBuf<int> blist, rel, level_nodes;
-  DevBuf<int> piv;
+  DevBuf<int> piv, rowperm;
   DevBuf<double> factors, work, xperm;
   DevBuf<int> counters;
   DevBuf<uint8_t> active;
@@ -99,6 +99,7 @@ void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements
   up(d.level_nodes, S.level_nodes, s);
   d.active.upload(active.data(), active.size(), s);
   d.piv.alloc((size_t)std::max(1, S.n_active));
+  d.rowperm.alloc((size_t)std::max(1, S.n_active));
   d.counters.alloc(4);
   FW_CHECK_CUDA(cudaStreamSynchronize(s));
 }
@@ -393,6 +394,27 @@ __global__ void __launch_bounds__(256) k_lu_gemm(FrontTab T, const int* __restri
   }
 }
 
+// ------------------------------------------------------------------------------ composed row permutation
+// LAPACK-style sequential interchanges (row j <-> piv[j], j = 0..ns-1) composed once per front into a
+// gather: (P b)[i] = b[rowperm[i]].  The forward substitution needs P b up front because the L rows it
+// uses are in their final (fully interchanged) positions.
+__global__ void k_lu_compose_perm(FrontTab T, int n_nodes, const int* __restrict__ piv, int* __restrict__ rowperm) {
+  const int node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= n_nodes) return;
+  const int ns = T.ns[node], os = T.own_start[node];
+  int* rp = rowperm + os;
+  const int* pv = piv + os;
+  for (int i = 0; i < ns; ++i) rp[i] = i;
+  for (int j = 0; j < ns; ++j) {
+    const int p = pv[j];
+    if (p != j) {
+      const int tmp = rp[j];
+      rp[j] = rp[p];
+      rp[p] = tmp;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ factorisation driver
 template <class S>
 __global__ void k_absmax(const S* __restrict__ v, int64_t n, double* __restrict__ out) {
@@ -462,6 +484,8 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
       launches += 3;
     }
   }
+  k_lu_compose_perm<<<cdiv(Sy.n_nodes, 64), 64, 0, s>>>(T, Sy.n_nodes, d.piv.p, d.rowperm.p);
+  launches += 1;
   FW_CHECK_CUDA(cudaGetLastError());
   int cnt[4] = {0, 0, 0, 0};
   d.counters.download(cnt, 4, s);
@@ -507,9 +531,9 @@ constexpr int SOLVE_THREADS = 512;
 
 template <class S, int NRHS>
 __global__ void __launch_bounds__(SOLVE_THREADS) k_lu_forward(FrontTab T, const int* __restrict__ nodes,
-                                                              const S* __restrict__ F, const int* __restrict__ piv,
-                                                              S* __restrict__ work, int64_t work_stride,
-                                                              const S* __restrict__ xp, int na) {
+                                                              const S* __restrict__ F,
+                                                              const int* __restrict__ rowperm, S* __restrict__ work,
+                                                              int64_t work_stride, S* __restrict__ xp, int na) {
   __shared__ S D[PW][PW + 1];
   __shared__ S xs[NRHS][PW];
   const int node = nodes[blockIdx.x];
@@ -538,21 +562,22 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_lu_forward(FrontTab T, const 
     }
     __syncthreads();
   }
+  // row interchanges of the whole front first: stage the assembled own part in xp, gather it back
+  for (int i = t; i < ns; i += SOLVE_THREADS)
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) xp[(size_t)r * na + os + i] = w[r][i];
+  __syncthreads();
+  for (int i = t; i < ns; i += SOLVE_THREADS) {
+    const int src = rowperm[os + i];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) w[r][i] = xp[(size_t)r * na + os + src];
+  }
+  __syncthreads();
   for (int k0 = 0; k0 < ns; k0 += PW) {
     const int wd = min(PW, ns - k0);
     for (int idx = t; idx < wd * wd; idx += SOLVE_THREADS) {
       int r = idx % wd, c = idx / wd;
       D[r][c] = Fn[(k0 + r) + (long long)(k0 + c) * m];
-    }
-    if (t < NRHS) {
-      for (int j = 0; j < wd; ++j) {
-        const int p = piv[os + k0 + j];
-        if (p != k0 + j) {
-          S tmp = w[t][k0 + j];
-          w[t][k0 + j] = w[t][p];
-          w[t][p] = tmp;
-        }
-      }
     }
     __syncthreads();
     if (t < 32 * NRHS) {
@@ -682,7 +707,7 @@ static void solve_typed(Handle& h, const S* b, S* x) {
   if (na > 0) k_lu_permute_in<S><<<cdiv(na, 256), 256, 0, s>>>(na, d.perm.p, b, n, NRHS, xp);
   for (int lev = Sy.n_levels - 1; lev >= 0; --lev) {
     const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
-    k_lu_forward<S, NRHS><<<nfront, SOLVE_THREADS, 0, s>>>(T, d.level_nodes.p + Sy.level_start[lev], F, d.piv.p, work,
+    k_lu_forward<S, NRHS><<<nfront, SOLVE_THREADS, 0, s>>>(T, d.level_nodes.p + Sy.level_start[lev], F, d.rowperm.p, work,
                                                            Sy.work_entries, xp, na);
   }
   for (int lev = 0; lev < Sy.n_levels; ++lev) {
@@ -711,4 +736,20 @@ void lu_solve_dev(Handle& h, const void* b, void* x, int nrhs) {
   }
 }
 
+}  // namespace fw
+
+// ---- debug export (tests only): factor arena and pivot vector
+namespace fw {
+void lu_debug_download(Handle& h, int which, void* out) {
+  FW_REQUIRE(h.lu && h.lu->factored, "LU has not been factored");
+  LU& lu = *h.lu;
+  LUDevice& d = *lu.dev;
+  if (which == 0) {
+    size_t cnt = (size_t)lu.sym.factor_entries * (lu.is_complex ? 2 : 1);
+    d.factors.download((double*)out, cnt, h.stream);
+  } else {
+    d.piv.download((int*)out, (size_t)lu.sym.n_active, h.stream);
+  }
+  FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
+}
 }  // namespace fw

@@ -334,7 +334,7 @@ __global__ void k_segreduce(const uint32_t* __restrict__ seg, const uint32_t* __
   if (sidx >= nnz) return;
   uint32_t a = seg[sidx], b = seg[sidx + 1];
   S acc = scalar_traits<S>::zero();
-  bool nz = false;
+  bool nz = false, any = false;
   for (uint32_t i = a; i < b; ++i) {
     uint32_t src = perm[i];
     S v;
@@ -346,11 +346,13 @@ __global__ void k_segreduce(const uint32_t* __restrict__ seg, const uint32_t* __
     } else {
       v = vals[src];
     }
+    any = true;
     nz |= !is_zero_(v);
     acc = acc + v;
   }
   out[sidx] = acc;
-  flag[sidx] = nz ? 1 : 0;
+  // bit 0: structurally present, bit 1: at least one non-zero contribution (survives eliminate_zeros)
+  flag[sidx] = (any ? 1 : 0) | (nz ? 2 : 0);
 }
 
 template <class S>
@@ -367,17 +369,17 @@ template void reduce_onto_pattern<cplx>(const Pattern&, const cplx*, const int*,
                                         cudaStream_t);
 
 // ------------------------------------------------------------------------------ eliminate_zeros compaction
-__global__ void k_flag_to_u32(const uint8_t* __restrict__ f, int64_t n, uint32_t* __restrict__ out) {
+__global__ void k_flag_to_u32(const uint8_t* __restrict__ f, int64_t n, uint8_t mask, uint32_t* __restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = f[i];
+  if (i < n) out[i] = (f[i] & mask) ? 1u : 0u;
 }
 
 template <class S>
-__global__ void k_compact(const uint8_t* __restrict__ flag, const uint32_t* __restrict__ pos, int64_t nnz,
-                          const int* __restrict__ indices, const S* __restrict__ vals, int* __restrict__ oind,
-                          S* __restrict__ oval) {
+__global__ void k_compact(const uint8_t* __restrict__ flag, uint8_t mask, const uint32_t* __restrict__ pos,
+                          int64_t nnz, const int* __restrict__ indices, const S* __restrict__ vals,
+                          int* __restrict__ oind, S* __restrict__ oval) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nnz || !flag[i]) return;
+  if (i >= nnz || !(flag[i] & mask)) return;
   uint32_t p = pos[i];
   oind[p] = indices[i];
   oval[p] = vals[i];
@@ -398,14 +400,15 @@ int64_t count_kept(Handle& h, const Pattern& pat, Values& val) {
     return 0;
   }
   h.scan_tmp2.alloc((size_t)pat.nnz);
-  k_flag_to_u32<<<cdiv(pat.nnz, 256), 256, 0, s>>>(val.flag.p, pat.nnz, h.scan_tmp2.p);
+  const uint8_t mask = h.eliminate_zeros ? 2 : 1;
+  k_flag_to_u32<<<cdiv(pat.nnz, 256), 256, 0, s>>>(val.flag.p, pat.nnz, mask, h.scan_tmp2.p);
   exclusive_scan_u32(h.scan_tmp2.p, h.scan_tmp2.p, pat.nnz, h.scan_tmp, s);
   uint32_t last_scan = 0;
   uint8_t last_flag = 0;
   FW_CHECK_CUDA(cudaMemcpyAsync(&last_scan, h.scan_tmp2.p + (pat.nnz - 1), 4, cudaMemcpyDeviceToHost, s));
   FW_CHECK_CUDA(cudaMemcpyAsync(&last_flag, val.flag.p + (pat.nnz - 1), 1, cudaMemcpyDeviceToHost, s));
   FW_CHECK_CUDA(cudaStreamSynchronize(s));
-  val.nnz_kept = (int64_t)last_scan + last_flag;
+  val.nnz_kept = (int64_t)last_scan + ((last_flag & mask) ? 1 : 0);
   return val.nnz_kept;
 }
 
@@ -418,12 +421,13 @@ void export_compacted(Handle& h, const Pattern& pat, Values& val, int* indptr, i
   oind.alloc((size_t)(kept ? kept : 1));
   size_t w = val.is_complex ? 2 : 1;
   oval.alloc((size_t)(kept ? kept : 1) * w);
+  const uint8_t mask = h.eliminate_zeros ? 2 : 1;
   if (pat.nnz) {
     if (val.is_complex)
-      k_compact<cplx><<<cdiv(pat.nnz, 256), 256, 0, s>>>(val.flag.p, h.scan_tmp2.p, pat.nnz, pat.indices.p,
+      k_compact<cplx><<<cdiv(pat.nnz, 256), 256, 0, s>>>(val.flag.p, mask, h.scan_tmp2.p, pat.nnz, pat.indices.p,
                                                         (const cplx*)val.v.p, oind.p, (cplx*)oval.p);
     else
-      k_compact<double><<<cdiv(pat.nnz, 256), 256, 0, s>>>(val.flag.p, h.scan_tmp2.p, pat.nnz, pat.indices.p,
+      k_compact<double><<<cdiv(pat.nnz, 256), 256, 0, s>>>(val.flag.p, mask, h.scan_tmp2.p, pat.nnz, pat.indices.p,
                                                           val.v.p, oind.p, oval.p);
     k_compact_indptr<<<cdiv(pat.n + 1, 256), 256, 0, s>>>(pat.indptr.p, pat.n, h.scan_tmp2.p, pat.nnz, kept, oip.p);
   } else {
@@ -490,7 +494,7 @@ void coo_to_csr(Handle& h, int n_rows, int64_t n_entries, const int* rows, const
     reduce_onto_pattern<double>(h.coo_pat, dv.p, nullptr, 0, 1, val.v.p, val.flag.p, s);
   // every kept slot has at least one non-zero contribution by construction; a sum that cancels
   // to 0.0 stays as an explicit zero exactly like scipy's tocsr()
-  if (h.coo_pat.nnz) FW_CHECK_CUDA(cudaMemsetAsync(val.flag.p, 1, (size_t)h.coo_pat.nnz, s));
+  if (h.coo_pat.nnz) FW_CHECK_CUDA(cudaMemsetAsync(val.flag.p, 3, (size_t)h.coo_pat.nnz, s));
   val.valid = true;
   FW_CHECK_CUDA(cudaStreamSynchronize(s));
 }

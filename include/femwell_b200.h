@@ -60,6 +60,11 @@ int fw_version(void);
 int fw_create(fw_handle** out, int device);
 int fw_destroy(fw_handle* h);
 int fw_synchronize(fw_handle* h);
+/* FW_OPT_ELIMINATE_ZEROS (default 1): matrix export drops local contributions that are exactly 0.0
+ * like scikit-fem's COOData (coo_matrix.eliminate_zeros()); 0 exports the structural
+ * pattern (every (test dof, trial dof) pair of every element).                                   */
+enum { FW_OPT_ELIMINATE_ZEROS = 0 };
+int fw_set_option(fw_handle* h, int32_t option, int32_t value);
 
 /* ---- a1: mesh + FE space (waveguide.py:567-575; scikit-fem CellBasis) ------------ */
 typedef struct {
@@ -170,6 +175,8 @@ int fw_host_dense_eig(int32_t n, const double* a_c128_colmajor, double* w_c128, 
 int fw_debug_lu_symbolic(int32_t n, int32_t nb, int32_t ne, const int32_t* edofs, const double* cx,
                          const double* cy, const uint8_t* active, int32_t leaf_elements, int64_t* sizes8);
 int fw_debug_lu_symbolic_get(int32_t which, void* out);
+/* tests only: which = 0 factor arena (f64/c128, sum m^2 entries), 1 pivot vector (int32, n_active) */
+int fw_debug_lu_get(fw_handle* h, int32_t which, void* out);
 
 #ifdef __cplusplus
 }

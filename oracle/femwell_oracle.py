@@ -170,7 +170,7 @@ def interpolate_eps(eps_kind, epsilon_r, ne, X):
 
 
 # ----------------------------------------------------------------------------- assembly
-def _assemble(form, basis_fns, dofs, dxw, n, dtype):
+def _assemble(form, basis_fns, dofs, dxw, n, dtype, eliminate_zeros=True):
     """scikit-fem BilinearForm._assemble restated: data[j,i,:] =
     sum_q form(u_j, v_i) dx ; rows = test dofs, cols = trial dofs ; eliminate_zeros ; tocsr."""
     rows, cols, data = [], [], []
@@ -186,7 +186,8 @@ def _assemble(form, basis_fns, dofs, dxw, n, dtype):
     cols = np.concatenate(cols)
     data = np.concatenate(data)
     m = sp.coo_matrix((data, (rows, cols)), shape=(n, n))
-    m.eliminate_zeros()
+    if eliminate_zeros:
+        m.eliminate_zeros()
     return m.tocsr()
 
 
@@ -194,7 +195,8 @@ def _dot(a, b):
     return a[0] * b[0] + a[1] * b[1]
 
 
-def assemble_waveguide(p, t, dofs, order, X, W, eps_q, k0, mu_r=1.0, radius=np.inf, n=None, subset=None):
+def assemble_waveguide(p, t, dofs, order, X, W, eps_q, k0, mu_r=1.0, radius=np.inf, n=None, subset=None,
+                       eliminate_zeros=True):
     """A, B of waveguide.py:577-603 as canonical CSR."""
     if subset is not None:
         t = t[:, subset]
@@ -236,8 +238,8 @@ def assemble_waveguide(p, t, dofs, order, X, W, eps_q, k0, mu_r=1.0, radius=np.i
 
     if n is None:
         n = int(dofs.max()) + 1
-    A = _assemble(aform, fns, dofs, dxw, n, dtype)
-    B = _assemble(bform, fns, dofs, dxw, n, dtype)
+    A = _assemble(aform, fns, dofs, dxw, n, dtype, eliminate_zeros)
+    B = _assemble(bform, fns, dofs, dxw, n, dtype, eliminate_zeros)
     return A, B
 
 

@@ -30,10 +30,25 @@ def ctx():
     c.close()
 
 
-def _oracle_AB(m, b, eps_kind, eps, k0, mu_r=1.0, radius=np.inf):
+def _oracle_AB(m, b, eps_kind, eps, k0, mu_r=1.0, radius=np.inf, eliminate_zeros=True):
     order = b.elem.order
     return fo.assemble_waveguide(m.p, m.t.astype(np.int64), b.element_dofs.astype(np.int64), order, b.X, b.W,
-                                 fo.interpolate_eps(eps_kind, eps, m.nelements, b.X), k0, mu_r, radius, n=b.N)
+                                 fo.interpolate_eps(eps_kind, eps, m.nelements, b.X), k0, mu_r, radius, n=b.N,
+                                 eliminate_zeros=eliminate_zeros)
+
+
+def _pattern_diff_is_roundoff(M, R):
+    """eliminate_zeros makes the pattern depend on whether a mathematically-zero local integral rounds to
+    exactly 0.0: entries present in only one of the two matrices must be round-off zeros."""
+    scale = abs(R).max()
+    Mp, Rp = M.copy(), R.copy()
+    Mp.data = np.ones(Mp.nnz)
+    Rp.data = np.ones(Rp.nnz)
+    X = (Mp - Rp).tocoo()
+    sel = X.data != 0
+    vals = np.concatenate([np.abs(np.asarray(M[X.row[sel], X.col[sel]]).ravel()),
+                           np.abs(np.asarray(R[X.row[sel], X.col[sel]]).ravel())]) if sel.any() else np.zeros(0)
+    return bool((vals <= 1e-14 * scale).all()), int(sel.sum())
 
 
 # ----------------------------------------------------------------------------- K2: COO -> CSR
@@ -107,12 +122,25 @@ def test_assembly_matches_oracle(ctx, order, n, jitter, eps_kind, cplx, radius, 
     ctx.set_space(b)
     ctx.symbolic()
     ctx.assemble(eps_kind, eps, k0, 1.3, radius)
+    # (1) structural pattern (before eliminate_zeros): bit-exact integer parity
+    As, Bs = ctx.matrix(0, eliminate_zeros=False), ctx.matrix(1, eliminate_zeros=False)
+    As_ref, Bs_ref = _oracle_AB(m, b, eps_kind, eps, k0, 1.3, radius, eliminate_zeros=False)
+    for got, ref in ((As, As_ref), (Bs, Bs_ref)):
+        assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
+        assert abs(got - ref).max() < 1e-12 * abs(ref).max()
+    # (2) after eliminate_zeros: values to 1e-12; pattern equal up to round-off zeros
     A, B = ctx.matrix(0), ctx.matrix(1)
     assert A.dtype == A_ref.dtype and B.dtype == B_ref.dtype
     dA, sameA = csr_rel_diff(A, A_ref)
     dB, sameB = csr_rel_diff(B, B_ref)
-    assert sameA and sameB, "CSR sparsity pattern differs from the reference path"
     assert dA < 1e-12 and dB < 1e-12, (dA, dB)
+    okA, nA = _pattern_diff_is_roundoff(A, A_ref)
+    okB, nB = _pattern_diff_is_roundoff(B, B_ref)
+    assert okA and okB, "CSR sparsity pattern differs from the reference path beyond round-off zeros"
+    assert nA <= 0.02 * A_ref.nnz and nB <= 0.02 * B_ref.nnz
+    if jitter == 0.0:
+        # structured mesh: the oracle eliminates exact zeros; the GPU keeps them only as round-off
+        assert A_ref.nnz <= A.nnz <= As.nnz
 
 
 def test_assembly_golden_checksums(ctx):
@@ -123,7 +151,8 @@ def test_assembly_golden_checksums(ctx):
     ctx.symbolic()
     ctx.assemble(0, eps, 2 * np.pi / g["wavelength"])
     A, B = ctx.matrix(0), ctx.matrix(1)
-    assert A.nnz == g["nnzA"] and B.nnz == g["nnzB"]
+    # nnz after eliminate_zeros differs from the oracle's only by round-off zeros
+    assert 0 <= A.nnz - g["nnzA"] <= 0.01 * g["nnzA"] and 0 <= B.nnz - g["nnzB"] <= 0.01 * g["nnzB"]
     assert abs(abs(A).sum() - g["sumabsA"]) < 1e-11 * g["sumabsA"]
     assert abs(abs(B).sum() - g["sumabsB"]) < 1e-11 * g["sumabsB"]
 
@@ -186,7 +215,7 @@ def test_lu_solve_matches_scipy(ctx, order, n, cplx, dirichlet, leaf):
         x = ctx.lu_solve(rhs)
         I = np.nonzero(act)[0]
         OP = (-A + sigma * B).tocsr()[I][:, I]
-        xs = spla.splu(OP.tocsc()).solve(rhs[I].astype(complex))
+        xs = spla.splu(OP.tocsc().astype(complex)).solve(rhs[I].astype(complex))
         assert np.all(x[~act] == 0)
         assert np.linalg.norm(OP @ x[I] - rhs[I]) < 1e-11 * np.linalg.norm(rhs)
         assert np.linalg.norm(x[I] - xs) < 1e-9 * np.linalg.norm(xs)
@@ -229,12 +258,28 @@ def test_compute_modes_matches_oracle(ctx, order, n, k, cplx):
     r = fo.compute_modes(m.p, m.t, 0, eps, 1.55, b.X, b.W, num_modes=k, order=order, v0=v0)
     idx = _match(np.array([md.k**2 for md in modes]), r.lams)
     ed = b.element_dofs.astype(np.int64)
+    k0 = 2 * np.pi / 1.55
+    zd = b.split_indices()[1]
+
+    def eig_residual(E, lam):
+        x = np.array(E, dtype=complex)
+        x[zd] *= 1j * np.sqrt(lam / k0**4)  # back to the solved variable E_3 = i beta E_z
+        return np.linalg.norm(-(r.A @ x) + lam * (r.B @ x)) / np.linalg.norm(r.A @ x)
+
     for i, md in enumerate(modes):
         j = idx[i]
         assert abs(md.n_eff - r.n_effs[j]) < 1e-9 * abs(r.n_effs[j]), (md.n_eff, r.n_effs[j])
-        # normalised overlap with the oracle's mode (phase-free): |<gpu, ref>| = 1 within 1e-6
+        # the GPU eigenvector satisfies the oracle's pencil
+        assert eig_residual(md.E, md.k**2) < 1e-10
+        # normalised overlap with the oracle's mode (phase-free): |<gpu, ref>| = 1 within 1e-6.
+        # scipy/ARPACK returns vectors polluted by null(M) (the E_z block) for the last Ritz pairs --
+        # eigenvalue exact, eigen-residual O(1) -- so the field comparison is only meaningful where the
+        # oracle's own vector is an eigenvector.
         ov = fo.calculate_overlap(m.p, m.t, ed, order, b.X, b.W, md.E, md.H, r.E[:, j], r.H[:, j])
-        assert abs(abs(ov) - 1) < 1e-6, ov
+        res_ref = eig_residual(r.E[:, j], r.lams[j])
+        print("mode", i, "->", j, "n_eff", md.n_eff, r.n_effs[j], "overlap", ov, "oracle eig residual", res_ref)
+        if res_ref < 1e-9:
+            assert abs(abs(ov) - 1) < 1e-6, ov
         # power normalisation through the GPU functional
         assert abs(md.calculate_power() - 1) < 1e-9
         assert abs(calculate_overlap(b, md.E, md.H, b, md.E, md.H) - 1) < 1e-9
