@@ -60,7 +60,8 @@ class FwTimings(C.Structure):
     _fields_ = [
         ("upload_ms", c_f64), ("symbolic_ms", c_f64), ("element_kernel_ms", c_f64), ("reduce_ms", c_f64),
         ("lu_symbolic_ms", c_f64), ("lu_factor_ms", c_f64), ("arnoldi_ms", c_f64), ("postprocess_ms", c_f64),
-        ("total_ms", c_f64), ("element_kernel_launches", c_i64), ("kernel_launches", c_i64),
+        ("total_ms", c_f64), ("download_ms", c_f64), ("element_kernel_launches", c_i64),
+        ("kernel_launches", c_i64), ("nnz_structural", c_i64),
     ]
 
     def as_dict(self):

@@ -140,7 +140,7 @@ class Context:
         p.refine, p.leaf_elements = int(refine), int(leaf_elements)
         return p
 
-    def eigs(self, k, sigma, dirichlet=None, v0=None, ncv=0, tol=0.0, maxiter=0, refine=1, leaf_elements=0):
+    def eigs(self, k, sigma, dirichlet=None, v0=None, ncv=0, tol=0.0, maxiter=0, refine=0, leaf_elements=0):
         keep = []
         p = self._eigs_params(k, sigma, dirichlet, v0, ncv, tol, maxiter, refine, leaf_elements, keep)
         lams = np.empty(k, dtype=np.complex128)
@@ -183,7 +183,7 @@ class Context:
         return out
 
     def compute_modes(self, eps_kind, epsilon_r, wavelength, k, sigma, mu_r=1.0, radius=np.inf, dirichlet=None,
-                      v0=None, ncv=0, tol=0.0, maxiter=0, refine=1, leaf_elements=0, reuse_symbolic=False):
+                      v0=None, ncv=0, tol=0.0, maxiter=0, refine=0, leaf_elements=0, reuse_symbolic=False):
         keep = []
         cx = np.iscomplexobj(epsilon_r)
         eps = L.as_c128(epsilon_r) if cx else L.as_f64(epsilon_r)

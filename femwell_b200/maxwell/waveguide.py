@@ -225,8 +225,8 @@ def compute_modes(
     lams, E, H, powers, stats = ctx.compute_modes(
         eps_kind, epsilon_r, wavelength, num_modes, sigma, mu_r=float(mu_r), radius=float(radius),
         dirichlet=dirichlet, reuse_symbolic=reuse, **opts)
-    ctx.nnz_structural = ctx.nnz_structural or -1
     stats["timings"] = ctx.timings()
+    ctx.nnz_structural = stats["timings"]["nnz_structural"]
     return Modes(
         modes=[
             Mode(

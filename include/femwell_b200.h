@@ -119,7 +119,8 @@ typedef struct {
   int32_t n_dirichlet;
   const int32_t* dirichlet;
   const double* v0;
-  int32_t refine;       /* iterative-refinement steps per solve (default 1)        */
+  int32_t refine;       /* iterative-refinement steps per LU solve: 0 = none, retried with 1 if
+                           the returned pairs miss 1e-10; >0 fixed; <0 never            */
   int32_t leaf_elements;/* nested-dissection leaf size, 0: default                  */
 } fw_eigs_params;
 typedef struct {
@@ -164,8 +165,8 @@ int fw_compute_modes(fw_handle* h, const fw_modes_params* prm, double* lams, dou
 /* ---- timing of the most recent stages (ms, CUDA events on the handle's stream)        */
 typedef struct {
   double upload_ms, symbolic_ms, element_kernel_ms, reduce_ms, lu_symbolic_ms, lu_factor_ms,
-      arnoldi_ms, postprocess_ms, total_ms;
-  int64_t element_kernel_launches, kernel_launches;
+      arnoldi_ms, postprocess_ms, total_ms, download_ms;
+  int64_t element_kernel_launches, kernel_launches, nnz_structural;
 } fw_timings;
 int fw_get_timings(fw_handle* h, fw_timings* t);
 
