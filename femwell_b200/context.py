@@ -118,8 +118,13 @@ class Context:
         L.check(self.lib.fw_lu_factor_shifted(self._h, C.c_double(np.real(sigma)), C.c_double(np.imag(sigma)),
                                               0 if d is None else d.size, L.ptr(d), leaf_elements))
 
-    def lu_solve(self, b: np.ndarray, refine: int = 1) -> np.ndarray:
-        # always complex across the ABI: the factors may be complex even for a real right-hand side
+    def lu_solve(self, b: np.ndarray, refine: int = 1, force_real: bool = False) -> np.ndarray:
+        if force_real:  # real factors + real rhs: the single right-hand-side kernels
+            bb = L.as_f64(b)
+            x = np.empty_like(bb)
+            L.check(self.lib.fw_lu_solve(self._h, 0, L.ptr(bb), L.ptr(x), refine))
+            return x
+        # complex across the ABI: the factors may be complex even for a real right-hand side
         bb = L.as_c128(b)
         x = np.empty_like(bb)
         L.check(self.lib.fw_lu_solve(self._h, 1, L.ptr(bb), L.ptr(x), refine))

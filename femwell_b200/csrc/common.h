@@ -7,6 +7,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <ctime>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -186,6 +188,31 @@ struct Timer {
   ~Timer() {
     if (a) cudaEventDestroy(a);
     if (b) cudaEventDestroy(b);
+  }
+};
+
+// FW_TRACE=1: host wall-clock of the sub-stages (stream-synchronised), printed to stderr
+struct Trace {
+  cudaStream_t s;
+  double t0;
+  bool on;
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  }
+  explicit Trace(cudaStream_t st) : s(st), on(getenv("FW_TRACE") != nullptr) {
+    if (on) {
+      cudaStreamSynchronize(s);
+      t0 = now();
+    }
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    double t1 = now();
+    fprintf(stderr, "[fw-trace] %-28s %9.3f ms\n", what, t1 - t0);
+    t0 = t1;
   }
 };
 

@@ -71,8 +71,10 @@ void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements
     cx[e] = (sp.h_p[a] + sp.h_p[b] + sp.h_p[c]) / 3.0;
     cy[e] = (sp.h_p[sp.nv + a] + sp.h_p[sp.nv + b] + sp.h_p[sp.nv + c]) / 3.0;
   }
+  Trace tr(h.stream);
   lu_symbolic_build(lu.sym, sp.n, sp.nb, sp.ne, sp.h_edofs.data(), cx.data(), cy.data(), active.data(),
                     leaf_elements);
+  tr.mark("lu analyse: host symbolic");
   lu.dev.reset(new LUDevice());
   LUDevice& d = *lu.dev;
   const LUSymbolic& S = lu.sym;
@@ -102,6 +104,7 @@ void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements
   d.rowperm.alloc((size_t)std::max(1, S.n_active));
   d.counters.alloc(4);
   FW_CHECK_CUDA(cudaStreamSynchronize(s));
+  tr.mark("lu analyse: upload");
 }
 
 // ------------------------------------------------------------------------------ scatter of OP into fronts
@@ -153,12 +156,12 @@ __global__ void __launch_bounds__(256) k_lu_scatter(int n, const int* __restrict
 template <class S>
 __global__ void __launch_bounds__(256) k_lu_extend_add(FrontTab T, const int* __restrict__ nodes, int slot,
                                                        S* __restrict__ F) {
-  const int p = nodes[blockIdx.y];
+  const int p = nodes[blockIdx.x];
   const int c = slot ? T.child1[p] : T.child0[p];
   if (c < 0) return;
   const int mc = T.m[c], nsc = T.ns[c], nbc = mc - nsc;
   const int nt = (nbc + 31) >> 5;
-  const int tile = blockIdx.x;
+  const int tile = blockIdx.y;
   if (tile >= nt * nt) return;
   const int ti = tile % nt, tj = tile / nt;
   const int mp = T.m[p];
@@ -188,8 +191,9 @@ __global__ void __launch_bounds__(HWIN) k_lu_panel(FrontTab T, const int* __rest
   const int m = T.m[node], ns = T.ns[node];
   const int k0 = kstep * PW;
   if (k0 >= ns) return;
+  if (ns - k0 > HWIN) return;  // tall panels: k_lu_panel_tall (pivot search over all fully-summed rows)
   const int w = min(PW, ns - k0);
-  const int hw = min(HWIN, ns - k0);
+  const int hw = ns - k0;
   constexpr int LD = HWIN + 1;
   S* a = reinterpret_cast<S*>(smem_raw);              // a[c*LD + r]
   __shared__ double red_v[HWIN / 32];
@@ -245,6 +249,83 @@ __global__ void __launch_bounds__(HWIN) k_lu_panel(FrontTab T, const int* __rest
     if (t < hw) Fn[(k0 + t) + (long long)(k0 + c) * m] = a[c * LD + t];
 }
 
+// ------------------------------------------------------------------------------ tall panel kernel
+// Fronts whose remaining pivot block is taller than the shared-memory window: right-looking LU of the
+// (ns-k0) x 32 panel in global memory (L2 resident), partial pivoting over ALL fully-summed rows.
+// (A window restricted to 256 rows was measured to let the element growth reach 1e8-1e9 on the
+// 500k-triangle pencil; full partial pivoting keeps it at ~1e3-1e4.)
+constexpr int TALL_THREADS = 1024;
+template <class S>
+__global__ void __launch_bounds__(TALL_THREADS) k_lu_panel_tall(FrontTab T, const int* __restrict__ nodes, int kstep,
+                                                                S* __restrict__ F, int* __restrict__ piv, double thr,
+                                                                int* __restrict__ counters) {
+  __shared__ S prow[PW];
+  __shared__ double red_v[TALL_THREADS / 32];
+  __shared__ int red_i[TALL_THREADS / 32];
+  __shared__ int s_piv;
+  const int node = nodes[blockIdx.x];
+  const int m = T.m[node], ns = T.ns[node];
+  const int k0 = kstep * PW;
+  if (k0 >= ns) return;
+  const int h = ns - k0;
+  if (h <= HWIN) return;
+  const int w = min(PW, h);
+  S* P = F + T.front_off[node] + k0 + (long long)k0 * m;  // P[r + c*m]
+  const int t = threadIdx.x;
+  for (int j = 0; j < w; ++j) {
+    double v = -1.0;
+    int idx = 0x7fffffff;
+    for (int r = j + t; r < h; r += TALL_THREADS) {
+      const double a = abs1_(P[r + (long long)j * m]);
+      if (a > v) v = a, idx = r;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_down_sync(0xffffffffu, v, o);
+      int oi = __shfl_down_sync(0xffffffffu, idx, o);
+      if (ov > v || (ov == v && oi < idx)) v = ov, idx = oi;
+    }
+    if ((t & 31) == 0) red_v[t >> 5] = v, red_i[t >> 5] = idx;
+    __syncthreads();
+    if (t == 0) {
+      double bv = red_v[0];
+      int bi = red_i[0];
+      for (int q = 1; q < TALL_THREADS / 32; ++q)
+        if (red_v[q] > bv || (red_v[q] == bv && red_i[q] < bi)) bv = red_v[q], bi = red_i[q];
+      s_piv = bi;
+      piv[T.own_start[node] + k0 + j] = k0 + bi;
+      if (!(bv >= thr)) {
+        P[bi + (long long)j * m] = scalar_traits<S>::from(thr, 0.0);
+        atomicAdd(&counters[0], 1);
+      }
+    }
+    __syncthreads();
+    const int pr = s_piv;
+    if (t < w) {
+      S a = P[pr + (long long)t * m];
+      if (pr != j) {
+        const S b = P[j + (long long)t * m];
+        P[pr + (long long)t * m] = b;
+        P[j + (long long)t * m] = a;
+      }
+      prow[t] = a;  // the pivot row after the interchange
+    }
+    __syncthreads();
+    const S pivot = prow[j];
+    for (int r = j + 1 + t; r < h; r += TALL_THREADS) {
+      const S l = P[r + (long long)j * m] / pivot;
+      P[r + (long long)j * m] = l;
+      for (int c = j + 1; c < w; ++c) {
+        S* dst = P + r + (long long)c * m;
+        S x = *dst;
+        fnma_(x, l, prow[c]);
+        *dst = x;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------ swaps + TRSMs
 // blockIdx.x < ctiles : thread per column c outside the panel: row interchanges, and for c right of the
 //                       panel the unit-lower solve of the U row block.
@@ -254,14 +335,14 @@ __global__ void __launch_bounds__(128) k_lu_swap_trsm(FrontTab T, const int* __r
                                                       S* __restrict__ F, const int* __restrict__ piv, int ctiles) {
   __shared__ S D[PW][PW + 1];
   __shared__ int sp[PW];
-  const int node = nodes[blockIdx.y];
+  const int node = nodes[blockIdx.x];
   const int m = T.m[node], ns = T.ns[node];
   const int k0 = kstep * PW;
   if (k0 >= ns) return;
   const int w = min(PW, ns - k0);
-  const int hw = min(HWIN, ns - k0);
-  const bool col_role = (int)blockIdx.x < ctiles;
-  const int tile = col_role ? blockIdx.x : blockIdx.x - ctiles;
+  const int hw = ns - k0;  // every fully-summed row is handled by the panel kernels
+  const bool col_role = (int)blockIdx.y < ctiles;
+  const int tile = col_role ? blockIdx.y : blockIdx.y - ctiles;
   if (col_role ? (tile * 128 >= m) : (k0 + hw + tile * 128 >= m)) return;
   S* Fn = F + T.front_off[node];
   for (int idx = threadIdx.x; idx < w * w; idx += 128) {
@@ -333,7 +414,7 @@ __global__ void __launch_bounds__(256) k_lu_gemm(FrontTab T, const int* __restri
   constexpr int TM = 64, KC = GemmCfg<S>::KC;
   __shared__ S As[KC][TM];
   __shared__ S Bs[KC][TM + 1];
-  const int node = nodes[blockIdx.y];
+  const int node = nodes[blockIdx.x];
   const int m = T.m[node], ns = T.ns[node];
   const int k0 = kstep * PW;
   if (k0 >= ns) return;
@@ -342,7 +423,7 @@ __global__ void __launch_bounds__(256) k_lu_gemm(FrontTab T, const int* __restri
   const int nrem = m - r0;
   if (nrem <= 0) return;
   const int nt = (nrem + TM - 1) / TM;
-  const int tile = blockIdx.x;
+  const int tile = blockIdx.y;
   if (tile >= nt * nt) return;
   const int ti = tile % nt, tj = tile / nt;
   S* Fn = F + T.front_off[node];
@@ -434,8 +515,11 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
   const LUSymbolic& Sy = lu.sym;
   cudaStream_t s = h.stream;
   const size_t wsc = sizeof(S) / sizeof(double);
+  Trace tr(s);
   d.factors.alloc((size_t)std::max<int64_t>(1, Sy.factor_entries) * wsc);
+  tr.mark("lu factor: alloc");
   d.factors.zero(s, (size_t)Sy.factor_entries * wsc);
+  tr.mark("lu factor: memset");
   d.counters.zero(s);
   S* F = (S*)d.factors.p;
   FrontTab T = d.tab();
@@ -465,7 +549,7 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
       const int cnb = Sy.level_max_nb[lev + 1];
       const int nt = (cnb + 31) / 32;
       if (nt > 0) {
-        dim3 grid(nt * nt, nfront);
+        dim3 grid(nfront, nt * nt);
         k_lu_extend_add<S><<<grid, 256, 0, s>>>(T, nodes, 0, F);
         k_lu_extend_add<S><<<grid, 256, 0, s>>>(T, nodes, 1, F);
         launches += 2;
@@ -474,17 +558,21 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
     const int max_ns = Sy.level_max_ns[lev], max_m = Sy.level_max_m[lev];
     const int npan = (max_ns + PW - 1) / PW;
     for (int k = 0; k < npan; ++k) {
+      if (max_ns - k * PW > HWIN)
+        k_lu_panel_tall<S><<<nfront, TALL_THREADS, 0, s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
       k_lu_panel<S><<<nfront, HWIN, panel_smem, s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
       const int ctiles = (max_m + 127) / 128;
       const int rtiles = (max_m + 127) / 128;
-      k_lu_swap_trsm<S><<<dim3(ctiles + rtiles, nfront), 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles);
+      k_lu_swap_trsm<S><<<dim3(nfront, ctiles + rtiles), 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles);
       const int rem = max_m - (k * PW);  // upper bound of the trailing size
       const int nt = (rem + 63) / 64;
-      if (nt > 0) k_lu_gemm<S><<<dim3(nt * nt, nfront), 256, 0, s>>>(T, nodes, k, F);
+      if (nt > 0) k_lu_gemm<S><<<dim3(nfront, nt * nt), 256, 0, s>>>(T, nodes, k, F);
       launches += 3;
     }
   }
+  tr.mark("lu factor: levels");
   k_lu_compose_perm<<<cdiv(Sy.n_nodes, 64), 64, 0, s>>>(T, Sy.n_nodes, d.piv.p, d.rowperm.p);
+  tr.mark("lu factor: compose perm");
   launches += 1;
   FW_CHECK_CUDA(cudaGetLastError());
   int cnt[4] = {0, 0, 0, 0};
@@ -527,15 +615,34 @@ __global__ void k_lu_permute_out(int n, const int* __restrict__ iperm, const S* 
   for (int r = 0; r < nrhs; ++r) x[(size_t)r * n + i] = p >= 0 ? xp[(size_t)r * na + p] : scalar_traits<S>::zero();
 }
 
-constexpr int SOLVE_THREADS = 512;
+// Level-batched substitution, four kernels per tree level:
+//   forward : k_fwd_chain  (one CTA per front: assemble w from the rhs and the children, apply the row
+//                           permutation, unit-lower solve of the ns x ns pivot block, panel by panel)
+//             k_fwd_update (fronts x 128-row tiles: w_boundary -= L21 x1, the bulk of the L traffic)
+//   backward: k_bwd_update (fronts x 128-row tiles: gather x2 from the parent, y1 = w1 - U12 x2)
+//             k_bwd_chain  (one CTA per front: upper solve of the pivot block, write x)
+constexpr int SOLVE_MAX_THREADS = 512;
+constexpr int UPD_ROWS = 128;
+constexpr int UPD_CHUNK = 256;
+
+template <class S>
+__device__ inline S shfl_bcast_(S v, int src);
+template <>
+__device__ inline double shfl_bcast_<double>(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <>
+__device__ inline cplx shfl_bcast_<cplx>(cplx v, int src) {
+  return {__shfl_sync(0xffffffffu, v.re, src), __shfl_sync(0xffffffffu, v.im, src)};
+}
 
 template <class S, int NRHS>
-__global__ void __launch_bounds__(SOLVE_THREADS) k_lu_forward(FrontTab T, const int* __restrict__ nodes,
-                                                              const S* __restrict__ F,
-                                                              const int* __restrict__ rowperm, S* __restrict__ work,
-                                                              int64_t work_stride, S* __restrict__ xp, int na) {
+__global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_fwd_chain(FrontTab T, const int* __restrict__ nodes,
+                                                                 const S* __restrict__ F,
+                                                                 const int* __restrict__ rowperm,
+                                                                 S* __restrict__ work, int64_t work_stride,
+                                                                 S* __restrict__ xp, int na) {
   __shared__ S D[PW][PW + 1];
   __shared__ S xs[NRHS][PW];
+  const int nthr = blockDim.x;
   const int node = nodes[blockIdx.x];
   const int m = T.m[node], ns = T.ns[node], os = T.own_start[node];
   const S* Fn = F + T.front_off[node];
@@ -543,7 +650,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_lu_forward(FrontTab T, const 
 #pragma unroll
   for (int r = 0; r < NRHS; ++r) w[r] = work + (size_t)r * work_stride + T.work_off[node];
   const int t = threadIdx.x;
-  for (int i = t; i < m; i += SOLVE_THREADS)
+  for (int i = t; i < m; i += nthr)
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) w[r][i] = i < ns ? xp[(size_t)r * na + os + i] : scalar_traits<S>::zero();
   __syncthreads();
@@ -552,7 +659,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_lu_forward(FrontTab T, const 
     if (c < 0) continue;
     const int nsc = T.ns[c], nbc = T.m[c] - nsc;
     const int* rel = T.rel + T.blist_off[c];
-    for (int i = t; i < nbc; i += SOLVE_THREADS) {
+    for (int i = t; i < nbc; i += nthr) {
       const int ri = rel[i];
 #pragma unroll
       for (int r = 0; r < NRHS; ++r) {
@@ -562,12 +669,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_lu_forward(FrontTab T, const 
     }
     __syncthreads();
   }
+  if (ns == 0) return;
   // row interchanges of the whole front first: stage the assembled own part in xp, gather it back
-  for (int i = t; i < ns; i += SOLVE_THREADS)
+  for (int i = t; i < ns; i += nthr)
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) xp[(size_t)r * na + os + i] = w[r][i];
   __syncthreads();
-  for (int i = t; i < ns; i += SOLVE_THREADS) {
+  for (int i = t; i < ns; i += nthr) {
     const int src = rowperm[os + i];
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) w[r][i] = xp[(size_t)r * na + os + src];
@@ -575,7 +683,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_lu_forward(FrontTab T, const 
   __syncthreads();
   for (int k0 = 0; k0 < ns; k0 += PW) {
     const int wd = min(PW, ns - k0);
-    for (int idx = t; idx < wd * wd; idx += SOLVE_THREADS) {
+    for (int idx = t; idx < wd * wd; idx += nthr) {
       int r = idx % wd, c = idx / wd;
       D[r][c] = Fn[(k0 + r) + (long long)(k0 + c) * m];
     }
@@ -584,13 +692,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_lu_forward(FrontTab T, const 
       const int r = t >> 5, lane = t & 31;
       S x = lane < wd ? w[r][k0 + lane] : scalar_traits<S>::zero();
       for (int j = 0; j < wd; ++j) {
-        S xj;
-        if constexpr (scalar_traits<S>::is_complex) {
-          xj.re = __shfl_sync(0xffffffffu, x.re, j);
-          xj.im = __shfl_sync(0xffffffffu, x.im, j);
-        } else {
-          xj = __shfl_sync(0xffffffffu, x, j);
-        }
+        const S xj = shfl_bcast_<S>(x, j);
         if (lane > j && lane < wd) fnma_(x, D[lane][j], xj);
       }
       if (lane < wd) {
@@ -599,10 +701,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_lu_forward(FrontTab T, const 
       }
     }
     __syncthreads();
-    for (int row = k0 + wd + t; row < m; row += SOLVE_THREADS) {
+    // remaining own rows only; the boundary rows are updated by k_fwd_update
+    for (int row = k0 + wd + t; row < ns; row += nthr) {
       S acc[NRHS];
 #pragma unroll
       for (int r = 0; r < NRHS; ++r) acc[r] = w[r][row];
+#pragma unroll 8
       for (int j = 0; j < wd; ++j) {
         const S l = Fn[row + (long long)(k0 + j) * m];
 #pragma unroll
@@ -616,34 +720,123 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_lu_forward(FrontTab T, const 
 }
 
 template <class S, int NRHS>
-__global__ void __launch_bounds__(SOLVE_THREADS) k_lu_backward(FrontTab T, const int* __restrict__ nodes,
-                                                               const S* __restrict__ F, S* __restrict__ work,
-                                                               int64_t work_stride, S* __restrict__ xp, int na) {
-  constexpr int NG = SOLVE_THREADS / 32;
+__global__ void __launch_bounds__(UPD_ROWS) k_fwd_update(FrontTab T, const int* __restrict__ nodes,
+                                                         const S* __restrict__ F, S* __restrict__ work,
+                                                         int64_t work_stride) {
+  __shared__ S xs[NRHS][UPD_CHUNK];
+  const int node = nodes[blockIdx.x];
+  const int m = T.m[node], ns = T.ns[node];
+  const int nbd = m - ns;
+  const int r0 = blockIdx.y * UPD_ROWS;
+  if (r0 >= nbd || ns == 0) return;
+  const S* Fn = F + T.front_off[node];
+  S* w[NRHS];
+#pragma unroll
+  for (int r = 0; r < NRHS; ++r) w[r] = work + (size_t)r * work_stride + T.work_off[node];
+  const int t = threadIdx.x;
+  const int row = ns + r0 + t;
+  const bool valid = row < m;
+  S acc[NRHS];
+#pragma unroll
+  for (int r = 0; r < NRHS; ++r) acc[r] = scalar_traits<S>::zero();
+  for (int j0 = 0; j0 < ns; j0 += UPD_CHUNK) {
+    const int cn = min(UPD_CHUNK, ns - j0);
+    for (int j = t; j < cn; j += UPD_ROWS)
+#pragma unroll
+      for (int r = 0; r < NRHS; ++r) xs[r][j] = w[r][j0 + j];
+    __syncthreads();
+    if (valid) {
+      const S* col = Fn + row + (long long)j0 * m;
+#pragma unroll 8
+      for (int j = 0; j < cn; ++j) {
+        const S l = col[(long long)j * m];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) fnma_(acc[r], l, xs[r][j]);
+      }
+    }
+    __syncthreads();
+  }
+  if (valid)
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) w[r][row] = w[r][row] + acc[r];
+}
+
+template <class S, int NRHS>
+__global__ void __launch_bounds__(UPD_ROWS) k_bwd_update(FrontTab T, const int* __restrict__ nodes,
+                                                         const S* __restrict__ F, S* __restrict__ work,
+                                                         int64_t work_stride) {
+  __shared__ S xs[NRHS][UPD_CHUNK];
+  const int node = nodes[blockIdx.x];
+  const int m = T.m[node], ns = T.ns[node];
+  const int nbd = m - ns;
+  if (nbd == 0) return;  // root
+  const int r0 = blockIdx.y * UPD_ROWS;
+  if (r0 >= ns && blockIdx.y != 0) return;  // tile 0 always runs: it stores x2 for the children
+  const int p = T.parent[node];
+  const S* Fn = F + T.front_off[node];
+  const int* rel = T.rel + T.blist_off[node];
+  S* w[NRHS];
+  const S* wp[NRHS];
+#pragma unroll
+  for (int r = 0; r < NRHS; ++r) {
+    w[r] = work + (size_t)r * work_stride + T.work_off[node];
+    wp[r] = work + (size_t)r * work_stride + T.work_off[p];
+  }
+  const int t = threadIdx.x;
+  const int row = r0 + t;
+  const bool valid = row < ns;
+  S acc[NRHS];
+#pragma unroll
+  for (int r = 0; r < NRHS; ++r) acc[r] = scalar_traits<S>::zero();
+  for (int c0 = 0; c0 < nbd; c0 += UPD_CHUNK) {
+    const int cn = min(UPD_CHUNK, nbd - c0);
+    for (int c = t; c < cn; c += UPD_ROWS) {
+      const int ri = rel[c0 + c];
+#pragma unroll
+      for (int r = 0; r < NRHS; ++r) {
+        const S v = wp[r][ri];
+        xs[r][c] = v;
+        if (blockIdx.y == 0) w[r][ns + c0 + c] = v;
+      }
+    }
+    __syncthreads();
+    if (valid) {
+      const S* col = Fn + row + (long long)(ns + c0) * m;
+#pragma unroll 8
+      for (int c = 0; c < cn; ++c) {
+        const S u = col[(long long)c * m];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) fma_(acc[r], u, xs[r][c]);
+      }
+    }
+    __syncthreads();
+  }
+  if (valid)
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) w[r][row] = w[r][row] - acc[r];
+}
+
+template <class S, int NRHS>
+__global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_bwd_chain(FrontTab T, const int* __restrict__ nodes,
+                                                                 const S* __restrict__ F, S* __restrict__ work,
+                                                                 int64_t work_stride, S* __restrict__ xp, int na) {
+  constexpr int NGMAX = SOLVE_MAX_THREADS / 32;
   __shared__ S D[PW][PW + 1];
-  __shared__ S part[NRHS][NG][PW];
+  __shared__ S part[NRHS][NGMAX][PW];
+  const int nthr = blockDim.x, NG = nthr >> 5;
   const int node = nodes[blockIdx.x];
   const int m = T.m[node], ns = T.ns[node], os = T.own_start[node];
+  if (ns == 0) return;
   const S* Fn = F + T.front_off[node];
   S* w[NRHS];
 #pragma unroll
   for (int r = 0; r < NRHS; ++r) w[r] = work + (size_t)r * work_stride + T.work_off[node];
   const int t = threadIdx.x, lane = t & 31, g = t >> 5;
-  const int p = T.parent[node];
-  if (p >= 0) {
-    const int* rel = T.rel + T.blist_off[node];
-    for (int i = t; i < m - ns; i += SOLVE_THREADS) {
-      const int ri = rel[i];
-#pragma unroll
-      for (int r = 0; r < NRHS; ++r) w[r][ns + i] = (work + (size_t)r * work_stride + T.work_off[p])[ri];
-    }
-  }
-  __syncthreads();
   const int npan = (ns + PW - 1) / PW;
   for (int kp = npan - 1; kp >= 0; --kp) {
     const int k0 = kp * PW;
     const int wd = min(PW, ns - k0);
-    for (int idx = t; idx < wd * wd; idx += SOLVE_THREADS) {
+    for (int idx = t; idx < wd * wd; idx += nthr) {
       int r = idx % wd, c = idx / wd;
       D[r][c] = Fn[(k0 + r) + (long long)(k0 + c) * m];
     }
@@ -651,7 +844,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_lu_backward(FrontTab T, const
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) acc[r] = scalar_traits<S>::zero();
     if (lane < wd) {
-      for (int c = k0 + wd + g; c < m; c += NG) {
+      // own columns right of the panel (already final); boundary columns were folded in by k_bwd_update
+#pragma unroll 4
+      for (int c = k0 + wd + g; c < ns; c += NG) {
         const S u = Fn[(k0 + lane) + (long long)c * m];
 #pragma unroll
         for (int r = 0; r < NRHS; ++r) fma_(acc[r], u, w[r][c]);
@@ -673,21 +868,23 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_lu_backward(FrontTab T, const
           y = y / D[j][j];
           xj = y;
         }
-        if constexpr (scalar_traits<S>::is_complex) {
-          xj.re = __shfl_sync(0xffffffffu, xj.re, j);
-          xj.im = __shfl_sync(0xffffffffu, xj.im, j);
-        } else {
-          xj = __shfl_sync(0xffffffffu, xj, j);
-        }
+        xj = shfl_bcast_<S>(xj, j);
         if (lane < j) fnma_(y, D[lane][j], xj);
       }
       if (lane < wd) w[r][k0 + lane] = y;
     }
     __syncthreads();
   }
-  for (int i = t; i < ns; i += SOLVE_THREADS)
+  for (int i = t; i < ns; i += nthr)
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) xp[(size_t)r * na + os + i] = w[r][i];
+}
+
+static int chain_threads(int max_ns) {
+  if (max_ns <= 64) return 64;
+  if (max_ns <= 128) return 128;
+  if (max_ns <= 512) return 256;
+  return SOLVE_MAX_THREADS;
 }
 
 template <class S, int NRHS>
@@ -704,20 +901,44 @@ static void solve_typed(Handle& h, const S* b, S* x) {
   S* work = (S*)d.work.p;
   const S* F = (const S*)d.factors.p;
   FrontTab T = d.tab();
+  int64_t launches = 2;
+  const char* tenv = getenv("FW_TRACE");
+  const bool trace2 = tenv && atoi(tenv) >= 2;
+  Trace tr(s);
   if (na > 0) k_lu_permute_in<S><<<cdiv(na, 256), 256, 0, s>>>(na, d.perm.p, b, n, NRHS, xp);
   for (int lev = Sy.n_levels - 1; lev >= 0; --lev) {
     const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
-    k_lu_forward<S, NRHS><<<nfront, SOLVE_THREADS, 0, s>>>(T, d.level_nodes.p + Sy.level_start[lev], F, d.rowperm.p, work,
-                                                           Sy.work_entries, xp, na);
+    const int* nodes = d.level_nodes.p + Sy.level_start[lev];
+    const int thr = chain_threads(Sy.level_max_ns[lev]);
+    k_fwd_chain<S, NRHS><<<nfront, thr, 0, s>>>(T, nodes, F, d.rowperm.p, work, Sy.work_entries, xp, na);
+    if (trace2) tr.mark(("fwd chain  lev " + std::to_string(lev) + " fronts " + std::to_string(nfront) + " max_ns " +
+                         std::to_string(Sy.level_max_ns[lev])).c_str());
+    const int tiles = (Sy.level_max_nb[lev] + UPD_ROWS - 1) / UPD_ROWS;
+    if (tiles > 0) {
+      k_fwd_update<S, NRHS><<<dim3(nfront, tiles), UPD_ROWS, 0, s>>>(T, nodes, F, work, Sy.work_entries);
+      ++launches;
+      if (trace2) tr.mark(("fwd update lev " + std::to_string(lev) + " max_nb " +
+                           std::to_string(Sy.level_max_nb[lev])).c_str());
+    }
+    ++launches;
   }
   for (int lev = 0; lev < Sy.n_levels; ++lev) {
     const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
-    k_lu_backward<S, NRHS><<<nfront, SOLVE_THREADS, 0, s>>>(T, d.level_nodes.p + Sy.level_start[lev], F, work,
-                                                            Sy.work_entries, xp, na);
+    const int* nodes = d.level_nodes.p + Sy.level_start[lev];
+    const int thr = chain_threads(Sy.level_max_ns[lev]);
+    if (Sy.level_max_nb[lev] > 0) {
+      const int tiles = std::max(1, (Sy.level_max_ns[lev] + UPD_ROWS - 1) / UPD_ROWS);
+      k_bwd_update<S, NRHS><<<dim3(nfront, tiles), UPD_ROWS, 0, s>>>(T, nodes, F, work, Sy.work_entries);
+      ++launches;
+      if (trace2) tr.mark(("bwd update lev " + std::to_string(lev)).c_str());
+    }
+    k_bwd_chain<S, NRHS><<<nfront, thr, 0, s>>>(T, nodes, F, work, Sy.work_entries, xp, na);
+    ++launches;
+    if (trace2) tr.mark(("bwd chain  lev " + std::to_string(lev)).c_str());
   }
   k_lu_permute_out<S><<<cdiv(n, 256), 256, 0, s>>>(n, d.iperm.p, xp, na, NRHS, x);
   FW_CHECK_CUDA(cudaGetLastError());
-  h.tim.kernel_launches += 2 + 2 * Sy.n_levels;
+  h.tim.kernel_launches += launches;
 }
 
 void lu_solve_dev(Handle& h, const void* b, void* x, int nrhs) {

@@ -312,12 +312,20 @@ void symbolic_space(Handle& h) {
   int64_t n_coo = (int64_t)sp.nb * sp.nb * sp.ne;
   FW_REQUIRE(n_coo < (int64_t)0xffffffffll, "too many COO entries for 32-bit payload");
   int cb = bit_length(sp.n);
+  Trace tr(s);
   DevBuf<uint64_t> ka, kb;
   DevBuf<uint32_t> pa, pb, hist;
   ka.alloc((size_t)n_coo);
+  kb.alloc((size_t)n_coo);
+  pa.alloc((size_t)n_coo);
+  pb.alloc((size_t)n_coo);
+  tr.mark("symbolic: alloc");
   k_space_keys<<<cdiv(n_coo, 256), 256, 0, s>>>(sp.edofs.p, sp.ne, sp.nb, cb, ka.p);
+  tr.mark("symbolic: keys");
   radix_sort_pairs(ka, kb, pa, pb, n_coo, 2 * cb, true, hist, h.scan_tmp, s);
+  tr.mark("symbolic: radix sort");
   build_pattern_from_keys(h.pat, ka, pa, n_coo, sp.n, cb, h);
+  tr.mark("symbolic: pattern");
   h.has_symbolic = true;
   h.A.valid = h.B.valid = h.Mass.valid = h.C0.valid = h.C1.valid = false;
 }

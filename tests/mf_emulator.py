@@ -7,7 +7,7 @@ import numpy as np
 
 from femwell_b200 import _lib as L
 
-PW, HWIN = 32, 256
+PW, HWIN = 32, 1 << 30  # the GPU pivots over every fully-summed row of the front
 
 
 def lu_symbolic(n, edofs, cx, cy, active, leaf):
