@@ -378,9 +378,13 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
   int j0 = 0, restarts = 0, iterations = 0, nconv = 0, m_eff = m;
   bool done = false;
 
+  double tw_op = 0, tw_cgs = 0, tw_ritz = 0, tw_restart = 0;  // host wall-clock (FW_TRACE)
   while (!done) {
     for (int j = j0; j < m_eff; ++j) {
+      double tw0 = Trace::now();
       apply_op(Vb + (int64_t)j * ld, w);
+      double tw1 = Trace::now();
+      tw_op += tw1 - tw0;
       const int nvec = j + 1;
       T* h1 = (T*)W.hdev.p;
       T* h2 = h1 + MAXV;
@@ -415,8 +419,10 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
       }
       k_scale_copy<T><<<cdiv(n, 256), 256, 0, s>>>(w, Vb + (int64_t)(j + 1) * ld, n, 1.0 / beta);
       h.tim.kernel_launches += 1;
+      tw_cgs += Trace::now() - tw1;
     }
     // ---- Ritz pairs of the m_eff x m_eff projected matrix
+    const double tw2 = Trace::now();
     const int me = m_eff;
     for (int j = 0; j < me; ++j)
       for (int i = 0; i < me; ++i) Hm[(size_t)j * me + i] = Hat(i, j);
@@ -443,6 +449,8 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
       break;
     }
     // ---- thick restart: keep p Ritz directions, V <- V Q, H <- Q^H H Q, last row b^T Q
+    const double tw3 = Trace::now();
+    tw_ritz += tw3 - tw2;
     ++restarts;
     int p = std::min(me - 1, k + std::max(1, (me - k) / 2));
     std::vector<std::vector<cd>> basis;
@@ -531,7 +539,11 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
     FW_CHECK_CUDA(cudaStreamSynchronize(s));
     h.tim.kernel_launches += 1;
     j0 = p;
+    tw_restart += Trace::now() - tw3;
   }
+  if (getenv("FW_TRACE"))
+    fprintf(stderr, "[fw-trace] arnoldi host wall: op %.1f ms  cgs2 %.1f ms  ritz %.1f ms  restart %.1f ms\n", tw_op,
+            tw_cgs, tw_ritz, tw_restart);
 
   // ---- extract the k wanted Ritz pairs
   const int me = m_eff;

@@ -10,17 +10,27 @@
 // every term of every form is bilinear in the REFERENCE tables,
 //     a(u_j, v_i)|_q = vec_j(q) . alpha + sc_j(q) * beta,
 // where (alpha, beta) depend only on the test function i, the point q and per-element metric
-// tensors  G = A^-1 A^-T,  G_eps = A^-1 diag(eps_x, eps_y) A^-T  (A = affine Jacobian).  One thread
-// owns one triangle, keeps one row of the local block in registers, reads the reference tables as
-// warp-uniform constant-memory operands, and writes the row in SoA layout out[(i*NB+j)*Ne + e], so
-// every store instruction of a warp is one contiguous 256 B (f64) / 512 B (c128) segment.
+// tensors  G = A^-1 A^-T,  G_eps = A^-1 diag(eps_x, eps_y) A^-T  (A = affine Jacobian).
+//
+// Mapping: one thread per triangle; one launch per kind of test function (template KI: Nedelec rows /
+// Lagrange rows), so the structurally-zero terms of every (test kind, trial kind) pair vanish at
+// compile time and there is no divergence.  A warp covers 32 consecutive triangles.  The thread walks
+// the test functions of its kind and keeps one row of the local block (NB accumulators) in registers.
+// The quadrature loop and the trial loop are fully unrolled (NQ and NB are template parameters); the
+// reference tables are warp-uniform constant-bank loads which the compiler hoists out of the row loop
+// into registers (ncu of the first version showed short-scoreboard / MIO-throttle stalls: one LDC per
+// DFMA).  Stores are SoA, out[(i*NB+j)*Ne + e]: every store instruction of a warp is one contiguous
+// 256 B (f64) / 512 B (c128) segment.  The kernel sits at the FP64 ridge: the HBM-store floor and the
+// FP64-pipe floor are both ~0.16 ms at 500k triangles (profiles/).
 #include "handle.h"
 
 namespace fw {
 
+
 struct Tables {
   int nb, nq;
   int kind[MAXNB];
+  int rows[2][MAXNB];  // local dofs of kind 0 (Nedelec) / 1 (Lagrange), in ascending order
   double vx[MAXNB][MAXQ], vy[MAXNB][MAXQ], sc[MAXNB][MAXQ];
   double X[MAXQ], Y[MAXQ], W[MAXQ];
 };
@@ -32,8 +42,10 @@ void upload_tables(Handle& h) {
   memset(&t, 0, sizeof(t));
   t.nb = sp.nb;
   t.nq = sp.nq;
+  int cnt[2] = {0, 0};
   for (int l = 0; l < sp.nb; ++l) {
     t.kind[l] = sp.kind[l];
+    t.rows[sp.kind[l]][cnt[sp.kind[l]]++] = l;
     for (int q = 0; q < sp.nq; ++q) {
       t.vx[l][q] = sp.vec[((size_t)l * 2 + 0) * sp.nq + q];
       t.vy[l][q] = sp.vec[((size_t)l * 2 + 1) * sp.nq + q];
@@ -66,158 +78,242 @@ __host__ __device__ constexpr int nrank_of(int l) {
   return r;
 }
 
+// per-triangle state kept in registers
 template <class S>
-struct Vec2 {
-  S x, y;
+struct Elem {
+  double x0, a11, a12, adet, idet, g11, g12, g22, c_curl;
+  S e0, e1, e2, ge11, ge12, ge22;
 };
 
-template <int NB, class S, int EPSKIND, int FORM>
+// NQ > 0: compile-time number of quadrature points (loops fully unrolled); NQ == 0: run-time nq.
+// KI: kind of the test functions handled by this launch (0 = Nedelec rows, 1 = Lagrange rows).
+// EPT: triangles per thread (block b covers triangles [b*128*EPT, (b+1)*128*EPT)).
+template <int NB, int NQ, class S, int EPSKIND, int FORM, int KI, int EPT>
 __global__ void __launch_bounds__(128) k_element_blocks(int ne, int nv, const double* __restrict__ p,
                                                         const int* __restrict__ t, const S* __restrict__ eps,
                                                         double k0, double mu_r, double inv_radius,
                                                         S* __restrict__ out) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= ne) return;
   constexpr int NT = (NB == 6) ? 3 : 8;
   using T = scalar_traits<S>;
-  const int v0 = t[e], v1 = t[ne + e], v2 = t[2 * ne + e];
-  const double x0 = p[v0], y0 = p[nv + v0];
-  const double a11 = p[v1] - x0, a21 = p[nv + v1] - y0;
-  const double a12 = p[v2] - x0, a22 = p[nv + v2] - y0;
-  const double det = a11 * a22 - a12 * a21;
-  const double idet = 1.0 / det;
-  const double adet = fabs(det);
-  const double id2 = idet * idet;
-  // G = A^-1 A^-T (symmetric)
-  const double g11 = id2 * (a22 * a22 + a12 * a12);
-  const double g12 = -id2 * (a22 * a21 + a12 * a11);
-  const double g22 = id2 * (a21 * a21 + a11 * a11);
-  // epsilon degrees of freedom of this element
-  S e0 = T::zero(), e1 = T::zero(), e2 = T::zero();
-  if (FORM == FORM_A) {
-    if (EPSKIND == FW_EPS_P0) {
-      e0 = eps[e];
-    } else {
-      e0 = eps[3 * (size_t)e], e1 = eps[3 * (size_t)e + 1], e2 = eps[3 * (size_t)e + 2];
-    }
-  }
+  // blockIdx.y enumerates groups of `rpt` test functions of kind KI (the per-triangle prologue -- the
+  // dependent t -> p loads and the metric tensors -- is amortised over the rows of the group)
+  constexpr int NROWS = KI == 0 ? NT : NB - NT;
+  const int rpt = (NROWS + (int)gridDim.y - 1) / (int)gridDim.y;
   const double ik02 = 1.0 / (k0 * k0);
   const double imu = 1.0 / mu_r;
-  const int nq = c_tab.nq;
+  const bool bend = inv_radius != 0.0;  // warp-uniform: radius=inf makes the bend factor exactly 1
+  const int nq = NQ > 0 ? NQ : c_tab.nq;
 
-  for (int i = 0; i < NB; ++i) {
-    const int ki = c_tab.kind[i];
-    if (FORM == FORM_B && ki != 0) continue;  // only the tt block exists
-    S acc[NB];
+  int el[EPT];
+  Elem<S> E[EPT];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) acc[j] = T::zero();
-    for (int q = 0; q < nq; ++q) {
-      const double Xq = c_tab.X[q], Yq = c_tab.Y[q];
-      const double w = c_tab.W[q] * adet;
-      const double f = 1.0 + (x0 + a11 * Xq + a12 * Yq) * inv_radius;  // bend factor (waveguide.py:580-586)
-      const double vxi = c_tab.vx[i][q], vyi = c_tab.vy[i][q], sci = c_tab.sc[i][q];
+  for (int k = 0; k < EPT; ++k) {
+    const int e = (blockIdx.x * EPT + k) * 128 + threadIdx.x;
+    el[k] = e;
+    const int ec = e < ne ? e : ne - 1;  // out-of-range slots compute on a valid triangle, never store
+    const int v0 = t[ec], v1 = t[ne + ec], v2 = t[2 * ne + ec];
+    const double x0 = p[v0], y0 = p[nv + v0];
+    const double a11 = p[v1] - x0, a21 = p[nv + v1] - y0;
+    const double a12 = p[v2] - x0, a22 = p[nv + v2] - y0;
+    const double det = a11 * a22 - a12 * a21;
+    const double idet = 1.0 / det;
+    const double id2 = idet * idet;
+    Elem<S>& g = E[k];
+    g.x0 = x0, g.a11 = a11, g.a12 = a12;
+    g.adet = fabs(det), g.idet = idet;
+    // G = A^-1 A^-T (symmetric)
+    g.g11 = id2 * (a22 * a22 + a12 * a12);
+    g.g12 = -id2 * (a22 * a21 + a12 * a11);
+    g.g22 = id2 * (a21 * a21 + a11 * a11);
+    g.c_curl = imu * ik02 * id2;  // 1/(mu k0^2 det^2): curl-curl coefficient
+    g.e0 = g.e1 = g.e2 = g.ge11 = g.ge12 = g.ge22 = T::zero();
+    if (FORM == FORM_A) {
+      if (EPSKIND == FW_EPS_P0) {
+        g.e0 = eps[ec];
+      } else {
+        g.e0 = eps[3 * (size_t)ec], g.e1 = eps[3 * (size_t)ec + 1], g.e2 = eps[3 * (size_t)ec + 2];
+      }
+      if (EPSKIND == FW_EPS_VEC_P0) {
+        // G_eps = A^-1 diag(eps_x, eps_y) A^-T for diagonal anisotropy (constant per element)
+        g.ge11 = (g.e0 * (a22 * a22) + g.e1 * (a12 * a12)) * id2;
+        g.ge12 = (g.e0 * (a22 * a21) + g.e1 * (a12 * a11)) * (-id2);
+        g.ge22 = (g.e0 * (a21 * a21) + g.e1 * (a11 * a11)) * id2;
+      }
+    }
+  }
+
+  // which of (alpha, beta) are structurally non-zero for this (form, test kind)
+  constexpr bool useAN = (FORM == FORM_A) || (FORM == FORM_B) || (FORM == FORM_MASS && KI == 0) || (FORM == FORM_C1 && KI == 0);
+  constexpr bool useBN = (FORM == FORM_A && KI == 0) || (FORM == FORM_C0 && KI == 1);
+  constexpr bool useAP = (FORM == FORM_A && KI == 0) || (FORM == FORM_C0 && KI == 0);
+  constexpr bool useBP = (FORM == FORM_A && KI == 1) || (FORM == FORM_MASS && KI == 1);
+
+#pragma unroll 1
+  for (int rr = 0; rr < rpt; ++rr) {
+  const int irow = blockIdx.y * rpt + rr;  // rank of the test function among those of kind KI
+  if (irow >= NROWS) break;
+  const int i = c_tab.rows[KI][irow];
+  S acc[EPT][NB];
+#pragma unroll
+  for (int k = 0; k < EPT; ++k)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[k][j] = T::zero();
+
+#pragma unroll
+  for (int q = 0; q < (NQ > 0 ? NQ : MAXQ); ++q) {
+    if (NQ == 0 && q >= nq) break;
+    const double Xq = c_tab.X[q], Yq = c_tab.Y[q], Wq = c_tab.W[q];
+    const double vxi = c_tab.vx[i][q], vyi = c_tab.vy[i][q], sci = c_tab.sc[i][q];
+    S aNx[EPT], aNy[EPT], aPx[EPT], aPy[EPT], bN[EPT], bP[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+      const Elem<S>& g = E[k];
+      const double w = Wq * g.adet;
+      // bend factor f = 1 + x/R (waveguide.py:580-586); wf = w f, wrf = w / f
+      double wf = w, wrf = w;
+      if (bend) {
+        const double f = 1.0 + (g.x0 + g.a11 * Xq + g.a12 * Yq) * inv_radius;
+        wf = w * f;
+        wrf = w / f;
+      }
       // G v_i (geometry only)
-      const double gvx = g11 * vxi + g12 * vyi, gvy = g12 * vxi + g22 * vyi;
-      Vec2<S> aN{T::zero(), T::zero()}, aP{T::zero(), T::zero()};
-      S bN = T::zero(), bP = T::zero();
+      const double gvx = g.g11 * vxi + g.g12 * vyi, gvy = g.g12 * vxi + g.g22 * vyi;
+      aNx[k] = aNy[k] = aPx[k] = aPy[k] = bN[k] = bP[k] = T::zero();
       if (FORM == FORM_A) {
-        // epsilon at the point
-        S ex, ey, ez;
+        // G_eps v_i and eps_z at the point
+        S gex, gey, ez;
         if (EPSKIND == FW_EPS_P0) {
-          ex = ey = ez = e0;
+          gex = g.e0 * gvx, gey = g.e0 * gvy, ez = g.e0;
         } else if (EPSKIND == FW_EPS_DG_P1) {
-          ex = e0 * (1.0 - Xq - Yq) + e1 * Xq + e2 * Yq;
-          ey = ez = ex;
+          ez = g.e0 * (1.0 - Xq - Yq) + g.e1 * Xq + g.e2 * Yq;
+          gex = ez * gvx, gey = ez * gvy;
         } else {
-          ex = e0, ey = e1, ez = e2;
+          gex = g.ge11 * vxi + g.ge12 * vyi, gey = g.ge12 * vxi + g.ge22 * vyi, ez = g.e2;
         }
-        // G_eps v_i = A^-1 diag(ex,ey) A^-T v_i ;  A^-T v = idet*(a22 vx - a21 vy, -a12 vx + a11 vy)
-        const double tx = idet * (a22 * vxi - a21 * vyi), ty = idet * (-a12 * vxi + a11 * vyi);
-        const S sx = ex * tx, sy = ey * ty;
-        // A^-1 s = idet*(a22 sx - a12 sy, -a21 sx + a11 sy)
-        const S gex = (sx * a22 - sy * a12) * idet, gey = (sy * a11 - sx * a21) * idet;
-        if (ki == 0) {
+        if (KI == 0) {
           // test v_t: trial N -> curl curl / (mu_z k0^2) - eps_t e_t.v_t ; trial P -> grad e_z . v_t / mu_t
-          aN.x = gex * (-w * f), aN.y = gey * (-w * f);
-          bN = T::from(w * f * imu * ik02 * id2 * sci, 0.0);
-          aP.x = T::from(w * imu / f * gvx, 0.0), aP.y = T::from(w * imu / f * gvy, 0.0);
+          aNx[k] = gex * (-wf), aNy[k] = gey * (-wf);
+          bN[k] = T::from(wf * g.c_curl * sci, 0.0);
+          const double c = wrf * imu;
+          aPx[k] = T::from(c * gvx, 0.0), aPy[k] = T::from(c * gvy, 0.0);
         } else {
           // test v_z: trial N -> eps_t e_t . grad v_z ; trial P -> -eps_z e_z v_z k0^2
-          aN.x = gex * (w * f), aN.y = gey * (w * f);
-          bP = ez * (-w / f * k0 * k0 * sci);
+          aNx[k] = gex * wf, aNy[k] = gey * wf;
+          bP[k] = ez * (-wrf * k0 * k0 * sci);
         }
       } else if (FORM == FORM_B) {
-        const double c = -w * imu / f * ik02;
-        aN.x = T::from(c * gvx, 0.0), aN.y = T::from(c * gvy, 0.0);
+        const double c = -wrf * imu * ik02;
+        aNx[k] = T::from(c * gvx, 0.0), aNy[k] = T::from(c * gvy, 0.0);
       } else if (FORM == FORM_MASS) {
-        if (ki == 0) {
-          aN.x = T::from(w * gvx, 0.0), aN.y = T::from(w * gvy, 0.0);
+        if (KI == 0) {
+          aNx[k] = T::from(w * gvx, 0.0), aNy[k] = T::from(w * gvy, 0.0);
         } else {
-          bP = T::from(w * sci, 0.0);
+          bP[k] = T::from(w * sci, 0.0);
         }
       } else if (FORM == FORM_C1) {
         // i*beta * (e_x v_y - e_y v_x) = i*beta * idet * (u_hat x v_hat)
-        if (ki == 0) aN.x = T::from(w * idet * vyi, 0.0), aN.y = T::from(-w * idet * vxi, 0.0);
+        if (KI == 0) aNx[k] = T::from(w * g.idet * vyi, 0.0), aNy[k] = T::from(-w * g.idet * vxi, 0.0);
       } else {  // FORM_C0
-        if (ki == 0) {
+        if (KI == 0) {
           // d_y e_z v_x - d_x e_z v_y = -idet * (g_hat x v_hat)
-          aP.x = T::from(-w * idet * vyi, 0.0), aP.y = T::from(w * idet * vxi, 0.0);
+          aPx[k] = T::from(-w * g.idet * vyi, 0.0), aPy[k] = T::from(w * g.idet * vxi, 0.0);
         } else {
           // curl(e_t) v_z = idet * c_hat_j * psi_i
-          bN = T::from(w * idet * sci, 0.0);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        if (kind_of<NB>(j) == 0) {
-          fma_(acc[j], aN.x, c_tab.vx[j][q]);
-          fma_(acc[j], aN.y, c_tab.vy[j][q]);
-          fma_(acc[j], bN, c_tab.sc[j][q]);
-        } else {
-          fma_(acc[j], aP.x, c_tab.vx[j][q]);
-          fma_(acc[j], aP.y, c_tab.vy[j][q]);
-          fma_(acc[j], bP, c_tab.sc[j][q]);
+          bN[k] = T::from(w * g.idet * sci, 0.0);
         }
       }
     }
-    if (FORM == FORM_B) {
-      // compact NT x NT block: entry (rank(i), rank(j))
-      int ri = 0;
-      for (int m = 0; m < i; ++m) ri += (c_tab.kind[m] == 0);
 #pragma unroll
-      for (int j = 0; j < NB; ++j)
-        if (kind_of<NB>(j) == 0) out[(size_t)(ri * NT + nrank_of<NB>(j)) * ne + e] = acc[j];
-    } else {
+    for (int j = 0; j < NB; ++j) {
+      // one table fetch feeds EPT accumulators
+      const double tvx = c_tab.vx[j][q], tvy = c_tab.vy[j][q], tsc = c_tab.sc[j][q];
 #pragma unroll
-      for (int j = 0; j < NB; ++j) out[(size_t)(i * NB + j) * ne + e] = acc[j];
+      for (int k = 0; k < EPT; ++k) {
+        if (kind_of<NB>(j) == 0) {
+          if (useAN) {
+            fma_(acc[k][j], aNx[k], tvx);
+            fma_(acc[k][j], aNy[k], tvy);
+          }
+          if (useBN) fma_(acc[k][j], bN[k], tsc);
+        } else {
+          if (useAP) {
+            fma_(acc[k][j], aPx[k], tvx);
+            fma_(acc[k][j], aPy[k], tvy);
+          }
+          if (useBP) fma_(acc[k][j], bP[k], tsc);
+        }
+      }
     }
   }
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const int e = el[k];
+    if (e >= ne) continue;
+    if (FORM == FORM_B) {
+      // compact NT x NT block: entry (rank(i), rank(j))
+      const int ri = irow;
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (kind_of<NB>(j) == 0) out[(size_t)(ri * NT + nrank_of<NB>(j)) * ne + e] = acc[k][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) out[(size_t)(i * NB + j) * ne + e] = acc[k][j];
+    }
+  }
+  }  // rows of this thread
 }
 
-template <int NB, class S, int EPSKIND>
-static void launch_ab(Handle& h, const S* eps_dev, double k0, double mu_r, double inv_radius, S* blocksA,
-                      S* blocksB) {
+template <int NB, int NQ, class S, int EPSKIND, int FORM>
+static void launch_form(Handle& h, const S* eps_dev, double k0, double mu_r, double inv_radius, S* blocks) {
   const Space& sp = h.sp;
-  dim3 grid(cdiv(sp.ne, 128)), block(128);
-  k_element_blocks<NB, S, EPSKIND, FORM_A>
-      <<<grid, block, 0, h.stream>>>(sp.ne, sp.nv, sp.p.p, sp.t.p, eps_dev, k0, mu_r, inv_radius, blocksA);
-  k_element_blocks<NB, S, EPSKIND, FORM_B>
-      <<<grid, block, 0, h.stream>>>(sp.ne, sp.nv, sp.p.p, sp.t.p, eps_dev, k0, mu_r, inv_radius, blocksB);
+  constexpr int NT = (NB == 6) ? 3 : 8;
+  constexpr int EPT = 1;
+  dim3 block(128);
+  const int gx = cdiv(sp.ne, 128 * EPT);
+  // one launch per test-function kind: NT Nedelec rows, NB-NT Lagrange rows (bform has Nedelec rows only);
+  // grid.y = number of row groups (FW_K1_GROUPS, default 1: a thread walks all rows of its kind)
+  static const int groups = getenv("FW_K1_GROUPS") ? std::max(1, atoi(getenv("FW_K1_GROUPS"))) : 1;
+  const int gyN = std::min(groups, NT), gyP = std::min(groups, NB - NT);
+  k_element_blocks<NB, NQ, S, EPSKIND, FORM, 0, EPT><<<dim3(gx, gyN), block, 0, h.stream>>>(
+      sp.ne, sp.nv, sp.p.p, sp.t.p, eps_dev, k0, mu_r, inv_radius, blocks);
+  if (FORM != FORM_B)
+    k_element_blocks<NB, NQ, S, EPSKIND, FORM, 1, EPT><<<dim3(gx, gyP), block, 0, h.stream>>>(
+        sp.ne, sp.nv, sp.p.p, sp.t.p, eps_dev, k0, mu_r, inv_radius, blocks);
+}
+
+template <int NB, class S, int EPSKIND, int FORM>
+static void dispatch_nq(Handle& h, const S* eps_dev, double k0, double mu_r, double inv_radius, S* blocks) {
+  switch (h.sp.nq) {
+    case 3:
+      launch_form<NB, 3, S, EPSKIND, FORM>(h, eps_dev, k0, mu_r, inv_radius, blocks);
+      break;
+    case 6:
+      launch_form<NB, 6, S, EPSKIND, FORM>(h, eps_dev, k0, mu_r, inv_radius, blocks);
+      break;
+    case 7:
+      launch_form<NB, 7, S, EPSKIND, FORM>(h, eps_dev, k0, mu_r, inv_radius, blocks);
+      break;
+    case 12:
+      launch_form<NB, 12, S, EPSKIND, FORM>(h, eps_dev, k0, mu_r, inv_radius, blocks);
+      break;
+    default:
+      launch_form<NB, 0, S, EPSKIND, FORM>(h, eps_dev, k0, mu_r, inv_radius, blocks);
+  }
   FW_CHECK_CUDA(cudaGetLastError());
 }
 
-template <int NB, class S>
+template <int NB, class S, int FORM>
 static void dispatch_eps(Handle& h, int eps_kind, const S* eps_dev, double k0, double mu_r, double inv_radius,
-                         S* bA, S* bB) {
+                         S* blocks) {
   switch (eps_kind) {
     case FW_EPS_P0:
-      launch_ab<NB, S, FW_EPS_P0>(h, eps_dev, k0, mu_r, inv_radius, bA, bB);
+      dispatch_nq<NB, S, FW_EPS_P0, FORM>(h, eps_dev, k0, mu_r, inv_radius, blocks);
       break;
     case FW_EPS_DG_P1:
-      launch_ab<NB, S, FW_EPS_DG_P1>(h, eps_dev, k0, mu_r, inv_radius, bA, bB);
+      dispatch_nq<NB, S, FW_EPS_DG_P1, FORM>(h, eps_dev, k0, mu_r, inv_radius, blocks);
       break;
     case FW_EPS_VEC_P0:
-      launch_ab<NB, S, FW_EPS_VEC_P0>(h, eps_dev, k0, mu_r, inv_radius, bA, bB);
+      dispatch_nq<NB, S, FW_EPS_VEC_P0, FORM>(h, eps_dev, k0, mu_r, inv_radius, blocks);
       break;
     default:
       throw Error(FW_ERR_INVALID, "unknown eps_kind");
@@ -255,13 +351,16 @@ static void assemble_ab_typed(Handle& h, int eps_kind, const void* eps_host, dou
   upload_tables(h);
   {
     Timer tk(s);
-    if (sp.nb == 6)
-      dispatch_eps<6, S>(h, eps_kind, (const S*)eps_dev.p, k0, mu_r, inv_radius, bA, bB);
-    else
-      dispatch_eps<14, S>(h, eps_kind, (const S*)eps_dev.p, k0, mu_r, inv_radius, bA, bB);
+    if (sp.nb == 6) {
+      dispatch_eps<6, S, FORM_A>(h, eps_kind, (const S*)eps_dev.p, k0, mu_r, inv_radius, bA);
+      dispatch_nq<6, S, FW_EPS_P0, FORM_B>(h, (const S*)eps_dev.p, k0, mu_r, inv_radius, bB);
+    } else {
+      dispatch_eps<14, S, FORM_A>(h, eps_kind, (const S*)eps_dev.p, k0, mu_r, inv_radius, bA);
+      dispatch_nq<14, S, FW_EPS_P0, FORM_B>(h, (const S*)eps_dev.p, k0, mu_r, inv_radius, bB);
+    }
     h.tim.element_kernel_ms = tk.stop();
-    h.tim.element_kernel_launches = 2;
-    h.tim.kernel_launches += 2;
+    h.tim.element_kernel_launches = 3;  // aform: Nedelec rows + Lagrange rows; bform: Nedelec rows
+    h.tim.kernel_launches += 3;
   }
   // segmented reduce onto the structural pattern
   std::vector<int> lut;
@@ -305,27 +404,25 @@ void assemble_aux(Handle& h) {
   const size_t nA = (size_t)sp.nb * sp.nb * sp.ne;
   h.blocks.alloc(nA);
   upload_tables(h);
-  dim3 grid(cdiv(sp.ne, 128)), block(128);
   const Pattern& pat = h.pat;
   Values* vals[3] = {&h.Mass, &h.C0, &h.C1};
   for (int f = 0; f < 3; ++f) {
     double* b = h.blocks.p;
     if (sp.nb == 6) {
       if (f == 0)
-        k_element_blocks<6, double, FW_EPS_P0, FORM_MASS><<<grid, block, 0, s>>>(sp.ne, sp.nv, sp.p.p, sp.t.p, nullptr, 1.0, 1.0, 0.0, b);
+        dispatch_nq<6, double, FW_EPS_P0, FORM_MASS>(h, nullptr, 1.0, 1.0, 0.0, b);
       else if (f == 1)
-        k_element_blocks<6, double, FW_EPS_P0, FORM_C0><<<grid, block, 0, s>>>(sp.ne, sp.nv, sp.p.p, sp.t.p, nullptr, 1.0, 1.0, 0.0, b);
+        dispatch_nq<6, double, FW_EPS_P0, FORM_C0>(h, nullptr, 1.0, 1.0, 0.0, b);
       else
-        k_element_blocks<6, double, FW_EPS_P0, FORM_C1><<<grid, block, 0, s>>>(sp.ne, sp.nv, sp.p.p, sp.t.p, nullptr, 1.0, 1.0, 0.0, b);
+        dispatch_nq<6, double, FW_EPS_P0, FORM_C1>(h, nullptr, 1.0, 1.0, 0.0, b);
     } else {
       if (f == 0)
-        k_element_blocks<14, double, FW_EPS_P0, FORM_MASS><<<grid, block, 0, s>>>(sp.ne, sp.nv, sp.p.p, sp.t.p, nullptr, 1.0, 1.0, 0.0, b);
+        dispatch_nq<14, double, FW_EPS_P0, FORM_MASS>(h, nullptr, 1.0, 1.0, 0.0, b);
       else if (f == 1)
-        k_element_blocks<14, double, FW_EPS_P0, FORM_C0><<<grid, block, 0, s>>>(sp.ne, sp.nv, sp.p.p, sp.t.p, nullptr, 1.0, 1.0, 0.0, b);
+        dispatch_nq<14, double, FW_EPS_P0, FORM_C0>(h, nullptr, 1.0, 1.0, 0.0, b);
       else
-        k_element_blocks<14, double, FW_EPS_P0, FORM_C1><<<grid, block, 0, s>>>(sp.ne, sp.nv, sp.p.p, sp.t.p, nullptr, 1.0, 1.0, 0.0, b);
+        dispatch_nq<14, double, FW_EPS_P0, FORM_C1>(h, nullptr, 1.0, 1.0, 0.0, b);
     }
-    FW_CHECK_CUDA(cudaGetLastError());
     Values& v = *vals[f];
     v.is_complex = false;
     v.v.alloc((size_t)pat.nnz);
@@ -333,7 +430,7 @@ void assemble_aux(Handle& h) {
     v.nnz_kept = -1;
     reduce_onto_pattern<double>(pat, b, nullptr, 0, sp.ne, v.v.p, v.flag.p, s);
     v.valid = true;
-    h.tim.kernel_launches += 2;
+    h.tim.kernel_launches += 3;
   }
 }
 

@@ -12,31 +12,9 @@
 
 #include "lu.h"
 
+#include "lu_dev.h"
+
 namespace fw {
-
-constexpr int PW = 32;    // panel width
-constexpr int HWIN = 256; // pivot window height (rows eligible as pivots per panel)
-
-struct FrontTab {
-  const int *m, *ns, *own_start, *parent, *child0, *child1;
-  const long long *front_off, *work_off, *blist_off;
-  const int *blist, *rel;
-};
-
-struct LUDevice {
-  DevBuf<int> iperm, perm, node_of;
-  DevBuf<int> parent, child0, child1, m, ns, own_start;
-  DevBuf<long long> front_off, work_off, blist_off;
-  DevBuf<int> blist, rel, level_nodes;
-  DevBuf<int> piv, rowperm;
-  DevBuf<double> factors, work, xperm;
-  DevBuf<int> counters;
-  DevBuf<uint8_t> active;
-  FrontTab tab() const {
-    return FrontTab{m.p, ns.p, own_start.p, parent.p, child0.p, child1.p, front_off.p, work_off.p, blist_off.p,
-                    blist.p, rel.p};
-  }
-};
 
 LU::LU() {}
 LU::~LU() {}
@@ -598,369 +576,7 @@ void lu_factor(Handle& h, double aAr, double aAi, double aBr, double aBi, bool c
     factor_typed<cplx, cplx>(h, cplx{aAr, aAi}, cplx{aBr, aBi});
 }
 
-// ------------------------------------------------------------------------------ triangular solves
-template <class S>
-__global__ void k_lu_permute_in(int na, const int* __restrict__ perm, const S* __restrict__ b, int n, int nrhs,
-                                S* __restrict__ xp) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= na) return;
-  for (int r = 0; r < nrhs; ++r) xp[(size_t)r * na + i] = b[(size_t)r * n + perm[i]];
-}
-template <class S>
-__global__ void k_lu_permute_out(int n, const int* __restrict__ iperm, const S* __restrict__ xp, int na, int nrhs,
-                                 S* __restrict__ x) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int p = iperm[i];
-  for (int r = 0; r < nrhs; ++r) x[(size_t)r * n + i] = p >= 0 ? xp[(size_t)r * na + p] : scalar_traits<S>::zero();
-}
-
-// Level-batched substitution, four kernels per tree level:
-//   forward : k_fwd_chain  (one CTA per front: assemble w from the rhs and the children, apply the row
-//                           permutation, unit-lower solve of the ns x ns pivot block, panel by panel)
-//             k_fwd_update (fronts x 128-row tiles: w_boundary -= L21 x1, the bulk of the L traffic)
-//   backward: k_bwd_update (fronts x 128-row tiles: gather x2 from the parent, y1 = w1 - U12 x2)
-//             k_bwd_chain  (one CTA per front: upper solve of the pivot block, write x)
-constexpr int SOLVE_MAX_THREADS = 512;
-constexpr int UPD_ROWS = 128;
-constexpr int UPD_CHUNK = 256;
-
-template <class S>
-__device__ inline S shfl_bcast_(S v, int src);
-template <>
-__device__ inline double shfl_bcast_<double>(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-template <>
-__device__ inline cplx shfl_bcast_<cplx>(cplx v, int src) {
-  return {__shfl_sync(0xffffffffu, v.re, src), __shfl_sync(0xffffffffu, v.im, src)};
-}
-
-template <class S, int NRHS>
-__global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_fwd_chain(FrontTab T, const int* __restrict__ nodes,
-                                                                 const S* __restrict__ F,
-                                                                 const int* __restrict__ rowperm,
-                                                                 S* __restrict__ work, int64_t work_stride,
-                                                                 S* __restrict__ xp, int na) {
-  __shared__ S D[PW][PW + 1];
-  __shared__ S xs[NRHS][PW];
-  const int nthr = blockDim.x;
-  const int node = nodes[blockIdx.x];
-  const int m = T.m[node], ns = T.ns[node], os = T.own_start[node];
-  const S* Fn = F + T.front_off[node];
-  S* w[NRHS];
-#pragma unroll
-  for (int r = 0; r < NRHS; ++r) w[r] = work + (size_t)r * work_stride + T.work_off[node];
-  const int t = threadIdx.x;
-  for (int i = t; i < m; i += nthr)
-#pragma unroll
-    for (int r = 0; r < NRHS; ++r) w[r][i] = i < ns ? xp[(size_t)r * na + os + i] : scalar_traits<S>::zero();
-  __syncthreads();
-  for (int sl = 0; sl < 2; ++sl) {
-    const int c = sl ? T.child1[node] : T.child0[node];
-    if (c < 0) continue;
-    const int nsc = T.ns[c], nbc = T.m[c] - nsc;
-    const int* rel = T.rel + T.blist_off[c];
-    for (int i = t; i < nbc; i += nthr) {
-      const int ri = rel[i];
-#pragma unroll
-      for (int r = 0; r < NRHS; ++r) {
-        const S* wc = work + (size_t)r * work_stride + T.work_off[c];
-        w[r][ri] = w[r][ri] + wc[nsc + i];
-      }
-    }
-    __syncthreads();
-  }
-  if (ns == 0) return;
-  // row interchanges of the whole front first: stage the assembled own part in xp, gather it back
-  for (int i = t; i < ns; i += nthr)
-#pragma unroll
-    for (int r = 0; r < NRHS; ++r) xp[(size_t)r * na + os + i] = w[r][i];
-  __syncthreads();
-  for (int i = t; i < ns; i += nthr) {
-    const int src = rowperm[os + i];
-#pragma unroll
-    for (int r = 0; r < NRHS; ++r) w[r][i] = xp[(size_t)r * na + os + src];
-  }
-  __syncthreads();
-  for (int k0 = 0; k0 < ns; k0 += PW) {
-    const int wd = min(PW, ns - k0);
-    for (int idx = t; idx < wd * wd; idx += nthr) {
-      int r = idx % wd, c = idx / wd;
-      D[r][c] = Fn[(k0 + r) + (long long)(k0 + c) * m];
-    }
-    __syncthreads();
-    if (t < 32 * NRHS) {
-      const int r = t >> 5, lane = t & 31;
-      S x = lane < wd ? w[r][k0 + lane] : scalar_traits<S>::zero();
-      for (int j = 0; j < wd; ++j) {
-        const S xj = shfl_bcast_<S>(x, j);
-        if (lane > j && lane < wd) fnma_(x, D[lane][j], xj);
-      }
-      if (lane < wd) {
-        w[r][k0 + lane] = x;
-        xs[r][lane] = x;
-      }
-    }
-    __syncthreads();
-    // remaining own rows only; the boundary rows are updated by k_fwd_update
-    for (int row = k0 + wd + t; row < ns; row += nthr) {
-      S acc[NRHS];
-#pragma unroll
-      for (int r = 0; r < NRHS; ++r) acc[r] = w[r][row];
-#pragma unroll 8
-      for (int j = 0; j < wd; ++j) {
-        const S l = Fn[row + (long long)(k0 + j) * m];
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) fnma_(acc[r], l, xs[r][j]);
-      }
-#pragma unroll
-      for (int r = 0; r < NRHS; ++r) w[r][row] = acc[r];
-    }
-    __syncthreads();
-  }
-}
-
-template <class S, int NRHS>
-__global__ void __launch_bounds__(UPD_ROWS) k_fwd_update(FrontTab T, const int* __restrict__ nodes,
-                                                         const S* __restrict__ F, S* __restrict__ work,
-                                                         int64_t work_stride) {
-  __shared__ S xs[NRHS][UPD_CHUNK];
-  const int node = nodes[blockIdx.x];
-  const int m = T.m[node], ns = T.ns[node];
-  const int nbd = m - ns;
-  const int r0 = blockIdx.y * UPD_ROWS;
-  if (r0 >= nbd || ns == 0) return;
-  const S* Fn = F + T.front_off[node];
-  S* w[NRHS];
-#pragma unroll
-  for (int r = 0; r < NRHS; ++r) w[r] = work + (size_t)r * work_stride + T.work_off[node];
-  const int t = threadIdx.x;
-  const int row = ns + r0 + t;
-  const bool valid = row < m;
-  S acc[NRHS];
-#pragma unroll
-  for (int r = 0; r < NRHS; ++r) acc[r] = scalar_traits<S>::zero();
-  for (int j0 = 0; j0 < ns; j0 += UPD_CHUNK) {
-    const int cn = min(UPD_CHUNK, ns - j0);
-    for (int j = t; j < cn; j += UPD_ROWS)
-#pragma unroll
-      for (int r = 0; r < NRHS; ++r) xs[r][j] = w[r][j0 + j];
-    __syncthreads();
-    if (valid) {
-      const S* col = Fn + row + (long long)j0 * m;
-#pragma unroll 8
-      for (int j = 0; j < cn; ++j) {
-        const S l = col[(long long)j * m];
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) fnma_(acc[r], l, xs[r][j]);
-      }
-    }
-    __syncthreads();
-  }
-  if (valid)
-#pragma unroll
-    for (int r = 0; r < NRHS; ++r) w[r][row] = w[r][row] + acc[r];
-}
-
-template <class S, int NRHS>
-__global__ void __launch_bounds__(UPD_ROWS) k_bwd_update(FrontTab T, const int* __restrict__ nodes,
-                                                         const S* __restrict__ F, S* __restrict__ work,
-                                                         int64_t work_stride) {
-  __shared__ S xs[NRHS][UPD_CHUNK];
-  const int node = nodes[blockIdx.x];
-  const int m = T.m[node], ns = T.ns[node];
-  const int nbd = m - ns;
-  if (nbd == 0) return;  // root
-  const int r0 = blockIdx.y * UPD_ROWS;
-  if (r0 >= ns && blockIdx.y != 0) return;  // tile 0 always runs: it stores x2 for the children
-  const int p = T.parent[node];
-  const S* Fn = F + T.front_off[node];
-  const int* rel = T.rel + T.blist_off[node];
-  S* w[NRHS];
-  const S* wp[NRHS];
-#pragma unroll
-  for (int r = 0; r < NRHS; ++r) {
-    w[r] = work + (size_t)r * work_stride + T.work_off[node];
-    wp[r] = work + (size_t)r * work_stride + T.work_off[p];
-  }
-  const int t = threadIdx.x;
-  const int row = r0 + t;
-  const bool valid = row < ns;
-  S acc[NRHS];
-#pragma unroll
-  for (int r = 0; r < NRHS; ++r) acc[r] = scalar_traits<S>::zero();
-  for (int c0 = 0; c0 < nbd; c0 += UPD_CHUNK) {
-    const int cn = min(UPD_CHUNK, nbd - c0);
-    for (int c = t; c < cn; c += UPD_ROWS) {
-      const int ri = rel[c0 + c];
-#pragma unroll
-      for (int r = 0; r < NRHS; ++r) {
-        const S v = wp[r][ri];
-        xs[r][c] = v;
-        if (blockIdx.y == 0) w[r][ns + c0 + c] = v;
-      }
-    }
-    __syncthreads();
-    if (valid) {
-      const S* col = Fn + row + (long long)(ns + c0) * m;
-#pragma unroll 8
-      for (int c = 0; c < cn; ++c) {
-        const S u = col[(long long)c * m];
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) fma_(acc[r], u, xs[r][c]);
-      }
-    }
-    __syncthreads();
-  }
-  if (valid)
-#pragma unroll
-    for (int r = 0; r < NRHS; ++r) w[r][row] = w[r][row] - acc[r];
-}
-
-template <class S, int NRHS>
-__global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_bwd_chain(FrontTab T, const int* __restrict__ nodes,
-                                                                 const S* __restrict__ F, S* __restrict__ work,
-                                                                 int64_t work_stride, S* __restrict__ xp, int na) {
-  constexpr int NGMAX = SOLVE_MAX_THREADS / 32;
-  __shared__ S D[PW][PW + 1];
-  __shared__ S part[NRHS][NGMAX][PW];
-  const int nthr = blockDim.x, NG = nthr >> 5;
-  const int node = nodes[blockIdx.x];
-  const int m = T.m[node], ns = T.ns[node], os = T.own_start[node];
-  if (ns == 0) return;
-  const S* Fn = F + T.front_off[node];
-  S* w[NRHS];
-#pragma unroll
-  for (int r = 0; r < NRHS; ++r) w[r] = work + (size_t)r * work_stride + T.work_off[node];
-  const int t = threadIdx.x, lane = t & 31, g = t >> 5;
-  const int npan = (ns + PW - 1) / PW;
-  for (int kp = npan - 1; kp >= 0; --kp) {
-    const int k0 = kp * PW;
-    const int wd = min(PW, ns - k0);
-    for (int idx = t; idx < wd * wd; idx += nthr) {
-      int r = idx % wd, c = idx / wd;
-      D[r][c] = Fn[(k0 + r) + (long long)(k0 + c) * m];
-    }
-    S acc[NRHS];
-#pragma unroll
-    for (int r = 0; r < NRHS; ++r) acc[r] = scalar_traits<S>::zero();
-    if (lane < wd) {
-      // own columns right of the panel (already final); boundary columns were folded in by k_bwd_update
-#pragma unroll 4
-      for (int c = k0 + wd + g; c < ns; c += NG) {
-        const S u = Fn[(k0 + lane) + (long long)c * m];
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) fma_(acc[r], u, w[r][c]);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < NRHS; ++r) part[r][g][lane] = acc[r];
-    __syncthreads();
-    if (t < 32 * NRHS) {
-      const int r = t >> 5;
-      S y = scalar_traits<S>::zero();
-      if (lane < wd) {
-        y = w[r][k0 + lane];
-        for (int q = 0; q < NG; ++q) y = y - part[r][q][lane];
-      }
-      for (int j = wd - 1; j >= 0; --j) {
-        S xj = scalar_traits<S>::zero();
-        if (lane == j) {
-          y = y / D[j][j];
-          xj = y;
-        }
-        xj = shfl_bcast_<S>(xj, j);
-        if (lane < j) fnma_(y, D[lane][j], xj);
-      }
-      if (lane < wd) w[r][k0 + lane] = y;
-    }
-    __syncthreads();
-  }
-  for (int i = t; i < ns; i += nthr)
-#pragma unroll
-    for (int r = 0; r < NRHS; ++r) xp[(size_t)r * na + os + i] = w[r][i];
-}
-
-static int chain_threads(int max_ns) {
-  if (max_ns <= 64) return 64;
-  if (max_ns <= 128) return 128;
-  if (max_ns <= 512) return 256;
-  return SOLVE_MAX_THREADS;
-}
-
-template <class S, int NRHS>
-static void solve_typed(Handle& h, const S* b, S* x) {
-  LU& lu = *h.lu;
-  LUDevice& d = *lu.dev;
-  const LUSymbolic& Sy = lu.sym;
-  cudaStream_t s = h.stream;
-  const size_t wsc = sizeof(S) / sizeof(double);
-  const int n = Sy.n, na = Sy.n_active;
-  d.work.alloc((size_t)std::max<int64_t>(1, Sy.work_entries) * 2 * wsc);
-  d.xperm.alloc((size_t)std::max(1, na) * 2 * wsc);
-  S* xp = (S*)d.xperm.p;
-  S* work = (S*)d.work.p;
-  const S* F = (const S*)d.factors.p;
-  FrontTab T = d.tab();
-  int64_t launches = 2;
-  const char* tenv = getenv("FW_TRACE");
-  const bool trace2 = tenv && atoi(tenv) >= 2;
-  Trace tr(s);
-  if (na > 0) k_lu_permute_in<S><<<cdiv(na, 256), 256, 0, s>>>(na, d.perm.p, b, n, NRHS, xp);
-  for (int lev = Sy.n_levels - 1; lev >= 0; --lev) {
-    const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
-    const int* nodes = d.level_nodes.p + Sy.level_start[lev];
-    const int thr = chain_threads(Sy.level_max_ns[lev]);
-    k_fwd_chain<S, NRHS><<<nfront, thr, 0, s>>>(T, nodes, F, d.rowperm.p, work, Sy.work_entries, xp, na);
-    if (trace2) tr.mark(("fwd chain  lev " + std::to_string(lev) + " fronts " + std::to_string(nfront) + " max_ns " +
-                         std::to_string(Sy.level_max_ns[lev])).c_str());
-    const int tiles = (Sy.level_max_nb[lev] + UPD_ROWS - 1) / UPD_ROWS;
-    if (tiles > 0) {
-      k_fwd_update<S, NRHS><<<dim3(nfront, tiles), UPD_ROWS, 0, s>>>(T, nodes, F, work, Sy.work_entries);
-      ++launches;
-      if (trace2) tr.mark(("fwd update lev " + std::to_string(lev) + " max_nb " +
-                           std::to_string(Sy.level_max_nb[lev])).c_str());
-    }
-    ++launches;
-  }
-  for (int lev = 0; lev < Sy.n_levels; ++lev) {
-    const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
-    const int* nodes = d.level_nodes.p + Sy.level_start[lev];
-    const int thr = chain_threads(Sy.level_max_ns[lev]);
-    if (Sy.level_max_nb[lev] > 0) {
-      const int tiles = std::max(1, (Sy.level_max_ns[lev] + UPD_ROWS - 1) / UPD_ROWS);
-      k_bwd_update<S, NRHS><<<dim3(nfront, tiles), UPD_ROWS, 0, s>>>(T, nodes, F, work, Sy.work_entries);
-      ++launches;
-      if (trace2) tr.mark(("bwd update lev " + std::to_string(lev)).c_str());
-    }
-    k_bwd_chain<S, NRHS><<<nfront, thr, 0, s>>>(T, nodes, F, work, Sy.work_entries, xp, na);
-    ++launches;
-    if (trace2) tr.mark(("bwd chain  lev " + std::to_string(lev)).c_str());
-  }
-  k_lu_permute_out<S><<<cdiv(n, 256), 256, 0, s>>>(n, d.iperm.p, xp, na, NRHS, x);
-  FW_CHECK_CUDA(cudaGetLastError());
-  h.tim.kernel_launches += launches;
-}
-
-void lu_solve_dev(Handle& h, const void* b, void* x, int nrhs) {
-  FW_REQUIRE(h.lu && h.lu->factored, "LU has not been factored");
-  FW_REQUIRE(nrhs == 1 || nrhs == 2, "nrhs must be 1 or 2");
-  if (h.lu->is_complex) {
-    if (nrhs == 1)
-      solve_typed<cplx, 1>(h, (const cplx*)b, (cplx*)x);
-    else
-      solve_typed<cplx, 2>(h, (const cplx*)b, (cplx*)x);
-  } else {
-    if (nrhs == 1)
-      solve_typed<double, 1>(h, (const double*)b, (double*)x);
-    else
-      solve_typed<double, 2>(h, (const double*)b, (double*)x);
-  }
-}
-
-}  // namespace fw
-
 // ---- debug export (tests only): factor arena and pivot vector
-namespace fw {
 void lu_debug_download(Handle& h, int which, void* out) {
   FW_REQUIRE(h.lu && h.lu->factored, "LU has not been factored");
   LU& lu = *h.lu;
