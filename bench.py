@@ -258,8 +258,22 @@ def main():
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     achieved = alg_bytes / t_elem / 1e9
-    roofline = {"kernel": "k_element_blocks (K1: A and B local blocks, 2 launches per solve)", "bound": "hbm",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # DRAM traffic of the same three launches from the committed ncu --set full capture (bytes per solve)
+    traffic = None
+    try:
+        import csv
+
+        rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", "ncu_r01_assembly_full.csv")))
+                if r and not r[0].startswith("#")]
+        hdr = rows[0]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        k1 = [r for r in rows[2:] if "k_element_blocks" in r[1]][:3]
+        traffic = sum(float(r[ir]) * 1e9 + float(r[iw]) * 1e6 for r in k1)
+    except Exception:
+        pass
+    roofline = {"kernel": "k_element_blocks (K1: aform Nedelec rows + aform Lagrange rows + bform, 3 launches per solve)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic,
                 "algorithmic_bytes_per_solve": alg_bytes, "seconds_per_solve": t_elem,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
