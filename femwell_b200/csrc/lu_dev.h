@@ -20,7 +20,7 @@ struct LUDevice {
   DevBuf<long long> front_off, work_off, blist_off;
   DevBuf<int> blist, rel, level_nodes;
   DevBuf<int> piv, rowperm;
-  DevBuf<double> factors, work, xperm;
+  DevBuf<double> factors, work, xperm, scratch;
   DevBuf<int> counters;
   DevBuf<uint8_t> active;
   FrontTab tab() const {

@@ -5,14 +5,17 @@
 // Four kernels per tree level:
 //   forward : chain  (assemble w from the rhs and the children, apply the composed row permutation,
 //                     unit-lower solve of the ns x ns pivot block, 32 columns at a time)
-//             update (fronts x 128-row tiles: w_boundary -= L21 x1 -- the bulk of the L traffic)
-//   backward: update (fronts x 128-row tiles: gather x2 from the parent, y1 = w1 - U12 x2)
+//             update (fronts x 128-row tiles x 4 column groups: w_boundary -= L21 x1 -- the bulk of
+//                     the L traffic)
+//   backward: update (same tiling: gather x2 from the parent, y1 = w1 - U12 x2)
 //             chain  (right-looking upper solve of the pivot block, write x)
-// The chain is the only sequential part (ns/32 dependent steps).  Fronts with a tall pivot block
-// (top of the tree: ns up to a few thousand, only a handful of fronts per level) run it on a
-// thread-block CLUSTER of 8 CTAs -- every CTA owns a slice of the rows, the 32x32 diagonal solve is
-// replicated per CTA, one hardware cluster barrier per step -- instead of a single CTA.
-// HBM-bound work (each factor entry is read once per solve); no tensor cores.
+// The chain is the only sequential part (ns/32 dependent steps).  Every thread owns one fixed row of the
+// pivot block; the 32 factor entries it needs for the NEXT step and the next 32x32 diagonal block are
+// prefetched into registers while the current step runs (software pipelining: the chain is bound by HBM
+// latency, not bandwidth).  Fronts with a tall pivot block (top of the tree: ns up to a few thousand,
+// a handful of fronts per level) run the chain on a thread-block CLUSTER of 8 CTAs -- every CTA owns a
+// slice of the rows, the 32x32 diagonal solve is replicated per CTA, one hardware cluster barrier per
+// step.  HBM-bound work (each factor entry is read once per solve); no tensor cores.
 #include <cooperative_groups.h>
 
 #include <algorithm>
@@ -29,6 +32,7 @@ constexpr int UPD_CHUNK = 256;
 constexpr int CL = 8;             // CTAs per cluster in the tall-front chain kernels
 constexpr int CL_THREADS = 512;
 constexpr int CL_MIN_NS = 384;    // levels whose largest pivot block exceeds this use the cluster kernels
+constexpr int DPT = 4;            // prefetched diagonal-block entries per thread (blockDim >= 256)
 
 template <class S>
 __global__ void k_lu_permute_in(int na, const int* __restrict__ perm, const S* __restrict__ b, int n, int nrhs,
@@ -56,35 +60,37 @@ __device__ inline cplx shfl_bcast_<cplx>(cplx v, int src) {
 }
 
 // acc[r] -= sum_j col[j*m] * xs[r][j]: the strided factor entries of one row are fetched 16 at a time so
-// that 16 independent HBM requests are in flight per thread (the chain is latency bound, not bandwidth bound)
+// that 16 independent HBM requests are in flight per thread
 template <class S, int NRHS, int LD>
 __device__ __forceinline__ void row_dot_sub(S (&acc)[NRHS], const S* __restrict__ col, long long m, int cnt,
-                                            S (&xs)[NRHS][LD]) {
+                                            S (&xs)[NRHS][LD], int x0 = 0, int stride = 1) {
   int j = 0;
   for (; j + 16 <= cnt; j += 16) {
     S l[16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) l[q] = col[(long long)(j + q) * m];
+    for (int q = 0; q < 16; ++q) l[q] = col[(long long)(j + q) * stride * m];
 #pragma unroll
     for (int q = 0; q < 16; ++q)
 #pragma unroll
-      for (int r = 0; r < NRHS; ++r) fnma_(acc[r], l[q], xs[r][j + q]);
+      for (int r = 0; r < NRHS; ++r) fnma_(acc[r], l[q], xs[r][x0 + (j + q) * stride]);
   }
   for (; j < cnt; ++j) {
-    const S l = col[(long long)j * m];
+    const S l = col[(long long)j * stride * m];
 #pragma unroll
-    for (int r = 0; r < NRHS; ++r) fnma_(acc[r], l, xs[r][j]);
+    for (int r = 0; r < NRHS; ++r) fnma_(acc[r], l, xs[r][x0 + j * stride]);
   }
 }
 
 // Synchronisation policy of the chain kernels: one CTA (block barrier) or one cluster (cluster barrier).
 struct SyncCta {
+  static constexpr bool pipe = false;  // small fronts: occupancy matters more than the register prefetch
   __device__ static int rank() { return 0; }
   __device__ static int nctas() { return 1; }
   __device__ static int front(int bx) { return bx; }
   __device__ static void sync() { __syncthreads(); }
 };
 struct SyncCluster {
+  static constexpr bool pipe = true;
   __device__ static int rank() { return (int)cg::this_cluster().block_rank(); }
   __device__ static int nctas() { return CL; }
   __device__ static int front(int bx) { return bx / CL; }
@@ -92,6 +98,33 @@ struct SyncCluster {
   // cluster (and invalidates L1) before anyone proceeds
   __device__ static void sync() { cg::this_cluster().sync(); }
 };
+
+// prefetch / commit of a 32x32 diagonal block (column-major panel of the front) through registers
+template <class S>
+__device__ __forceinline__ void diag_fetch(S (&dn)[DPT], const S* __restrict__ Fn, int m, int k0, int wd, int t,
+                                           int nthr) {
+#pragma unroll
+  for (int q = 0; q < DPT; ++q) {
+    const int idx = t + q * nthr;
+    dn[q] = scalar_traits<S>::zero();
+    if (idx < wd * wd) {
+      const int r = idx % wd, c = idx / wd;
+      dn[q] = Fn[(k0 + r) + (long long)(k0 + c) * m];
+    }
+  }
+}
+template <class S, bool RECIP_DIAG>
+__device__ __forceinline__ void diag_commit(S (*D)[PW + 1], const S (&dn)[DPT], int wd, int t, int nthr) {
+#pragma unroll
+  for (int q = 0; q < DPT; ++q) {
+    const int idx = t + q * nthr;
+    if (idx < wd * wd) {
+      const int r = idx % wd, c = idx / wd;
+      // reciprocal of the diagonal here (32 threads in parallel) keeps the divisions out of the serial chain
+      D[r][c] = (RECIP_DIAG && r == c) ? (scalar_traits<S>::one() / dn[q]) : dn[q];
+    }
+  }
+}
 
 // ------------------------------------------------------------------------------ forward chain
 template <class S, int NRHS, class SY>
@@ -107,8 +140,21 @@ __device__ __forceinline__ void fwd_chain_body(FrontTab T, const int* __restrict
 #pragma unroll
   for (int r = 0; r < NRHS; ++r) w[r] = work + (size_t)r * work_stride + T.work_off[node];
   const int t = threadIdx.x;
-  const int nth = blockDim.x * SY::nctas();
-  const int gt = SY::rank() * blockDim.x + t;
+  const int nthr = blockDim.x;
+  const int nth = nthr * SY::nctas();
+  const int gt = SY::rank() * nthr + t;
+  // register prefetch for real arithmetic and block sizes >= 256 (32 c128 values would not fit the budget)
+  const bool pipelined = SY::pipe && !scalar_traits<S>::is_complex && nthr * DPT >= PW * PW;
+  // the first diagonal block and this thread's first row segment do not depend on the rhs: fetch them now
+  S dn[DPT], ln[PW];
+  const int row0 = gt;  // the fixed row of the pivot block owned by this thread (further rows: gt + c*nth)
+  if (ns > 0 && pipelined) {
+    diag_fetch<S>(dn, Fn, m, 0, min(PW, ns), t, nthr);
+    if (row0 >= PW && row0 < ns) {
+#pragma unroll
+      for (int j = 0; j < PW; ++j) ln[j] = Fn[row0 + (long long)j * m];
+    }
+  }
   for (int i = gt; i < m; i += nth)
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) w[r][i] = i < ns ? xp[(size_t)r * na + os + i] : scalar_traits<S>::zero();
@@ -142,11 +188,18 @@ __device__ __forceinline__ void fwd_chain_body(FrontTab T, const int* __restrict
   SY::sync();
   for (int k0 = 0; k0 < ns; k0 += PW) {
     const int wd = min(PW, ns - k0);
-    for (int idx = t; idx < wd * wd; idx += blockDim.x) {
-      int r = idx % wd, c = idx / wd;
-      D[r][c] = Fn[(k0 + r) + (long long)(k0 + c) * m];
+    if (pipelined) {
+      diag_commit<S, false>(D, dn, wd, t, nthr);
+    } else {
+      for (int idx = t; idx < wd * wd; idx += nthr) {
+        int r = idx % wd, c = idx / wd;
+        D[r][c] = Fn[(k0 + r) + (long long)(k0 + c) * m];
+      }
     }
     __syncthreads();
+    // prefetch the next diagonal block while warp 0 runs the serial 32-step solve
+    const int k1 = k0 + PW;
+    if (pipelined && k1 < ns) diag_fetch<S>(dn, Fn, m, k1, min(PW, ns - k1), t, nthr);
     if (t < 32 * NRHS) {  // replicated in every CTA of a cluster; rank 0 stores the result
       const int r = t >> 5, lane = t & 31;
       S x = lane < wd ? w[r][k0 + lane] : scalar_traits<S>::zero();
@@ -158,13 +211,47 @@ __device__ __forceinline__ void fwd_chain_body(FrontTab T, const int* __restrict
     }
     __syncthreads();
     // remaining own rows only; the boundary rows are updated by k_fwd_update
-    for (int row = k0 + wd + gt; row < ns; row += nth) {
+    if (pipelined && wd == PW && row0 >= k0 + PW && row0 < ns) {
       S acc[NRHS];
 #pragma unroll
-      for (int r = 0; r < NRHS; ++r) acc[r] = w[r][row];
-      row_dot_sub<S, NRHS, PW>(acc, Fn + row + (long long)k0 * m, m, wd, xs);
+      for (int r = 0; r < NRHS; ++r) acc[r] = w[r][row0];
 #pragma unroll
-      for (int r = 0; r < NRHS; ++r) w[r][row] = acc[r];
+      for (int j = 0; j < PW; ++j)
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) fnma_(acc[r], ln[j], xs[r][j]);
+#pragma unroll
+      for (int r = 0; r < NRHS; ++r) w[r][row0] = acc[r];
+      // this row's entries of the next panel (used one step later)
+      if (row0 >= k1 + PW && k1 + PW <= ns) {
+#pragma unroll
+        for (int j = 0; j < PW; ++j) ln[j] = Fn[row0 + (long long)(k1 + j) * m];
+      } else if (row0 >= k1 + PW) {
+        // the next panel is the ragged last one: it is handled by the generic path below
+      }
+      for (int row = row0 + nth; row < ns; row += nth) {
+        S a2[NRHS];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) a2[r] = w[r][row];
+        row_dot_sub<S, NRHS, PW>(a2, Fn + row + (long long)k0 * m, m, wd, xs);
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) w[r][row] = a2[r];
+      }
+    } else {
+      const int first = (pipelined && wd == PW) ? row0 + nth : k0 + wd + gt;
+      for (int row = first; row < ns; row += nth) {
+        if (row < k0 + wd) continue;
+        S acc[NRHS];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) acc[r] = w[r][row];
+        row_dot_sub<S, NRHS, PW>(acc, Fn + row + (long long)k0 * m, m, wd, xs);
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) w[r][row] = acc[r];
+      }
+      // keep the pipeline primed for the next full panel
+      if (pipelined && wd == PW && row0 >= k1 + PW && row0 < ns && k1 + PW <= ns) {
+#pragma unroll
+        for (int j = 0; j < PW; ++j) ln[j] = Fn[row0 + (long long)(k1 + j) * m];
+      }
     }
     SY::sync();
     // x_k is stored only now: the other CTAs of a cluster have read the old w[k0:k0+wd) by this point
@@ -200,19 +287,32 @@ __device__ __forceinline__ void bwd_chain_body(FrontTab T, const int* __restrict
 #pragma unroll
   for (int r = 0; r < NRHS; ++r) w[r] = work + (size_t)r * work_stride + T.work_off[node];
   const int t = threadIdx.x;
-  const int nth = blockDim.x * SY::nctas();
-  const int gt = SY::rank() * blockDim.x + t;
+  const int nthr = blockDim.x;
+  const int nth = nthr * SY::nctas();
+  const int gt = SY::rank() * nthr + t;
   const int npan = (ns + PW - 1) / PW;
+  const bool pipelined = SY::pipe && !scalar_traits<S>::is_complex && nthr * DPT >= PW * PW;
+  const int row0 = gt;
+  S dn[DPT], un[PW];
+  {
+    const int k0 = (npan - 1) * PW;
+    if (pipelined) diag_fetch<S>(dn, Fn, m, k0, min(PW, ns - k0), t, nthr);
+  }
+  bool un_valid = false;  // un holds U[row0, panel kp] for the panel about to be processed
   for (int kp = npan - 1; kp >= 0; --kp) {
     const int k0 = kp * PW;
     const int wd = min(PW, ns - k0);
-    for (int idx = t; idx < wd * wd; idx += blockDim.x) {
-      int r = idx % wd, c = idx / wd;
-      const S v = Fn[(k0 + r) + (long long)(k0 + c) * m];
-      // reciprocal of the diagonal here (32 threads in parallel) keeps the divisions out of the serial chain
-      D[r][c] = (r == c) ? (scalar_traits<S>::one() / v) : v;
+    if (pipelined) {
+      diag_commit<S, true>(D, dn, wd, t, nthr);
+    } else {
+      for (int idx = t; idx < wd * wd; idx += nthr) {
+        int r = idx % wd, c = idx / wd;
+        const S v = Fn[(k0 + r) + (long long)(k0 + c) * m];
+        D[r][c] = (r == c) ? (scalar_traits<S>::one() / v) : v;
+      }
     }
     __syncthreads();
+    if (pipelined && kp > 0) diag_fetch<S>(dn, Fn, m, k0 - PW, PW, t, nthr);
     if (t < 32 * NRHS) {
       const int r = t >> 5, lane = t & 31;
       S y = lane < wd ? w[r][k0 + lane] : scalar_traits<S>::zero();
@@ -229,13 +329,35 @@ __device__ __forceinline__ void bwd_chain_body(FrontTab T, const int* __restrict
     }
     __syncthreads();
     // fold x_k into the rows above: w[0:k0) -= U[0:k0, panel] x_k  (thread owns rows: no reduction)
-    for (int row = gt; row < k0; row += nth) {
+    if (row0 < k0) {
       S acc[NRHS];
 #pragma unroll
-      for (int r = 0; r < NRHS; ++r) acc[r] = w[r][row];
-      row_dot_sub<S, NRHS, PW>(acc, Fn + row + (long long)k0 * m, m, wd, xs);
+      for (int r = 0; r < NRHS; ++r) acc[r] = w[r][row0];
+      if (un_valid && wd == PW) {
 #pragma unroll
-      for (int r = 0; r < NRHS; ++r) w[r][row] = acc[r];
+        for (int j = 0; j < PW; ++j)
+#pragma unroll
+          for (int r = 0; r < NRHS; ++r) fnma_(acc[r], un[j], xs[r][j]);
+      } else {
+        row_dot_sub<S, NRHS, PW>(acc, Fn + row0 + (long long)k0 * m, m, wd, xs);
+      }
+#pragma unroll
+      for (int r = 0; r < NRHS; ++r) w[r][row0] = acc[r];
+    }
+    // this row's entries of the next (lower-index, always full) panel
+    un_valid = false;
+    if (pipelined && kp > 0 && row0 < k0 - PW) {
+#pragma unroll
+      for (int j = 0; j < PW; ++j) un[j] = Fn[row0 + (long long)(k0 - PW + j) * m];
+      un_valid = true;
+    }
+    for (int row = row0 + nth; row < k0; row += nth) {
+      S a2[NRHS];
+#pragma unroll
+      for (int r = 0; r < NRHS; ++r) a2[r] = w[r][row];
+      row_dot_sub<S, NRHS, PW>(a2, Fn + row + (long long)k0 * m, m, wd, xs);
+#pragma unroll
+      for (int r = 0; r < NRHS; ++r) w[r][row] = a2[r];
     }
     SY::sync();
     if (SY::rank() == 0 && t < 32 * NRHS && (t & 31) < wd) w[t >> 5][k0 + (t & 31)] = xs[t >> 5][t & 31];
@@ -260,10 +382,17 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
 }
 
 // ------------------------------------------------------------------------------ off-diagonal updates
-template <class S, int NRHS>
-__global__ void __launch_bounds__(UPD_ROWS) k_fwd_update(FrontTab T, const int* __restrict__ nodes,
-                                                         const S* __restrict__ F, S* work, int64_t work_stride) {
+// block = UPD_ROWS rows x UPD_GROUPS column groups; group g handles the columns j = g (mod UPD_GROUPS) of a
+// chunk, the partial sums are combined through shared memory in a fixed order (deterministic).
+// gridDim.z > 1: the column chunks are dealt round-robin to the z-slices; every slice writes its partial
+// sums to scratch[z][work_off + row] and k_upd_reduce adds them to w in a fixed order (deterministic).
+template <class S, int NRHS, int G>
+__global__ void __launch_bounds__(UPD_ROWS* G) k_fwd_update(FrontTab T, const int* __restrict__ nodes,
+                                                            const S* __restrict__ F, S* work, int64_t work_stride,
+                                                            S* scratch) {
+  constexpr int UPD_GROUPS = G;
   __shared__ S xs[NRHS][UPD_CHUNK];
+  __shared__ S part[NRHS][UPD_GROUPS][UPD_ROWS];
   const int node = nodes[blockIdx.x];
   const int m = T.m[node], ns = T.ns[node];
   const int nbd = m - ns;
@@ -274,29 +403,48 @@ __global__ void __launch_bounds__(UPD_ROWS) k_fwd_update(FrontTab T, const int* 
 #pragma unroll
   for (int r = 0; r < NRHS; ++r) w[r] = work + (size_t)r * work_stride + T.work_off[node];
   const int t = threadIdx.x;
-  const int row = ns + r0 + t;
+  const int lr = t % UPD_ROWS, g = t / UPD_ROWS;
+  const int row = ns + r0 + lr;
   const bool valid = row < m;
   S acc[NRHS];
 #pragma unroll
   for (int r = 0; r < NRHS; ++r) acc[r] = scalar_traits<S>::zero();
-  for (int j0 = 0; j0 < ns; j0 += UPD_CHUNK) {
+  for (int j0 = blockIdx.z * UPD_CHUNK; j0 < ns; j0 += UPD_CHUNK * gridDim.z) {
     const int cn = min(UPD_CHUNK, ns - j0);
-    for (int j = t; j < cn; j += UPD_ROWS)
+    for (int j = t; j < cn; j += UPD_ROWS * UPD_GROUPS)
 #pragma unroll
       for (int r = 0; r < NRHS; ++r) xs[r][j] = w[r][j0 + j];
     __syncthreads();
-    if (valid) row_dot_sub<S, NRHS, UPD_CHUNK>(acc, Fn + row + (long long)j0 * m, m, cn, xs);
+    if (valid && g < cn) {
+      const int cnt = (cn - g + UPD_GROUPS - 1) / UPD_GROUPS;
+      row_dot_sub<S, NRHS, UPD_CHUNK>(acc, Fn + row + (long long)(j0 + g) * m, m, cnt, xs, g, UPD_GROUPS);
+    }
     __syncthreads();
   }
-  if (valid)
 #pragma unroll
-    for (int r = 0; r < NRHS; ++r) w[r][row] = w[r][row] + acc[r];
+  for (int r = 0; r < NRHS; ++r) part[r][g][lr] = acc[r];
+  __syncthreads();
+  if (g == 0 && valid) {
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) {
+      S s = part[r][0][lr];
+#pragma unroll
+      for (int q = 1; q < UPD_GROUPS; ++q) s = s + part[r][q][lr];
+      if (gridDim.z == 1)
+        w[r][row] = w[r][row] + s;
+      else
+        scratch[((size_t)blockIdx.z * NRHS + r) * work_stride + T.work_off[node] + row] = s;
+    }
+  }
 }
 
-template <class S, int NRHS>
-__global__ void __launch_bounds__(UPD_ROWS) k_bwd_update(FrontTab T, const int* __restrict__ nodes,
-                                                         const S* __restrict__ F, S* work, int64_t work_stride) {
+template <class S, int NRHS, int G>
+__global__ void __launch_bounds__(UPD_ROWS* G) k_bwd_update(FrontTab T, const int* __restrict__ nodes,
+                                                            const S* __restrict__ F, S* work, int64_t work_stride,
+                                                            S* scratch) {
+  constexpr int UPD_GROUPS = G;
   __shared__ S xs[NRHS][UPD_CHUNK];
+  __shared__ S part[NRHS][UPD_GROUPS][UPD_ROWS];
   const int node = nodes[blockIdx.x];
   const int m = T.m[node], ns = T.ns[node];
   const int nbd = m - ns;
@@ -314,14 +462,15 @@ __global__ void __launch_bounds__(UPD_ROWS) k_bwd_update(FrontTab T, const int* 
     wp[r] = work + (size_t)r * work_stride + T.work_off[p];
   }
   const int t = threadIdx.x;
-  const int row = r0 + t;
+  const int lr = t % UPD_ROWS, g = t / UPD_ROWS;
+  const int row = r0 + lr;
   const bool valid = row < ns;
   S acc[NRHS];
 #pragma unroll
   for (int r = 0; r < NRHS; ++r) acc[r] = scalar_traits<S>::zero();
-  for (int c0 = 0; c0 < nbd; c0 += UPD_CHUNK) {
+  for (int c0 = blockIdx.z * UPD_CHUNK; c0 < nbd; c0 += UPD_CHUNK * gridDim.z) {
     const int cn = min(UPD_CHUNK, nbd - c0);
-    for (int c = t; c < cn; c += UPD_ROWS) {
+    for (int c = t; c < cn; c += UPD_ROWS * UPD_GROUPS) {
       const int ri = rel[c0 + c];
 #pragma unroll
       for (int r = 0; r < NRHS; ++r) {
@@ -331,15 +480,55 @@ __global__ void __launch_bounds__(UPD_ROWS) k_bwd_update(FrontTab T, const int* 
       }
     }
     __syncthreads();
-    if (valid) row_dot_sub<S, NRHS, UPD_CHUNK>(acc, Fn + row + (long long)(ns + c0) * m, m, cn, xs);
+    if (valid && g < cn) {
+      const int cnt = (cn - g + UPD_GROUPS - 1) / UPD_GROUPS;
+      row_dot_sub<S, NRHS, UPD_CHUNK>(acc, Fn + row + (long long)(ns + c0 + g) * m, m, cnt, xs, g, UPD_GROUPS);
+    }
     __syncthreads();
   }
-  if (valid)
 #pragma unroll
-    for (int r = 0; r < NRHS; ++r) w[r][row] = w[r][row] + acc[r];
+  for (int r = 0; r < NRHS; ++r) part[r][g][lr] = acc[r];
+  __syncthreads();
+  if (g == 0 && valid) {
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) {
+      S s = part[r][0][lr];
+#pragma unroll
+      for (int q = 1; q < UPD_GROUPS; ++q) s = s + part[r][q][lr];
+      if (gridDim.z == 1)
+        w[r][row] = w[r][row] + s;
+      else
+        scratch[((size_t)blockIdx.z * NRHS + r) * work_stride + T.work_off[node] + row] = s;
+    }
+  }
+}
+
+// w[row] += sum_z scratch[z][row] for the rows [lo_own ? 0 : ns, ...) of every front of a level
+template <class S, int NRHS>
+__global__ void k_upd_reduce(FrontTab T, const int* __restrict__ nodes, S* work, int64_t work_stride,
+                             const S* __restrict__ scratch, int nz, int boundary_rows) {
+  const int node = nodes[blockIdx.x];
+  const int m = T.m[node], ns = T.ns[node];
+  const int lo = boundary_rows ? ns : 0, hi = boundary_rows ? m : ns;
+  if (boundary_rows ? ns == 0 : m == ns) return;  // the update kernel did not run for this front
+  for (int row = lo + blockIdx.y * blockDim.x + threadIdx.x; row < hi; row += gridDim.y * blockDim.x) {
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) {
+      S* w = work + (size_t)r * work_stride + T.work_off[node];
+      S s = w[row];
+      for (int z = 0; z < nz; ++z) s = s + scratch[((size_t)z * NRHS + r) * work_stride + T.work_off[node] + row];
+      w[row] = s;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------ driver
+// z-slices so that a level with few, huge fronts still fills the 148 SMs
+static int upd_splits(int nfront, int tiles, int cols) {
+  const int chunks = (cols + UPD_CHUNK - 1) / UPD_CHUNK;
+  const int want = (2 * 148 + nfront * tiles - 1) / std::max(1, nfront * tiles);
+  return std::max(1, std::min(std::min(want, chunks), 16));
+}
 static int chain_threads(int max_ns) {
   if (max_ns <= 64) return 64;
   if (max_ns <= 128) return 128;
@@ -383,8 +572,18 @@ static void solve_typed(Handle& h, const S* b, S* x) {
                std::to_string(max_ns)).c_str());
     const int tiles = (Sy.level_max_nb[lev] + UPD_ROWS - 1) / UPD_ROWS;
     if (tiles > 0) {
-      k_fwd_update<S, NRHS><<<dim3(nfront, tiles), UPD_ROWS, 0, s>>>(T, nodes, F, work, Sy.work_entries);
+      const int nz = upd_splits(nfront, tiles, max_ns);
+      if (nz > 1) d.scratch.alloc((size_t)std::max<int64_t>(1, Sy.work_entries) * 16 * 2 * wsc);
+      S* scratch = (S*)d.scratch.p;
+      if (max_ns > 512)
+        k_fwd_update<S, NRHS, 4><<<dim3(nfront, tiles, nz), UPD_ROWS * 4, 0, s>>>(T, nodes, F, work, Sy.work_entries, scratch);
+      else
+        k_fwd_update<S, NRHS, 1><<<dim3(nfront, tiles, nz), UPD_ROWS, 0, s>>>(T, nodes, F, work, Sy.work_entries, scratch);
       ++launches;
+      if (nz > 1) {
+        k_upd_reduce<S, NRHS><<<dim3(nfront, tiles), UPD_ROWS, 0, s>>>(T, nodes, work, Sy.work_entries, scratch, nz, 1);
+        ++launches;
+      }
       if (trace2)
         tr.mark(("fwd update lev " + std::to_string(lev) + " max_nb " + std::to_string(Sy.level_max_nb[lev])).c_str());
     }
@@ -395,8 +594,19 @@ static void solve_typed(Handle& h, const S* b, S* x) {
     const int max_ns = Sy.level_max_ns[lev];
     if (Sy.level_max_nb[lev] > 0) {
       const int tiles = std::max(1, (max_ns + UPD_ROWS - 1) / UPD_ROWS);
-      k_bwd_update<S, NRHS><<<dim3(nfront, tiles), UPD_ROWS, 0, s>>>(T, nodes, F, work, Sy.work_entries);
+      const int max_nb = Sy.level_max_nb[lev];
+      const int nz = upd_splits(nfront, tiles, max_nb);
+      if (nz > 1) d.scratch.alloc((size_t)std::max<int64_t>(1, Sy.work_entries) * 16 * 2 * wsc);
+      S* scratch = (S*)d.scratch.p;
+      if (max_nb > 512)
+        k_bwd_update<S, NRHS, 4><<<dim3(nfront, tiles, nz), UPD_ROWS * 4, 0, s>>>(T, nodes, F, work, Sy.work_entries, scratch);
+      else
+        k_bwd_update<S, NRHS, 1><<<dim3(nfront, tiles, nz), UPD_ROWS, 0, s>>>(T, nodes, F, work, Sy.work_entries, scratch);
       ++launches;
+      if (nz > 1) {
+        k_upd_reduce<S, NRHS><<<dim3(nfront, tiles), UPD_ROWS, 0, s>>>(T, nodes, work, Sy.work_entries, scratch, nz, 0);
+        ++launches;
+      }
       if (trace2) tr.mark(("bwd update lev " + std::to_string(lev)).c_str());
     }
     if (max_ns > CL_MIN_NS && !no_cluster)

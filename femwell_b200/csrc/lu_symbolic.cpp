@@ -5,56 +5,116 @@
 // tree node whose element set contains every element touching the dof; dofs shared between the
 // two halves of a node therefore form its separator.  Because FE couplings only exist inside
 // elements, the front of a node is exactly {own dofs} + {ancestor dofs touched by its elements}.
+//
+// The tree levels are processed with a small std::thread pool (nodes of one level are independent).
 #include <algorithm>
+#include <atomic>
 #include <numeric>
+#include <thread>
 
 #include "lu.h"
 
 namespace fw {
+
+namespace {
+int worker_count() {
+  static int n = [] {
+    const char* e = getenv("FW_HOST_THREADS");
+    int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(v, 16));
+  }();
+  return n;
+}
+
+// f(begin, end, thread_id) over [0, n) in contiguous chunks
+template <class F>
+void parallel_chunks(int n, int min_per_thread, F&& f) {
+  int nt = std::min(worker_count(), std::max(1, n / std::max(1, min_per_thread)));
+  if (nt <= 1) {
+    f(0, n, 0);
+    return;
+  }
+  std::vector<std::thread> th;
+  std::atomic<bool> failed{false};
+  std::string msg;
+  for (int t = 0; t < nt; ++t) {
+    int a = (int)((int64_t)n * t / nt), b = (int)((int64_t)n * (t + 1) / nt);
+    th.emplace_back([&, a, b, t] {
+      try {
+        f(a, b, t);
+      } catch (const std::exception& e) {
+        if (!failed.exchange(true)) msg = e.what();
+      }
+    });
+  }
+  for (auto& x : th) x.join();
+  if (failed) throw Error(FW_ERR_INTERNAL, msg);
+}
+}  // namespace
 
 void lu_symbolic_build(LUSymbolic& S, int n, int nb, int ne, const int* edofs, const double* cx, const double* cy,
                        const uint8_t* active, int leaf_elements) {
   if (leaf_elements <= 0) leaf_elements = 32;
   S = LUSymbolic();
   S.n = n;
-  // ---- 1. kd-tree over elements
+  const bool trace = getenv("FW_TRACE") != nullptr;
+  double t_last = Trace::now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    double t = Trace::now();
+    fprintf(stderr, "[fw-trace]   symbolic/%-20s %9.3f ms\n", what, t - t_last);
+    t_last = t;
+  };
+  // ---- 1. kd-tree over elements, breadth first (the nodes of a level own disjoint ranges of eperm)
   std::vector<int> eperm(ne);
   std::iota(eperm.begin(), eperm.end(), 0);
   std::vector<int> node_lo, node_hi;
-  struct Item {
-    int lo, hi, parent, depth;
-  };
-  std::vector<Item> stack;
-  stack.push_back({0, ne, -1, 0});
-  while (!stack.empty()) {
-    Item it = stack.back();
-    stack.pop_back();
+  auto new_node = [&](int lo, int hi, int parent, int depth) {
     int id = (int)S.parent.size();
-    S.parent.push_back(it.parent);
+    S.parent.push_back(parent);
     S.child0.push_back(-1);
     S.child1.push_back(-1);
-    S.depth.push_back(it.depth);
-    node_lo.push_back(it.lo);
-    node_hi.push_back(it.hi);
-    if (it.parent >= 0) {
-      if (S.child0[it.parent] < 0)
-        S.child0[it.parent] = id;
-      else
-        S.child1[it.parent] = id;
+    S.depth.push_back(depth);
+    node_lo.push_back(lo);
+    node_hi.push_back(hi);
+    return id;
+  };
+  {
+    std::vector<int> level{new_node(0, ne, -1, 0)};
+    std::vector<int> mids;
+    while (!level.empty()) {
+      mids.assign(level.size(), -1);
+      parallel_chunks((int)level.size(), 1, [&](int a, int b, int) {
+        for (int q = a; q < b; ++q) {
+          const int v = level[q], lo = node_lo[v], hi = node_hi[v];
+          if (hi - lo <= leaf_elements) continue;
+          double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+          for (int i = lo; i < hi; ++i) {
+            int e = eperm[i];
+            x0 = std::min(x0, cx[e]), x1 = std::max(x1, cx[e]);
+            y0 = std::min(y0, cy[e]), y1 = std::max(y1, cy[e]);
+          }
+          const double* c = (x1 - x0 >= y1 - y0) ? cx : cy;
+          int mid = (lo + hi) / 2;
+          std::nth_element(eperm.begin() + lo, eperm.begin() + mid, eperm.begin() + hi,
+                           [c](int p, int r) { return c[p] < c[r] || (c[p] == c[r] && p < r); });
+          mids[q] = mid;
+        }
+      });
+      std::vector<int> next;
+      for (size_t q = 0; q < level.size(); ++q) {
+        if (mids[q] < 0) continue;
+        const int v = level[q];
+        const int lo = node_lo[v], hi = node_hi[v], d = S.depth[v];
+        const int c0 = new_node(lo, mids[q], v, d + 1);
+        const int c1 = new_node(mids[q], hi, v, d + 1);
+        S.child0[v] = c0;
+        S.child1[v] = c1;
+        next.push_back(c0);
+        next.push_back(c1);
+      }
+      level.swap(next);
     }
-    if (it.hi - it.lo <= leaf_elements) continue;
-    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
-    for (int i = it.lo; i < it.hi; ++i) {
-      int e = eperm[i];
-      x0 = std::min(x0, cx[e]), x1 = std::max(x1, cx[e]);
-      y0 = std::min(y0, cy[e]), y1 = std::max(y1, cy[e]);
-    }
-    const double* c = (x1 - x0 >= y1 - y0) ? cx : cy;
-    int mid = (it.lo + it.hi) / 2;
-    std::nth_element(eperm.begin() + it.lo, eperm.begin() + mid, eperm.begin() + it.hi,
-                     [c](int a, int b) { return c[a] < c[b] || (c[a] == c[b] && a < b); });
-    stack.push_back({mid, it.hi, id, it.depth + 1});
-    stack.push_back({it.lo, mid, id, it.depth + 1});
   }
   const int nn = (int)S.parent.size();
   S.n_nodes = nn;
@@ -62,6 +122,7 @@ void lu_symbolic_build(LUSymbolic& S, int n, int nb, int ne, const int* edofs, c
   for (int v = 0; v < nn; ++v)
     if (S.child0[v] < 0)
       for (int i = node_lo[v]; i < node_hi[v]; ++i) leaf_of[eperm[i]] = v;
+  mark("kd-tree");
 
   // ---- 2. owner of every dof = LCA of the leaves of its elements
   std::vector<int> owner(n, -1);
@@ -89,6 +150,7 @@ void lu_symbolic_build(LUSymbolic& S, int n, int nb, int ne, const int* edofs, c
       owner[d] = a;
     }
   }
+  mark("owners (LCA)");
 
   // ---- 3. postorder numbering
   S.ns.assign(nn, 0);
@@ -147,85 +209,9 @@ void lu_symbolic_build(LUSymbolic& S, int n, int nb, int ne, const int* edofs, c
       S.node_of[ni] = o;
     }
   }
+  mark("numbering");
 
-  // ---- 4. boundary lists (children before parents) and extend-add maps
-  S.m.assign(nn, 0);
-  S.blist_off.assign(nn, 0);
-  std::vector<std::vector<int>> bl(nn);
-  std::vector<int> tmp;
-  for (int v : post) {
-    const int os = S.own_start[v], nsv = S.ns[v];
-    std::vector<int>& out = bl[v];
-    int own_seen = 0;
-    if (S.child0[v] < 0) {
-      tmp.clear();
-      for (int i = node_lo[v]; i < node_hi[v]; ++i) {
-        int e = eperm[i];
-        for (int l = 0; l < nb; ++l) {
-          int ni = S.iperm[edofs[(size_t)l * ne + e]];
-          if (ni >= 0) tmp.push_back(ni);
-        }
-      }
-      std::sort(tmp.begin(), tmp.end());
-      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-      for (int x : tmp) {
-        if (x >= os && x < os + nsv)
-          own_seen++;
-        else if (x >= os + nsv)
-          out.push_back(x);
-        else
-          throw Error(FW_ERR_INTERNAL, "lu symbolic: leaf sees a descendant index");
-      }
-    } else {
-      const std::vector<int>& a = bl[S.child0[v]];
-      const std::vector<int>& b = bl[S.child1[v]];
-      tmp.resize(a.size() + b.size());
-      auto end = std::set_union(a.begin(), a.end(), b.begin(), b.end(), tmp.begin());
-      tmp.resize(end - tmp.begin());
-      for (int x : tmp) {
-        if (x >= os && x < os + nsv)
-          own_seen++;
-        else if (x >= os + nsv)
-          out.push_back(x);
-        else
-          throw Error(FW_ERR_INTERNAL, "lu symbolic: child boundary holds a descendant index");
-      }
-    }
-    if (own_seen != nsv) throw Error(FW_ERR_INTERNAL, "lu symbolic: separator dofs missing from the front");
-    S.m[v] = nsv + (int)out.size();
-  }
-  {
-    int64_t run = 0;
-    for (int v = 0; v < nn; ++v) {
-      S.blist_off[v] = run;
-      run += (int64_t)bl[v].size();
-    }
-    S.blist.resize((size_t)run);
-    S.rel.assign((size_t)run, -1);
-    for (int v = 0; v < nn; ++v) std::copy(bl[v].begin(), bl[v].end(), S.blist.begin() + S.blist_off[v]);
-    for (int v = 0; v < nn; ++v) {
-      int p = S.parent[v];
-      if (p < 0) continue;
-      const std::vector<int>& mine = bl[v];
-      const std::vector<int>& pb = bl[p];
-      const int pos = S.own_start[p], pns = S.ns[p];
-      size_t k = 0;
-      for (size_t i = 0; i < mine.size(); ++i) {
-        int x = mine[i];
-        int r;
-        if (x < pos + pns) {
-          r = x - pos;
-        } else {
-          while (k < pb.size() && pb[k] < x) ++k;
-          if (k >= pb.size() || pb[k] != x) throw Error(FW_ERR_INTERNAL, "lu symbolic: extend-add map broken");
-          r = pns + (int)k;
-        }
-        S.rel[(size_t)S.blist_off[v] + i] = r;
-      }
-    }
-  }
-
-  // ---- 5. levels and arena offsets (deepest level first in memory)
+  // ---- levels (by depth)
   int maxd = 0;
   for (int v = 0; v < nn; ++v) maxd = std::max(maxd, S.depth[v]);
   S.n_levels = maxd + 1;
@@ -237,6 +223,88 @@ void lu_symbolic_build(LUSymbolic& S, int n, int nb, int ne, const int* edofs, c
     std::vector<int> fill(S.level_start.begin(), S.level_start.end() - 1);
     for (int v = 0; v < nn; ++v) S.level_nodes[fill[S.depth[v]]++] = v;
   }
+
+  // ---- 4. boundary lists, deepest level first (children before parents), nodes of a level in parallel
+  S.m.assign(nn, 0);
+  S.blist_off.assign(nn, 0);
+  std::vector<std::vector<int>> bl(nn);
+  for (int lev = S.n_levels - 1; lev >= 0; --lev) {
+    const int l0 = S.level_start[lev], cnt = S.level_start[lev + 1] - l0;
+    parallel_chunks(cnt, 8, [&](int qa, int qb, int) {
+      std::vector<int> tmp;
+      for (int q = qa; q < qb; ++q) {
+        const int v = S.level_nodes[l0 + q];
+        const int os = S.own_start[v], nsv = S.ns[v];
+        std::vector<int>& out = bl[v];
+        int own_seen = 0;
+        if (S.child0[v] < 0) {
+          tmp.clear();
+          for (int i = node_lo[v]; i < node_hi[v]; ++i) {
+            int e = eperm[i];
+            for (int l = 0; l < nb; ++l) {
+              int ni = S.iperm[edofs[(size_t)l * ne + e]];
+              if (ni >= 0) tmp.push_back(ni);
+            }
+          }
+          std::sort(tmp.begin(), tmp.end());
+          tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        } else {
+          const std::vector<int>& a = bl[S.child0[v]];
+          const std::vector<int>& b = bl[S.child1[v]];
+          tmp.resize(a.size() + b.size());
+          auto end = std::set_union(a.begin(), a.end(), b.begin(), b.end(), tmp.begin());
+          tmp.resize(end - tmp.begin());
+        }
+        out.reserve(tmp.size());
+        for (int x : tmp) {
+          if (x >= os && x < os + nsv)
+            own_seen++;
+          else if (x >= os + nsv)
+            out.push_back(x);
+          else
+            throw Error(FW_ERR_INTERNAL, "lu symbolic: front holds a descendant index");
+        }
+        if (own_seen != nsv) throw Error(FW_ERR_INTERNAL, "lu symbolic: separator dofs missing from the front");
+        S.m[v] = nsv + (int)out.size();
+      }
+    });
+  }
+  mark("boundary lists");
+  {
+    int64_t run = 0;
+    for (int v = 0; v < nn; ++v) {
+      S.blist_off[v] = run;
+      run += (int64_t)bl[v].size();
+    }
+    S.blist.resize((size_t)run);
+    S.rel.assign((size_t)run, -1);
+    parallel_chunks(nn, 64, [&](int va, int vb, int) {
+      for (int v = va; v < vb; ++v) {
+        std::copy(bl[v].begin(), bl[v].end(), S.blist.begin() + S.blist_off[v]);
+        int p = S.parent[v];
+        if (p < 0) continue;
+        const std::vector<int>& mine = bl[v];
+        const std::vector<int>& pb = bl[p];
+        const int pos = S.own_start[p], pns = S.ns[p];
+        size_t k = 0;
+        for (size_t i = 0; i < mine.size(); ++i) {
+          int x = mine[i];
+          int r;
+          if (x < pos + pns) {
+            r = x - pos;
+          } else {
+            while (k < pb.size() && pb[k] < x) ++k;
+            if (k >= pb.size() || pb[k] != x) throw Error(FW_ERR_INTERNAL, "lu symbolic: extend-add map broken");
+            r = pns + (int)k;
+          }
+          S.rel[(size_t)S.blist_off[v] + i] = r;
+        }
+      }
+    });
+  }
+  mark("extend-add maps");
+
+  // ---- 5. arena offsets (deepest level first in memory)
   S.front_off.assign(nn, 0);
   S.work_off.assign(nn, 0);
   S.level_max_ns.assign(S.n_levels, 0);
@@ -258,6 +326,7 @@ void lu_symbolic_build(LUSymbolic& S, int n, int nb, int ne, const int* edofs, c
     }
   S.factor_entries = fo;
   S.work_entries = wo;
+  mark("levels/offsets");
 }
 
 }  // namespace fw

@@ -7,6 +7,7 @@
 // (spsolve).  Here the mode-independent real operators Mass, C0, C1 (C = C0 + i beta C1) live on the
 // structural CSR pattern, rhs = C0 e + i beta C1 e is two SpMVs and the SPD mass system is solved by
 // Jacobi-preconditioned CG (condition number O(1)) with hand-written kernels.
+#include <algorithm>
 #include <complex>
 
 #include "solver.h"
@@ -46,8 +47,8 @@ __global__ void k_unscale_ez(cplx* __restrict__ x, const uint8_t* __restrict__ i
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && is_z[i]) x[i] = x[i] * inv_factor;
 }
-__global__ void k_cscale(cplx* __restrict__ x, int n, cplx f) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_cscale(cplx* __restrict__ x, int64_t n, cplx f) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] = x[i] * f;
 }
 __global__ void k_rhs_combine(const cplx* __restrict__ a, const cplx* __restrict__ b, cplx ibeta, int n,
@@ -204,24 +205,39 @@ static void mass_solve(Handle& h, const cplx* b, cplx* x) {
 }
 
 // H = (-i / (mu0 omega)) Mass^-1 (C0 + i beta C1) E        (waveguide.py:657-677)
-void hfield_dev(Handle& h, const cplx* E_dev, cplx beta, double omega, double mu0, cplx* H_dev) {
+// all k modes at once: rhs_i = C0 e_i + i beta_i C1 e_i, one block PCG for the k mass solves
+void hfield_multi_dev(Handle& h, int k, const cplx* E_dev, const cplx* betas, double omega, double mu0, cplx* H_dev) {
+  Trace tr(h.stream);
   assemble_aux(h);
+  tr.mark("  hfield: aux operators");
   const int n = h.sp.n;
   cudaStream_t s = h.stream;
   const Pattern& pat = h.pat;
   DevBuf<double> t0, t1, rhs;
   t0.alloc((size_t)2 * n);
   t1.alloc((size_t)2 * n);
-  rhs.alloc((size_t)2 * n);
-  spmv<double, cplx>(n, pat.indptr.p, pat.indices.p, h.C0.v.p, E_dev, (cplx*)t0.p, s);
-  spmv<double, cplx>(n, pat.indptr.p, pat.indices.p, h.C1.v.p, E_dev, (cplx*)t1.p, s);
-  const cplx ibeta = cplx{0.0, 1.0} * beta;
-  k_rhs_combine<<<cdiv(n, 256), 256, 0, s>>>((const cplx*)t0.p, (const cplx*)t1.p, ibeta, n, (cplx*)rhs.p);
-  mass_solve(h, (const cplx*)rhs.p, H_dev);
+  rhs.alloc((size_t)2 * n * k);
   const cplx f = cplx{0.0, -1.0 / (mu0 * omega)};
-  k_cscale<<<cdiv(n, 256), 256, 0, s>>>(H_dev, n, f);
+  for (int k0 = 0; k0 < k; k0 += 8) {
+    const int kc = std::min(8, k - k0);
+    for (int i = k0; i < k0 + kc; ++i) {
+      const cplx* E = E_dev + (size_t)i * n;
+      spmv<double, cplx>(n, pat.indptr.p, pat.indices.p, h.C0.v.p, E, (cplx*)t0.p, s);
+      spmv<double, cplx>(n, pat.indptr.p, pat.indices.p, h.C1.v.p, E, (cplx*)t1.p, s);
+      const cplx ibeta = cplx{0.0, 1.0} * betas[i];
+      k_rhs_combine<<<cdiv(n, 256), 256, 0, s>>>((const cplx*)t0.p, (const cplx*)t1.p, ibeta, n,
+                                                (cplx*)rhs.p + (size_t)i * n);
+      h.tim.kernel_launches += 3;
+    }
+    mass_solve_multi(h, kc, (const cplx*)rhs.p + (size_t)k0 * n, H_dev + (size_t)k0 * n);
+  }
+  k_cscale<<<cdiv((int64_t)n * k, 256), 256, 0, s>>>(H_dev, n * k, f);
   FW_CHECK_CUDA(cudaGetLastError());
-  h.tim.kernel_launches += 4;
+  h.tim.kernel_launches += 1;
+}
+
+void hfield_dev(Handle& h, const cplx* E_dev, cplx beta, double omega, double mu0, cplx* H_dev) {
+  hfield_multi_dev(h, 1, E_dev, &beta, omega, mu0, H_dev);
 }
 
 // ------------------------------------------------------------------------------ functionals
@@ -411,15 +427,23 @@ void postprocess_modes_dev(Handle& h, int k, const cd* lams, const double* X_dev
   cudaStream_t s = h.stream;
   if ((const void*)E_dev != (const void*)X_dev)
     FW_CHECK_CUDA(cudaMemcpyAsync(E_dev, X_dev, (size_t)k * n * 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  Trace tr(s);
+  std::vector<cplx> betas(k);
   for (int i = 0; i < k; ++i) {
     cplx* E = (cplx*)E_dev + (size_t)i * n;
-    cplx* Hf = (cplx*)H_dev + (size_t)i * n;
     const cd beta = std::sqrt(lams[i]);
+    betas[i] = cplx{beta.real(), beta.imag()};
     // xs[z] /= 1j * sqrt(lam / k0^4)
     const cd denom = cd(0, 1) * std::sqrt(lams[i] / (k0 * k0 * k0 * k0));
     const cd inv = 1.0 / denom;
     k_unscale_ez<<<cdiv(n, 256), 256, 0, s>>>(E, h.sp.is_z.p, n, cplx{inv.real(), inv.imag()});
-    hfield_dev(h, E, cplx{beta.real(), beta.imag()}, omega, mu0, Hf);
+  }
+  tr.mark("post: unscale");
+  hfield_multi_dev(h, k, (const cplx*)E_dev, betas.data(), omega, mu0, (cplx*)H_dev);
+  tr.mark("post: hfield (aux assembly + rhs + PCG)");
+  for (int i = 0; i < k; ++i) {
+    cplx* E = (cplx*)E_dev + (size_t)i * n;
+    cplx* Hf = (cplx*)H_dev + (size_t)i * n;
     cd o3[3];
     functional_dev(h, FW_FUN_OVERLAP, E, Hf, E, Hf, 0, false, nullptr, 0, nullptr, 0, o3);
     const cd power = o3[0];
@@ -427,8 +451,9 @@ void postprocess_modes_dev(Handle& h, int k, const cd* lams, const double* X_dev
     const cd isq = 1.0 / std::sqrt(power);
     k_cscale<<<cdiv(n, 256), 256, 0, s>>>(E, n, cplx{isq.real(), isq.imag()});
     k_cscale<<<cdiv(n, 256), 256, 0, s>>>(Hf, n, cplx{isq.real(), isq.imag()});
-    h.tim.kernel_launches += 3;
+    h.tim.kernel_launches += 4;
   }
+  tr.mark("post: power normalisation");
   FW_CHECK_CUDA(cudaGetLastError());
 }
 

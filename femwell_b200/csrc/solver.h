@@ -19,6 +19,8 @@ void op_apply(Handle& h, const uint8_t* active, S alphaA, S alphaB, const S* x, 
 void postprocess_modes_dev(Handle& h, int k, const std::complex<double>* lams, const double* X_dev, double k0,
                            double omega, double mu0, double* E_dev, double* H_dev, std::complex<double>* powers);
 void hfield_dev(Handle& h, const cplx* E_dev, cplx beta, double omega, double mu0, cplx* H_dev);
+void hfield_multi_dev(Handle& h, int k, const cplx* E_dev, const cplx* betas, double omega, double mu0, cplx* H_dev);
+void mass_solve_multi(Handle& h, int k, const cplx* B, cplx* X);
 void functional_dev(Handle& h, int kind, const cplx* f0, const cplx* f1, const cplx* f2, const cplx* f3, int aux_kind,
                     bool aux_complex, const void* aux_dev, int n_sel, const int* elements_dev, int option,
                     std::complex<double>* out3);
