@@ -12,16 +12,15 @@
 // where (alpha, beta) depend only on the test function i, the point q and per-element metric
 // tensors  G = A^-1 A^-T,  G_eps = A^-1 diag(eps_x, eps_y) A^-T  (A = affine Jacobian).
 //
-// Mapping: one thread per triangle; one launch per kind of test function (template KI: Nedelec rows /
-// Lagrange rows), so the structurally-zero terms of every (test kind, trial kind) pair vanish at
-// compile time and there is no divergence.  A warp covers 32 consecutive triangles.  The thread walks
-// the test functions of its kind and keeps one row of the local block (NB accumulators) in registers.
+// Mapping: thread = (triangle, RPT test functions); blockIdx.y selects the row group; one launch per kind of
+// test function (template KI: Nedelec rows / Lagrange rows), so the structurally-zero terms of every
+// (test kind, trial kind) pair vanish at compile time and there is no divergence.  A warp covers 32
+// consecutive triangles.  The thread keeps its rows of the local block (RPT x NB accumulators) in registers.
 // The quadrature loop and the trial loop are fully unrolled (NQ and NB are template parameters); the
-// reference tables are warp-uniform constant-bank loads which the compiler hoists out of the row loop
-// into registers (ncu of the first version showed short-scoreboard / MIO-throttle stalls: one LDC per
-// DFMA).  Stores are SoA, out[(i*NB+j)*Ne + e]: every store instruction of a warp is one contiguous
-// 256 B (f64) / 512 B (c128) segment.  The kernel sits at the FP64 ridge: the HBM-store floor and the
-// FP64-pipe floor are both ~0.16 ms at 500k triangles (profiles/).
+// reference tables are warp-uniform constant-bank loads (LDCU) feeding DFMAs with uniform-register operands.
+// Stores are SoA, out[(i*NB+j)*Ne + e]: every store instruction of a warp is one contiguous 256 B (f64) /
+// 512 B (c128) segment.  The kernel sits at the FP64 ridge: the HBM-store floor and the FP64-pipe floor are
+// both ~0.16 ms at 500k triangles (profiles/).
 #include "handle.h"
 
 namespace fw {
@@ -87,38 +86,35 @@ struct Elem {
 
 // NQ > 0: compile-time number of quadrature points (loops fully unrolled); NQ == 0: run-time nq.
 // KI: kind of the test functions handled by this launch (0 = Nedelec rows, 1 = Lagrange rows).
-// EPT: triangles per thread (block b covers triangles [b*128*EPT, (b+1)*128*EPT)).
-template <int NB, int NQ, class S, int EPSKIND, int FORM, int KI, int EPT>
+// RPT: test functions (rows of the local block) a thread computes SIMULTANEOUSLY: blockIdx.y selects a group
+//      of RPT rows of kind KI.  Every reference-table value fetched (uniform constant load) feeds RPT DFMAs
+//      and the per-triangle prologue (dependent t -> p loads, metric tensors) is amortised over RPT rows --
+//      the ncu source page of the one-row variant showed 19 % of the stall samples on the constant loads
+//      and 22 % on the prologue.
+template <int NB, int NQ, class S, int EPSKIND, int FORM, int KI, int RPT>
 __global__ void __launch_bounds__(128) k_element_blocks(int ne, int nv, const double* __restrict__ p,
                                                         const int* __restrict__ t, const S* __restrict__ eps,
                                                         double k0, double mu_r, double inv_radius,
                                                         S* __restrict__ out) {
   constexpr int NT = (NB == 6) ? 3 : 8;
-  using T = scalar_traits<S>;
-  // blockIdx.y enumerates groups of `rpt` test functions of kind KI (the per-triangle prologue -- the
-  // dependent t -> p loads and the metric tensors -- is amortised over the rows of the group)
   constexpr int NROWS = KI == 0 ? NT : NB - NT;
-  const int rpt = (NROWS + (int)gridDim.y - 1) / (int)gridDim.y;
+  using T = scalar_traits<S>;
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  if (e >= ne) return;
   const double ik02 = 1.0 / (k0 * k0);
   const double imu = 1.0 / mu_r;
   const bool bend = inv_radius != 0.0;  // warp-uniform: radius=inf makes the bend factor exactly 1
   const int nq = NQ > 0 ? NQ : c_tab.nq;
 
-  int el[EPT];
-  Elem<S> E[EPT];
-#pragma unroll
-  for (int k = 0; k < EPT; ++k) {
-    const int e = (blockIdx.x * EPT + k) * 128 + threadIdx.x;
-    el[k] = e;
-    const int ec = e < ne ? e : ne - 1;  // out-of-range slots compute on a valid triangle, never store
-    const int v0 = t[ec], v1 = t[ne + ec], v2 = t[2 * ne + ec];
+  Elem<S> g;
+  {
+    const int v0 = t[e], v1 = t[ne + e], v2 = t[2 * ne + e];
     const double x0 = p[v0], y0 = p[nv + v0];
     const double a11 = p[v1] - x0, a21 = p[nv + v1] - y0;
     const double a12 = p[v2] - x0, a22 = p[nv + v2] - y0;
     const double det = a11 * a22 - a12 * a21;
     const double idet = 1.0 / det;
     const double id2 = idet * idet;
-    Elem<S>& g = E[k];
     g.x0 = x0, g.a11 = a11, g.a12 = a12;
     g.adet = fabs(det), g.idet = idet;
     // G = A^-1 A^-T (symmetric)
@@ -129,9 +125,9 @@ __global__ void __launch_bounds__(128) k_element_blocks(int ne, int nv, const do
     g.e0 = g.e1 = g.e2 = g.ge11 = g.ge12 = g.ge22 = T::zero();
     if (FORM == FORM_A) {
       if (EPSKIND == FW_EPS_P0) {
-        g.e0 = eps[ec];
+        g.e0 = eps[e];
       } else {
-        g.e0 = eps[3 * (size_t)ec], g.e1 = eps[3 * (size_t)ec + 1], g.e2 = eps[3 * (size_t)ec + 2];
+        g.e0 = eps[3 * (size_t)e], g.e1 = eps[3 * (size_t)e + 1], g.e2 = eps[3 * (size_t)e + 2];
       }
       if (EPSKIND == FW_EPS_VEC_P0) {
         // G_eps = A^-1 diag(eps_x, eps_y) A^-T for diagonal anisotropy (constant per element)
@@ -148,136 +144,139 @@ __global__ void __launch_bounds__(128) k_element_blocks(int ne, int nv, const do
   constexpr bool useAP = (FORM == FORM_A && KI == 0) || (FORM == FORM_C0 && KI == 0);
   constexpr bool useBP = (FORM == FORM_A && KI == 1) || (FORM == FORM_MASS && KI == 1);
 
-#pragma unroll 1
-  for (int rr = 0; rr < rpt; ++rr) {
-  const int irow = blockIdx.y * rpt + rr;  // rank of the test function among those of kind KI
-  if (irow >= NROWS) break;
-  const int i = c_tab.rows[KI][irow];
-  S acc[EPT][NB];
+  // the RPT rows of this thread (block-uniform); groups at the end may be short
+  int irow[RPT], il[RPT];
 #pragma unroll
-  for (int k = 0; k < EPT; ++k)
+  for (int r = 0; r < RPT; ++r) {
+    irow[r] = blockIdx.y * RPT + r;
+    il[r] = c_tab.rows[KI][irow[r] < NROWS ? irow[r] : NROWS - 1];
+  }
+
+  S acc[RPT][NB];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) acc[k][j] = T::zero();
+  for (int r = 0; r < RPT; ++r)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[r][j] = T::zero();
 
 #pragma unroll
   for (int q = 0; q < (NQ > 0 ? NQ : MAXQ); ++q) {
     if (NQ == 0 && q >= nq) break;
     const double Xq = c_tab.X[q], Yq = c_tab.Y[q], Wq = c_tab.W[q];
-    const double vxi = c_tab.vx[i][q], vyi = c_tab.vy[i][q], sci = c_tab.sc[i][q];
-    S aNx[EPT], aNy[EPT], aPx[EPT], aPy[EPT], bN[EPT], bP[EPT];
+    const double w = Wq * g.adet;
+    // bend factor f = 1 + x/R (waveguide.py:580-586); wf = w f, wrf = w / f
+    double wf = w, wrf = w;
+    if (bend) {
+      const double f = 1.0 + (g.x0 + g.a11 * Xq + g.a12 * Yq) * inv_radius;
+      wf = w * f;
+      wrf = w / f;
+    }
+    S ezq = g.e0;  // eps_z at the point (isotropic kinds)
+    if (FORM == FORM_A && EPSKIND == FW_EPS_DG_P1) ezq = g.e0 * (1.0 - Xq - Yq) + g.e1 * Xq + g.e2 * Yq;
+    if (FORM == FORM_A && EPSKIND == FW_EPS_VEC_P0) ezq = g.e2;
+    S aNx[RPT], aNy[RPT], aPx[RPT], aPy[RPT], bN[RPT], bP[RPT];
 #pragma unroll
-    for (int k = 0; k < EPT; ++k) {
-      const Elem<S>& g = E[k];
-      const double w = Wq * g.adet;
-      // bend factor f = 1 + x/R (waveguide.py:580-586); wf = w f, wrf = w / f
-      double wf = w, wrf = w;
-      if (bend) {
-        const double f = 1.0 + (g.x0 + g.a11 * Xq + g.a12 * Yq) * inv_radius;
-        wf = w * f;
-        wrf = w / f;
-      }
+    for (int r = 0; r < RPT; ++r) {
+      const int i = il[r];
+      const double vxi = c_tab.vx[i][q], vyi = c_tab.vy[i][q], sci = c_tab.sc[i][q];
       // G v_i (geometry only)
       const double gvx = g.g11 * vxi + g.g12 * vyi, gvy = g.g12 * vxi + g.g22 * vyi;
-      aNx[k] = aNy[k] = aPx[k] = aPy[k] = bN[k] = bP[k] = T::zero();
+      aNx[r] = aNy[r] = aPx[r] = aPy[r] = bN[r] = bP[r] = T::zero();
       if (FORM == FORM_A) {
-        // G_eps v_i and eps_z at the point
-        S gex, gey, ez;
-        if (EPSKIND == FW_EPS_P0) {
-          gex = g.e0 * gvx, gey = g.e0 * gvy, ez = g.e0;
-        } else if (EPSKIND == FW_EPS_DG_P1) {
-          ez = g.e0 * (1.0 - Xq - Yq) + g.e1 * Xq + g.e2 * Yq;
-          gex = ez * gvx, gey = ez * gvy;
+        // G_eps v_i
+        S gex, gey;
+        if (EPSKIND == FW_EPS_VEC_P0) {
+          gex = g.ge11 * vxi + g.ge12 * vyi, gey = g.ge12 * vxi + g.ge22 * vyi;
         } else {
-          gex = g.ge11 * vxi + g.ge12 * vyi, gey = g.ge12 * vxi + g.ge22 * vyi, ez = g.e2;
+          gex = ezq * gvx, gey = ezq * gvy;
         }
         if (KI == 0) {
           // test v_t: trial N -> curl curl / (mu_z k0^2) - eps_t e_t.v_t ; trial P -> grad e_z . v_t / mu_t
-          aNx[k] = gex * (-wf), aNy[k] = gey * (-wf);
-          bN[k] = T::from(wf * g.c_curl * sci, 0.0);
+          aNx[r] = gex * (-wf), aNy[r] = gey * (-wf);
+          bN[r] = T::from(wf * g.c_curl * sci, 0.0);
           const double c = wrf * imu;
-          aPx[k] = T::from(c * gvx, 0.0), aPy[k] = T::from(c * gvy, 0.0);
+          aPx[r] = T::from(c * gvx, 0.0), aPy[r] = T::from(c * gvy, 0.0);
         } else {
           // test v_z: trial N -> eps_t e_t . grad v_z ; trial P -> -eps_z e_z v_z k0^2
-          aNx[k] = gex * wf, aNy[k] = gey * wf;
-          bP[k] = ez * (-wrf * k0 * k0 * sci);
+          aNx[r] = gex * wf, aNy[r] = gey * wf;
+          bP[r] = ezq * (-wrf * k0 * k0 * sci);
         }
       } else if (FORM == FORM_B) {
         const double c = -wrf * imu * ik02;
-        aNx[k] = T::from(c * gvx, 0.0), aNy[k] = T::from(c * gvy, 0.0);
+        aNx[r] = T::from(c * gvx, 0.0), aNy[r] = T::from(c * gvy, 0.0);
       } else if (FORM == FORM_MASS) {
         if (KI == 0) {
-          aNx[k] = T::from(w * gvx, 0.0), aNy[k] = T::from(w * gvy, 0.0);
+          aNx[r] = T::from(w * gvx, 0.0), aNy[r] = T::from(w * gvy, 0.0);
         } else {
-          bP[k] = T::from(w * sci, 0.0);
+          bP[r] = T::from(w * sci, 0.0);
         }
       } else if (FORM == FORM_C1) {
         // i*beta * (e_x v_y - e_y v_x) = i*beta * idet * (u_hat x v_hat)
-        if (KI == 0) aNx[k] = T::from(w * g.idet * vyi, 0.0), aNy[k] = T::from(-w * g.idet * vxi, 0.0);
+        if (KI == 0) aNx[r] = T::from(w * g.idet * vyi, 0.0), aNy[r] = T::from(-w * g.idet * vxi, 0.0);
       } else {  // FORM_C0
         if (KI == 0) {
           // d_y e_z v_x - d_x e_z v_y = -idet * (g_hat x v_hat)
-          aPx[k] = T::from(-w * g.idet * vyi, 0.0), aPy[k] = T::from(w * g.idet * vxi, 0.0);
+          aPx[r] = T::from(-w * g.idet * vyi, 0.0), aPy[r] = T::from(w * g.idet * vxi, 0.0);
         } else {
           // curl(e_t) v_z = idet * c_hat_j * psi_i
-          bN[k] = T::from(w * g.idet * sci, 0.0);
+          bN[r] = T::from(w * g.idet * sci, 0.0);
         }
       }
     }
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
-      // one table fetch feeds EPT accumulators
+      // one table fetch feeds RPT accumulators
       const double tvx = c_tab.vx[j][q], tvy = c_tab.vy[j][q], tsc = c_tab.sc[j][q];
 #pragma unroll
-      for (int k = 0; k < EPT; ++k) {
+      for (int r = 0; r < RPT; ++r) {
         if (kind_of<NB>(j) == 0) {
           if (useAN) {
-            fma_(acc[k][j], aNx[k], tvx);
-            fma_(acc[k][j], aNy[k], tvy);
+            fma_(acc[r][j], aNx[r], tvx);
+            fma_(acc[r][j], aNy[r], tvy);
           }
-          if (useBN) fma_(acc[k][j], bN[k], tsc);
+          if (useBN) fma_(acc[r][j], bN[r], tsc);
         } else {
           if (useAP) {
-            fma_(acc[k][j], aPx[k], tvx);
-            fma_(acc[k][j], aPy[k], tvy);
+            fma_(acc[r][j], aPx[r], tvx);
+            fma_(acc[r][j], aPy[r], tvy);
           }
-          if (useBP) fma_(acc[k][j], bP[k], tsc);
+          if (useBP) fma_(acc[r][j], bP[r], tsc);
         }
       }
     }
   }
 #pragma unroll
-  for (int k = 0; k < EPT; ++k) {
-    const int e = el[k];
-    if (e >= ne) continue;
+  for (int r = 0; r < RPT; ++r) {
+    if (irow[r] >= NROWS) continue;
     if (FORM == FORM_B) {
       // compact NT x NT block: entry (rank(i), rank(j))
-      const int ri = irow;
 #pragma unroll
       for (int j = 0; j < NB; ++j)
-        if (kind_of<NB>(j) == 0) out[(size_t)(ri * NT + nrank_of<NB>(j)) * ne + e] = acc[k][j];
+        if (kind_of<NB>(j) == 0) out[(size_t)(irow[r] * NT + nrank_of<NB>(j)) * ne + e] = acc[r][j];
     } else {
+      const int i = il[r];
 #pragma unroll
-      for (int j = 0; j < NB; ++j) out[(size_t)(i * NB + j) * ne + e] = acc[k][j];
+      for (int j = 0; j < NB; ++j) out[(size_t)(i * NB + j) * ne + e] = acc[r][j];
     }
   }
-  }  // rows of this thread
 }
 
 template <int NB, int NQ, class S, int EPSKIND, int FORM>
 static void launch_form(Handle& h, const S* eps_dev, double k0, double mu_r, double inv_radius, S* blocks) {
   const Space& sp = h.sp;
   constexpr int NT = (NB == 6) ? 3 : 8;
-  constexpr int EPT = 1;
+  // rows computed simultaneously per thread.  Measured on B200 (500k triangles, f64): 1 row/thread 0.335 ms
+  // (76 registers), 4+3 rows/thread 0.358 ms (236 registers), 2 triangles/thread 0.36 ms: the kernel is
+  // issue-latency bound (FP64 pipe 43-65 % busy), not bound by constant loads or by HBM stores (a pure
+  // store kernel with the same pattern reaches 6.3-7.0 TB/s, scripts/microbench/store_bw.cu).
+  constexpr int RN = 1;
+  constexpr int RP = 1;
   dim3 block(128);
-  const int gx = cdiv(sp.ne, 128 * EPT);
-  // one launch per test-function kind: NT Nedelec rows, NB-NT Lagrange rows (bform has Nedelec rows only);
-  // grid.y = number of row groups (FW_K1_GROUPS, default 1: a thread walks all rows of its kind)
-  static const int groups = getenv("FW_K1_GROUPS") ? std::max(1, atoi(getenv("FW_K1_GROUPS"))) : 1;
-  const int gyN = std::min(groups, NT), gyP = std::min(groups, NB - NT);
-  k_element_blocks<NB, NQ, S, EPSKIND, FORM, 0, EPT><<<dim3(gx, gyN), block, 0, h.stream>>>(
+  const int gx = cdiv(sp.ne, 128);
+  // one launch per test-function kind (bform has Nedelec rows only)
+  k_element_blocks<NB, NQ, S, EPSKIND, FORM, 0, RN><<<dim3(gx, (NT + RN - 1) / RN), block, 0, h.stream>>>(
       sp.ne, sp.nv, sp.p.p, sp.t.p, eps_dev, k0, mu_r, inv_radius, blocks);
   if (FORM != FORM_B)
-    k_element_blocks<NB, NQ, S, EPSKIND, FORM, 1, EPT><<<dim3(gx, gyP), block, 0, h.stream>>>(
+    k_element_blocks<NB, NQ, S, EPSKIND, FORM, 1, RP><<<dim3(gx, (NB - NT + RP - 1) / RP), block, 0, h.stream>>>(
         sp.ne, sp.nv, sp.p.p, sp.t.p, eps_dev, k0, mu_r, inv_radius, blocks);
 }
 

@@ -386,7 +386,11 @@ struct GemmCfg<cplx> {
   static constexpr int KC = 16;
 };
 
-template <class S>
+// SCHUR = false: per-panel rank-32 update of everything that feeds later panels (all trailing entries with a
+//                 row or a column inside the pivot block); the boundary x boundary block S22 is skipped.
+// SCHUR = true : once per front after its last panel, S22 -= L21 U12 with the full inner dimension ns, so the
+//                 Schur complement (the bulk of the flops for nb >> ns) is read and written once.
+template <class S, bool SCHUR>
 __global__ void __launch_bounds__(256) k_lu_gemm(FrontTab T, const int* __restrict__ nodes, int kstep,
                                                  S* __restrict__ F) {
   constexpr int TM = 64, KC = GemmCfg<S>::KC;
@@ -394,16 +398,17 @@ __global__ void __launch_bounds__(256) k_lu_gemm(FrontTab T, const int* __restri
   __shared__ S Bs[KC][TM + 1];
   const int node = nodes[blockIdx.x];
   const int m = T.m[node], ns = T.ns[node];
-  const int k0 = kstep * PW;
+  const int k0 = SCHUR ? 0 : kstep * PW;
   if (k0 >= ns) return;
-  const int w = min(PW, ns - k0);
-  const int r0 = k0 + w;
+  const int w = SCHUR ? ns : min(PW, ns - k0);
+  const int r0 = SCHUR ? ns : k0 + w;
   const int nrem = m - r0;
   if (nrem <= 0) return;
   const int nt = (nrem + TM - 1) / TM;
   const int tile = blockIdx.y;
   if (tile >= nt * nt) return;
   const int ti = tile % nt, tj = tile / nt;
+  if (!SCHUR && r0 + ti * TM >= ns && r0 + tj * TM >= ns) return;  // tile entirely inside S22
   S* Fn = F + T.front_off[node];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   S acc[4][4];
@@ -445,7 +450,7 @@ __global__ void __launch_bounds__(256) k_lu_gemm(FrontTab T, const int* __restri
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int gr = rbase + tx * 4 + i;
-      if (gr < m) {
+      if (gr < m && (SCHUR || gr < ns || gc < ns)) {
         S* dst = Fn + gr + (long long)gc * m;
         *dst = *dst + acc[i][j];
       }
@@ -544,8 +549,15 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
       k_lu_swap_trsm<S><<<dim3(nfront, ctiles + rtiles), 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles);
       const int rem = max_m - (k * PW);  // upper bound of the trailing size
       const int nt = (rem + 63) / 64;
-      if (nt > 0) k_lu_gemm<S><<<dim3(nfront, nt * nt), 256, 0, s>>>(T, nodes, k, F);
+      if (nt > 0) k_lu_gemm<S, false><<<dim3(nfront, nt * nt), 256, 0, s>>>(T, nodes, k, F);
       launches += 3;
+    }
+    {
+      const int nt = (Sy.level_max_nb[lev] + 63) / 64;
+      if (nt > 0 && npan > 0) {
+        k_lu_gemm<S, true><<<dim3(nfront, nt * nt), 256, 0, s>>>(T, nodes, 0, F);
+        launches += 1;
+      }
     }
   }
   tr.mark("lu factor: levels");
