@@ -154,6 +154,28 @@ class Context:
         L.check(self.lib.fw_eigs(self._h, C.byref(p), L.ptr(lams), L.ptr(X), C.byref(st)))
         return lams, X, st.as_dict()
 
+    def eigs_csr(self, K, M, k, sigma, coords=None, v0=None, ncv=0, tol=0.0, maxiter=0, refine=0, leaf_elements=0):
+        """K x = lam M x on caller-assembled scipy CSR matrices (EigenSolver protocol, femwell/solver.py:87-142)."""
+        K = K.tocsr()
+        M = M.tocsr()
+        n = K.shape[0]
+        cx = np.iscomplexobj(K.data) or np.iscomplexobj(M.data)
+        conv = L.as_c128 if cx else L.as_f64
+        kd, md = conv(K.data), conv(M.data)
+        kp, ki, mp, mi = L.as_i32(K.indptr), L.as_i32(K.indices), L.as_i32(M.indptr), L.as_i32(M.indices)
+        keep = []
+        self.n = n
+        self._space_key = None
+        self.nnz_structural = None
+        p = self._eigs_params(k, sigma, None, v0, ncv, tol, maxiter, refine, leaf_elements, keep)
+        co = None if coords is None else L.as_f64(coords)
+        lams = np.empty(k, dtype=np.complex128)
+        X = np.empty((k, n), dtype=np.complex128)
+        st = L.FwEigsStats()
+        L.check(self.lib.fw_eigs_csr(self._h, n, L.ptr(kp), L.ptr(ki), L.ptr(kd), L.ptr(mp), L.ptr(mi), L.ptr(md),
+                                     int(cx), L.ptr(co), C.byref(p), L.ptr(lams), L.ptr(X), C.byref(st)))
+        return lams, X, st.as_dict()
+
     # ---------------------------------------------------------------- post-processing
     def postprocess(self, lams, X, k0, omega, mu0):
         k = len(lams)

@@ -136,6 +136,7 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
   sp.is_z.upload(isz.data(), isz.size(), h.stream);
   FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
   sp.valid = true;
+  h.generic.valid = false;
   h.has_symbolic = false;
   h.A.valid = h.B.valid = h.Mass.valid = h.C0.valid = h.C1.valid = false;
   h.lu.reset();
@@ -270,6 +271,26 @@ int fw_eigs(fw_handle* hh, const fw_eigs_params* prm, double* lams, double* X, f
   DevBuf<double> Xd;
   eigs_shift_invert(h, *prm, (std::complex<double>*)lams, Xd, st);
   Xd.download(X, (size_t)prm->k * h.sp.n * 2, h.stream);
+  FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
+  FW_API_END
+}
+
+int fw_eigs_csr(fw_handle* hh, int32_t n, const int32_t* K_indptr, const int32_t* K_indices, const void* K_data,
+                const int32_t* M_indptr, const int32_t* M_indices, const void* M_data, int32_t is_complex,
+                const double* coords, const fw_eigs_params* prm, double* lams, double* X, fw_eigs_stats* st) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && prm && lams && X, "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  h.tim = fw_timings{};
+  {
+    Timer t(h.stream);
+    setup_generic_csr(h, n, K_indptr, K_indices, K_data, M_indptr, M_indices, M_data, is_complex != 0, coords);
+    h.tim.upload_ms = t.stop();
+  }
+  DevBuf<double> Xd;
+  eigs_shift_invert(h, *prm, (std::complex<double>*)lams, Xd, st);
+  Xd.download(X, (size_t)prm->k * n * 2, h.stream);
   FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
   FW_API_END
 }

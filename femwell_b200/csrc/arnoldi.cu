@@ -603,7 +603,7 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
 }
 
 void eigs_shift_invert(Handle& h, const fw_eigs_params& prm, cd* lams, DevBuf<double>& X_dev, fw_eigs_stats* st) {
-  FW_REQUIRE(h.sp.valid && h.has_symbolic && h.A.valid && h.B.valid, "assemble A and B first");
+  FW_REQUIRE((h.sp.valid || h.generic.valid) && h.has_symbolic && h.A.valid && h.B.valid, "assemble A and B first");
   FW_REQUIRE(prm.k >= 1, "k must be >= 1");
   const int n = h.sp.n;
   std::vector<uint8_t> active((size_t)n, 1);

@@ -38,6 +38,15 @@ struct Space {
   bool valid = false;
 };
 
+// Clique cover of the matrix graph used by the nested-dissection analysis when no FE mesh is available
+// (generic CSR eigen-solver, fw_eigs_csr): every coupled pair of unknowns shares at least one clique.
+struct Connectivity {
+  int n = 0, nb = 0, ne = 0;
+  std::vector<int> edofs;      // [nb, ne]
+  std::vector<double> cx, cy;  // clique "centroids" (real or pseudo coordinates)
+  bool valid = false;
+};
+
 struct Handle {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -46,6 +55,7 @@ struct Handle {
   bool has_symbolic = false;
   bool eliminate_zeros = true;  // export semantics of scipy's coo.eliminate_zeros()
   Values A, B, Mass, C0, C1;
+  Connectivity generic;  // set by fw_eigs_csr instead of a space
   DevBuf<double> blocks;  // scratch: local element blocks (SoA [entry][Ne])
   // generic COO->CSR result
   Pattern coo_pat;

@@ -40,18 +40,24 @@ static void up64(DevBuf<long long>& d, const std::vector<int64_t>& v, cudaStream
 
 void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements) {
   const Space& sp = h.sp;
-  FW_REQUIRE(sp.valid, "space missing");
+  FW_REQUIRE(sp.valid || h.generic.valid, "space missing");
   h.lu.reset(new LU());
   LU& lu = *h.lu;
-  std::vector<double> cx(sp.ne), cy(sp.ne);
-  for (int e = 0; e < sp.ne; ++e) {
-    int a = sp.h_t[e], b = sp.h_t[sp.ne + e], c = sp.h_t[2 * (size_t)sp.ne + e];
-    cx[e] = (sp.h_p[a] + sp.h_p[b] + sp.h_p[c]) / 3.0;
-    cy[e] = (sp.h_p[sp.nv + a] + sp.h_p[sp.nv + b] + sp.h_p[sp.nv + c]) / 3.0;
-  }
   Trace tr(h.stream);
-  lu_symbolic_build(lu.sym, sp.n, sp.nb, sp.ne, sp.h_edofs.data(), cx.data(), cy.data(), active.data(),
-                    leaf_elements);
+  if (h.generic.valid) {
+    const Connectivity& c = h.generic;
+    lu_symbolic_build(lu.sym, c.n, c.nb, c.ne, c.edofs.data(), c.cx.data(), c.cy.data(), active.data(),
+                      leaf_elements);
+  } else {
+    std::vector<double> cx(sp.ne), cy(sp.ne);
+    for (int e = 0; e < sp.ne; ++e) {
+      int a = sp.h_t[e], b = sp.h_t[sp.ne + e], c = sp.h_t[2 * (size_t)sp.ne + e];
+      cx[e] = (sp.h_p[a] + sp.h_p[b] + sp.h_p[c]) / 3.0;
+      cy[e] = (sp.h_p[sp.nv + a] + sp.h_p[sp.nv + b] + sp.h_p[sp.nv + c]) / 3.0;
+    }
+    lu_symbolic_build(lu.sym, sp.n, sp.nb, sp.ne, sp.h_edofs.data(), cx.data(), cy.data(), active.data(),
+                      leaf_elements);
+  }
   tr.mark("lu analyse: host symbolic");
   lu.dev.reset(new LUDevice());
   LUDevice& d = *lu.dev;

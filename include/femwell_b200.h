@@ -130,6 +130,14 @@ typedef struct {
 } fw_eigs_stats;
 int fw_eigs(fw_handle* h, const fw_eigs_params* prm, double* lams, double* X, fw_eigs_stats* st);
 
+/* ---- the scikit-fem EigenSolver protocol on caller-assembled matrices (femwell/solver.py:87-142:
+ *      solver(K, M) -> (lams, xs) for K x = lam M x, shift-invert around sigma).  K, M: n x n CSR (f64 or both
+ *      c128); coords: optional [2, n] coordinates of the unknowns for the nested dissection (NULL: pseudo
+ *      coordinates from two breadth-first sweeps of the matrix graph).  X [k, n] c128, unit 2-norm.        */
+int fw_eigs_csr(fw_handle* h, int32_t n, const int32_t* K_indptr, const int32_t* K_indices, const void* K_data,
+                const int32_t* M_indptr, const int32_t* M_indices, const void* M_data, int32_t is_complex,
+                const double* coords, const fw_eigs_params* prm, double* lams, double* X, fw_eigs_stats* st);
+
 /* ---- sparse LU exposed for tests: factor (A_which*alpha + B_which*beta) and solve      */
 int fw_lu_factor_shifted(fw_handle* h, double sigma_re, double sigma_im, int32_t n_dirichlet,
                          const int32_t* dirichlet, int32_t leaf_elements);

@@ -396,3 +396,54 @@ def test_large_assembly_properties(ctx):
     assert abs(one_z @ (Mass @ one_z) - area) < 1e-10 * area
     assert abs(one_z @ ctx.spmv(2, one_z) - area) < 1e-10 * area
     assert nnz >= Mass.nnz
+
+
+# ----------------------------------------------------------------------------- EigenSolver protocol on generic CSR
+@pytest.mark.parametrize("order,n,cplx,with_coords,condensed", [(2, 12, False, False, False), (1, 20, False, True, True),
+                                                              (2, 10, True, False, False), (2, 24, False, False, True)])
+def test_solver_eigen_b200_protocol_matches_scipy(ctx, order, n, cplx, with_coords, condensed):
+    """solver(K, M) -> (lams, xs) on matrices assembled elsewhere (here: by the oracle), as skfem.solve would
+    call it (femwell/solver.py:87-142, waveguide.py:611-625)."""
+    from femwell_b200.solver import solver_eigen_b200
+
+    m, eps = strip_problem(n)
+    if cplx:
+        eps = eps.astype(complex)
+        eps[m.subdomains["clad"]] -= 0.03j
+    b = Basis(m, ElementTriP0(), intorder=4).with_element(mode_element(order))
+    k0 = 2 * np.pi / 1.55
+    A, B = _oracle_AB(m, b, 0, eps, k0)
+    K, M = (-A).tocsr(), (-B).tocsr()
+    coords = None
+    if condensed:  # what skfem's condense hands to the solver: the interior sub-matrices
+        I = np.setdiff1d(np.arange(b.N), b.get_dofs(None))
+        K, M = K[I][:, I], M[I][:, I]
+    sigma = k0**2 * np.max(eps.real) * 1.1
+    if with_coords:
+        # dof coordinates: vertices, facet midpoints (order 1: Nv + Nf unknowns)
+        xy = np.concatenate([m.p, m.facet_midpoints()], axis=1)
+        coords = xy[:, I] if condensed else xy
+    solver = solver_eigen_b200(k=3, sigma=sigma, coords=coords)
+    lams, xs = solver(K, M)
+    ref, _ = spla.eigs(K, M=M, k=3, sigma=sigma, v0=np.random.default_rng(0).uniform(-1, 1, K.shape[0]))
+    assert xs.shape == (K.shape[0], 3)
+    for i, lam in enumerate(lams):
+        assert np.min(abs(ref - lam)) < 1e-9 * abs(lam)
+        x = xs[:, i]
+        assert np.linalg.norm(K @ x - lam * (M @ x)) < 1e-9 * np.linalg.norm(K @ x)
+        assert abs(np.linalg.norm(x) - 1) < 1e-12
+    assert solver.stats["nconv"] == 3
+
+
+def test_solver_eigen_b200_generic_stencil(ctx):
+    """not an FE matrix at all: 2-D 5-point Laplacian pencil with a diagonal mass matrix."""
+    from femwell_b200.solver import solver_eigen_b200
+
+    nx = 40
+    T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(nx, nx))
+    K = (sp.kron(sp.eye(nx), T) + sp.kron(T, sp.eye(nx))).tocsr()
+    M = sp.diags(np.linspace(1.0, 2.0, nx * nx)).tocsr()
+    lams, xs = solver_eigen_b200(k=4, sigma=0.05)(K, M)
+    ref = spla.eigs(K, M=M, k=4, sigma=0.05, return_eigenvectors=False)
+    for lam in lams:
+        assert np.min(abs(ref - lam)) < 1e-10 * abs(lam)
