@@ -199,3 +199,38 @@ def test_lu_analysis_drives_a_correct_multifrontal_solve(order, n, leaf, dirichl
     assert np.all(x[act == 0] == 0)
     xs = spla.splu(OPc.tocsc()).solve(rhs[I])
     assert np.linalg.norm(x[I] - xs) < 1e-10 * np.linalg.norm(xs)
+
+
+# ----------------------------------------------------------------------------- scikit-fem facing bridge (duck-typed)
+def test_bridge_extracts_arrays_from_duck_typed_basis():
+    from types import SimpleNamespace
+
+    from femwell_b200 import bridge
+    from femwell_b200.element import EPS_DG_P1, eps_kind_of
+
+    m, eps = strip_problem(6)
+
+    class ElementDG:  # same class names as scikit-fem's
+        def __init__(self, elem):
+            self.elem = elem
+
+    class ElementTriP1:
+        pass
+
+    sk_mesh = SimpleNamespace(p=m.p, t=m.t, subdomains={"core": m.subdomains["core"]}, boundaries={"left": m.boundaries["left"]})
+    mm = bridge.mesh_from_skfem(sk_mesh)
+    assert np.array_equal(mm.t, m.t) and np.array_equal(mm.facets, m.facets)
+    assert np.array_equal(mm.subdomains["core"], m.subdomains["core"])
+    assert eps_kind_of(bridge._eps_element(ElementDG(ElementTriP1()))) == EPS_DG_P1
+    # lbasis-style table extraction reproduces the built-in tables when fed the built-in basis
+    X, W = triangle_quadrature(4)
+    tb = element_tables(2, X, W)
+
+    class FakeElem:
+        def lbasis(self, Xq, i):
+            f = SimpleNamespace(value=tb.vec[i], curl=tb.sc[i]) if tb.kind[i] == 0 else None
+            g = SimpleNamespace(value=tb.sc[i], grad=tb.vec[i]) if tb.kind[i] == 1 else None
+            return (f, g)
+
+    kind, vec, sc = bridge.tables_from_lbasis(FakeElem(), X, 2)
+    assert np.array_equal(kind, tb.kind) and np.allclose(vec, tb.vec) and np.allclose(sc, tb.sc)
