@@ -93,6 +93,12 @@ class Basis:
     @property
     def element_dofs(self) -> np.ndarray:
         """int32 (Nbfun, Ne): vertex dofs, facet dofs, interior dofs."""
+        if self._dofs is None and self.is_mode_basis:
+            # the numbering depends on (mesh, order) only: share it between the Basis objects that
+            # compute_modes re-creates on every call (sweeps on one mesh)
+            cache = self.mesh.__dict__.setdefault("_dof_cache", {})
+            if self.elem.order in cache:
+                self._dofs = cache[self.elem.order]
         if self._dofs is None:
             m = self.mesh
             nv, nf, ne = m.nvertices, m.nfacets, m.nelements
@@ -112,6 +118,8 @@ class Basis:
                 e = np.arange(ne, dtype=np.int64)
                 ed = e[None, :] if kind == EPS_P0 else np.stack([3 * e, 3 * e + 1, 3 * e + 2])
             self._dofs = np.ascontiguousarray(ed, dtype=np.int32)
+            if self.is_mode_basis:
+                self.mesh.__dict__.setdefault("_dof_cache", {})[self.elem.order] = self._dofs
         return self._dofs
 
     def zeros(self, dtype=np.float64) -> np.ndarray:

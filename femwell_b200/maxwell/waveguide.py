@@ -235,8 +235,8 @@ def compute_modes(
                 basis_epsilon_r=basis_epsilon_r,
                 epsilon_r=epsilon_r,
                 basis=basis,
-                E=E[i].copy(),
-                H=H[i].copy(),
+                E=E[i],  # row views of the (k, N) result arrays (contiguous, no extra host copy)
+                H=H[i],
             )
             for i in range(num_modes)
         ],
