@@ -444,6 +444,11 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
     const int kk = std::min(k, me);
     for (int i = 0; i < kk; ++i)
       if (resid[order[i]] <= tol * std::max(eps23, std::abs(theta[order[i]]))) ++nconv;
+    if (getenv("FW_TRACE")) {
+      fprintf(stderr, "[fw-trace] arnoldi cycle %d (ops %d): rel. residual estimates", restarts, n_op);
+      for (int i = 0; i < kk; ++i) fprintf(stderr, " %.2e", resid[order[i]] / std::abs(theta[order[i]]));
+      fprintf(stderr, "\n");
+    }
     if (nconv >= kk || me < m || restarts >= maxrestart) {
       done = true;
       break;

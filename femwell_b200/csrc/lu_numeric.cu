@@ -145,9 +145,8 @@ __global__ void __launch_bounds__(256) k_lu_extend_add(FrontTab T, const int* __
   if (c < 0) return;
   const int mc = T.m[c], nsc = T.ns[c], nbc = mc - nsc;
   const int nt = (nbc + 31) >> 5;
-  const int tile = blockIdx.y;
-  if (tile >= nt * nt) return;
-  const int ti = tile % nt, tj = tile / nt;
+  const int ti = blockIdx.y, tj = blockIdx.z;  // 2-D tile index (each <= 65535)
+  if (ti >= nt || tj >= nt) return;
   const int mp = T.m[p];
   const int* rel = T.rel + T.blist_off[c];
   const S* Fc = F + T.front_off[c];
@@ -411,9 +410,8 @@ __global__ void __launch_bounds__(256) k_lu_gemm(FrontTab T, const int* __restri
   const int nrem = m - r0;
   if (nrem <= 0) return;
   const int nt = (nrem + TM - 1) / TM;
-  const int tile = blockIdx.y;
-  if (tile >= nt * nt) return;
-  const int ti = tile % nt, tj = tile / nt;
+  const int ti = blockIdx.y, tj = blockIdx.z;
+  if (ti >= nt || tj >= nt) return;
   if (!SCHUR && r0 + ti * TM >= ns && r0 + tj * TM >= ns) return;  // tile entirely inside S22
   S* Fn = F + T.front_off[node];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -538,7 +536,7 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
       const int cnb = Sy.level_max_nb[lev + 1];
       const int nt = (cnb + 31) / 32;
       if (nt > 0) {
-        dim3 grid(nfront, nt * nt);
+        dim3 grid(nfront, nt, nt);
         k_lu_extend_add<S><<<grid, 256, 0, s>>>(T, nodes, 0, F);
         k_lu_extend_add<S><<<grid, 256, 0, s>>>(T, nodes, 1, F);
         launches += 2;
@@ -555,13 +553,13 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
       k_lu_swap_trsm<S><<<dim3(nfront, ctiles + rtiles), 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles);
       const int rem = max_m - (k * PW);  // upper bound of the trailing size
       const int nt = (rem + 63) / 64;
-      if (nt > 0) k_lu_gemm<S, false><<<dim3(nfront, nt * nt), 256, 0, s>>>(T, nodes, k, F);
+      if (nt > 0) k_lu_gemm<S, false><<<dim3(nfront, nt, nt), 256, 0, s>>>(T, nodes, k, F);
       launches += 3;
     }
     {
       const int nt = (Sy.level_max_nb[lev] + 63) / 64;
       if (nt > 0 && npan > 0) {
-        k_lu_gemm<S, true><<<dim3(nfront, nt * nt), 256, 0, s>>>(T, nodes, 0, F);
+        k_lu_gemm<S, true><<<dim3(nfront, nt, nt), 256, 0, s>>>(T, nodes, 0, F);
         launches += 1;
       }
     }
