@@ -420,6 +420,29 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
       k_scale_copy<T><<<cdiv(n, 256), 256, 0, s>>>(w, Vb + (int64_t)(j + 1) * ld, n, 1.0 / beta);
       h.tim.kernel_launches += 1;
       tw_cgs += Trace::now() - tw1;
+      // ---- early exit: test the Ritz estimates of the current (j+1)-dimensional decomposition every step
+      // (ARPACK only looks at a full basis; for k = 1..2 -- sweeps -- that wastes up to half of the OP calls).
+      // The last row of the decomposition is beta e_{j+1}^T here, so the estimate is beta |y_i[j]|.
+      const int mc = j + 1;
+      if (mc < m_eff && mc >= k + 2 && mc - j0 >= 2) {
+        for (int c = 0; c < mc; ++c)
+          for (int i = 0; i < mc; ++i) Hm[(size_t)c * mc + i] = Hat(i, c);
+        if (dense_eig(mc, Hm.data(), theta.data(), Y.data())) {
+          for (int i = 0; i < mc; ++i) order[i] = i;
+          std::sort(order.begin(), order.begin() + mc,
+                    [&](int a, int b) { return std::abs(theta[a]) > std::abs(theta[b]); });
+          int okc = 0;
+          for (int i = 0; i < k; ++i) {
+            const int o = order[i];
+            const double est = beta * std::abs(Y[(size_t)o * mc + (mc - 1)]);
+            if (est <= tol * std::max(3.666852862501036e-11, std::abs(theta[o]))) ++okc;
+          }
+          if (okc >= k) {
+            m_eff = mc;  // the Ritz section below re-evaluates this block and finishes
+            break;
+          }
+        }
+      }
     }
     // ---- Ritz pairs of the m_eff x m_eff projected matrix
     const double tw2 = Trace::now();

@@ -47,6 +47,8 @@ struct LU {
   bool is_complex = false;
   bool factored = false;
   int perturbed = 0;
+  std::vector<uint8_t> active_key;  // the analysis is reusable while mesh, Dirichlet set and leaf size stay
+  int leaf_key = 0;
   std::unique_ptr<LUDevice> dev;
   LU();
   ~LU();

@@ -41,8 +41,15 @@ static void up64(DevBuf<long long>& d, const std::vector<int64_t>& v, cudaStream
 void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements) {
   const Space& sp = h.sp;
   FW_REQUIRE(sp.valid || h.generic.valid, "space missing");
+  if (h.lu && h.lu->dev && h.lu->leaf_key == leaf_elements && h.lu->active_key == active) {
+    // same mesh (fw_set_space / fw_eigs_csr reset h.lu), same Dirichlet set: wavelength / epsilon sweeps
+    h.lu->factored = false;
+    return;
+  }
   h.lu.reset(new LU());
   LU& lu = *h.lu;
+  lu.active_key = active;
+  lu.leaf_key = leaf_elements;
   Trace tr(h.stream);
   if (h.generic.valid) {
     const Connectivity& c = h.generic;
@@ -529,6 +536,10 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
   const size_t panel_smem = (size_t)PW * (HWIN + 1) * sizeof(S);
   FW_CHECK_CUDA(cudaFuncSetAttribute(k_lu_panel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
   int64_t launches = 3;
+  // trailing blocks at least this wide use the 128x128 register-tiled GEMM (FW_BIG_GEMM_MIN to experiment)
+  const char* tenv = getenv("FW_TRACE");
+  const bool trace2 = tenv && atoi(tenv) >= 2;
+  static const int big_gemm_min = getenv("FW_BIG_GEMM_MIN") ? atoi(getenv("FW_BIG_GEMM_MIN")) : 384;
   for (int lev = Sy.n_levels - 1; lev >= 0; --lev) {
     const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
     const int* nodes = d.level_nodes.p + Sy.level_start[lev];
@@ -553,16 +564,25 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
       k_lu_swap_trsm<S><<<dim3(nfront, ctiles + rtiles), 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles);
       const int rem = max_m - (k * PW);  // upper bound of the trailing size
       const int nt = (rem + 63) / 64;
-      if (nt > 0) k_lu_gemm<S, false><<<dim3(nfront, nt, nt), 256, 0, s>>>(T, nodes, k, F);
+      if (rem >= big_gemm_min)
+        lu_gemm_big_launch<S>(T, nodes, nfront, k, F, rem, false, s);
+      else if (nt > 0)
+        k_lu_gemm<S, false><<<dim3(nfront, nt, nt), 256, 0, s>>>(T, nodes, k, F);
       launches += 3;
     }
+    if (trace2) tr.mark(("  factor lev " + std::to_string(lev) + " panels (" + std::to_string(npan) + " steps, " +
+                         std::to_string(nfront) + " fronts, max m " + std::to_string(max_m) + ")").c_str());
     {
       const int nt = (Sy.level_max_nb[lev] + 63) / 64;
       if (nt > 0 && npan > 0) {
-        k_lu_gemm<S, true><<<dim3(nfront, nt, nt), 256, 0, s>>>(T, nodes, 0, F);
+        if (Sy.level_max_nb[lev] >= big_gemm_min)
+          lu_gemm_big_launch<S>(T, nodes, nfront, 0, F, Sy.level_max_nb[lev], true, s);
+        else
+          k_lu_gemm<S, true><<<dim3(nfront, nt, nt), 256, 0, s>>>(T, nodes, 0, F);
         launches += 1;
       }
     }
+    if (trace2) tr.mark(("  factor lev " + std::to_string(lev) + " schur gemm").c_str());
   }
   tr.mark("lu factor: levels");
   k_lu_compose_perm<<<cdiv(Sy.n_nodes, 64), 64, 0, s>>>(T, Sy.n_nodes, d.piv.p, d.rowperm.p);
