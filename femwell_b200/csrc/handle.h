@@ -63,11 +63,17 @@ struct Handle {
   // compacted export scratch
   DevBuf<uint32_t> scan_tmp, scan_tmp2;
   std::unique_ptr<LU> lu;
+  // pinned staging ring for large device -> pageable-host copies (results E, H)
+  void* pinned[2] = {nullptr, nullptr};
+  cudaEvent_t pinned_ev[2] = {nullptr, nullptr};
   double lu_sigma_re = 0, lu_sigma_im = 0;
   fw_timings tim{};
   Handle();
   ~Handle();
 };
+
+// device -> pageable host through the pinned ring, chunk copies overlapped with a threaded host memcpy (api.cu)
+void download_staged(Handle& h, void* host_dst, const void* dev_src, size_t bytes);
 
 // ---- scan / sort / COO->CSR (sort.cu)
 void exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, DevBuf<uint32_t>& tmp, cudaStream_t s);

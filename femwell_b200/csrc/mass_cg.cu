@@ -234,7 +234,7 @@ void mass_solve_multi(Handle& h, int k, const cplx* B, cplx* X) {
       FW_CHECK_CUDA(cudaStreamSynchronize(s));
       bool done = true;
       for (int i = 0; i < k; ++i)
-        if (!(rr[i] <= 1e-28 * bnorm2[i])) done = false;  // ||r|| <= 1e-14 ||b||
+        if (!(rr[i] <= 1e-26 * bnorm2[i])) done = false;  // ||r|| <= 1e-13 ||b|| (the reference's H carries complex64 rounding, 1e-7)
       if (done) break;
     }
   }
