@@ -195,6 +195,12 @@ class Context:
                                    C.c_double(omega), C.c_double(mu0), L.ptr(H)))
         return H
 
+    def intensity(self, E, H):
+        E, H = L.as_c128(E), L.as_c128(H)
+        out = np.empty(3 * self.basis.mesh.nelements, dtype=np.float64)
+        L.check(self.lib.fw_intensity(self._h, L.ptr(E), L.ptr(H), L.ptr(out)))
+        return out
+
     def functional(self, kind, fields, aux=None, aux_kind=0, elements=None, option=0):
         fs = [None if f is None else L.as_c128(f) for f in fields] + [None] * (4 - len(fields))
         a = None

@@ -456,6 +456,23 @@ int fw_hfield(fw_handle* hh, const double* E, double beta_re, double beta_im, do
   FW_API_END
 }
 
+int fw_intensity(fw_handle* hh, const double* E, const double* H, double* out) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && E && H && out, "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  FW_REQUIRE(h.sp.valid, "space missing");
+  const size_t cnt = (size_t)h.sp.n * 2;
+  DevBuf<double> dE, dH, dout;
+  dE.upload(E, cnt, h.stream);
+  dH.upload(H, cnt, h.stream);
+  dout.alloc((size_t)3 * h.sp.ne);
+  intensity_dev(h, (const cplx*)dE.p, (const cplx*)dH.p, dout.p);
+  dout.download(out, (size_t)3 * h.sp.ne, h.stream);
+  FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
+  FW_API_END
+}
+
 int fw_functional(fw_handle* hh, int32_t kind, const double* f0, const double* f1, const double* f2,
                   const double* f3, int32_t aux_kind, int32_t aux_is_complex, const void* aux, int32_t n_sel,
                   const int32_t* elements, int32_t option, double* out) {

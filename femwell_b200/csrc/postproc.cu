@@ -420,6 +420,84 @@ void functional_dev(Handle& h, int kind, const cplx* f0, const cplx* f1, const c
   h.tim.kernel_launches += 2;
 }
 
+// ------------------------------------------------------------------------------ intensity (a16)
+// Mode.calculate_intensity (waveguide.py:260-280): I = 0.5 Re(Ex Hy* - Ey Hx*) at the quadrature points,
+// L2-projected onto discontinuous P1 (one 3x3 solve per triangle, dof = 3 e + a).
+template <int NB>
+__global__ void __launch_bounds__(128) k_intensity(int ne, int nv, const double* __restrict__ p,
+                                                   const int* __restrict__ t, const int* __restrict__ edofs,
+                                                   const cplx* __restrict__ E, const cplx* __restrict__ Hf,
+                                                   double* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int v0 = t[e], v1 = t[ne + e], v2 = t[2 * ne + e];
+  const double x0 = p[v0], y0 = p[nv + v0];
+  const double a11 = p[v1] - x0, a21 = p[nv + v1] - y0;
+  const double a12 = p[v2] - x0, a22 = p[nv + v2] - y0;
+  const double det = a11 * a22 - a12 * a21;
+  const double idet = 1.0 / det, adet = fabs(det);
+  cplx ce[NB], ch[NB];
+#pragma unroll
+  for (int l = 0; l < NB; ++l) {
+    const int d = edofs[(size_t)l * ne + e];
+    ce[l] = E[d];
+    ch[l] = Hf[d];
+  }
+  double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, b[3] = {0, 0, 0};
+  const int nq = c_ptab.nq;
+  for (int q = 0; q < nq; ++q) {
+    const double w = c_ptab.W[q] * adet;
+    cplx sx{0, 0}, sy{0, 0}, hx{0, 0}, hy{0, 0};
+#pragma unroll
+    for (int l = 0; l < NB; ++l) {
+      if (c_ptab.kind[l] == 0) {
+        fma_(sx, ce[l], c_ptab.vx[l][q]);
+        fma_(sy, ce[l], c_ptab.vy[l][q]);
+        fma_(hx, ch[l], c_ptab.vx[l][q]);
+        fma_(hy, ch[l], c_ptab.vy[l][q]);
+      }
+    }
+    const cplx ex = (sx * a22 - sy * a21) * idet, ey = (sy * a11 - sx * a12) * idet;
+    const cplx bx = (hx * a22 - hy * a21) * idet, by = (hy * a11 - hx * a12) * idet;
+    // 0.5 Re(Ex conj(Hy) - Ey conj(Hx))
+    const double f = 0.5 * ((ex.re * by.re + ex.im * by.im) - (ey.re * bx.re + ey.im * bx.im));
+    const double lam[3] = {1.0 - c_ptab.X[q] - c_ptab.Y[q], c_ptab.X[q], c_ptab.Y[q]};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      b[a] += w * lam[a] * f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) M[a][c] += w * lam[a] * lam[c];
+    }
+  }
+  // 3x3 solve (Cramer; the local mass matrix is SPD)
+  const double c00 = M[1][1] * M[2][2] - M[1][2] * M[2][1];
+  const double c01 = M[1][2] * M[2][0] - M[1][0] * M[2][2];
+  const double c02 = M[1][0] * M[2][1] - M[1][1] * M[2][0];
+  const double dd = M[0][0] * c00 + M[0][1] * c01 + M[0][2] * c02;
+  const double id = 1.0 / dd;
+  const double x = (b[0] * c00 + b[1] * (M[0][2] * M[2][1] - M[0][1] * M[2][2]) +
+                    b[2] * (M[0][1] * M[1][2] - M[0][2] * M[1][1])) * id;
+  const double y = (b[0] * c01 + b[1] * (M[0][0] * M[2][2] - M[0][2] * M[2][0]) +
+                    b[2] * (M[0][2] * M[1][0] - M[0][0] * M[1][2])) * id;
+  const double z = (b[0] * c02 + b[1] * (M[0][1] * M[2][0] - M[0][0] * M[2][1]) +
+                    b[2] * (M[0][0] * M[1][1] - M[0][1] * M[1][0])) * id;
+  out[3 * (size_t)e] = x;
+  out[3 * (size_t)e + 1] = y;
+  out[3 * (size_t)e + 2] = z;
+}
+
+void intensity_dev(Handle& h, const cplx* E, const cplx* Hf, double* out) {
+  const Space& sp = h.sp;
+  FW_REQUIRE(sp.valid, "space missing");
+  upload_ptab(h);
+  if (sp.nb == 6)
+    k_intensity<6><<<cdiv(sp.ne, 128), 128, 0, h.stream>>>(sp.ne, sp.nv, sp.p.p, sp.t.p, sp.edofs.p, E, Hf, out);
+  else
+    k_intensity<14><<<cdiv(sp.ne, 128), 128, 0, h.stream>>>(sp.ne, sp.nv, sp.p.p, sp.t.p, sp.edofs.p, E, Hf, out);
+  FW_CHECK_CUDA(cudaGetLastError());
+  h.tim.kernel_launches += 1;
+}
+
 // waveguide.py:627-639: un-scale E_z, recover H, power-normalise
 void postprocess_modes_dev(Handle& h, int k, const cd* lams, const double* X_dev, double k0, double omega, double mu0,
                            double* E_dev, double* H_dev, cd* powers) {

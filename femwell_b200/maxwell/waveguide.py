@@ -144,6 +144,14 @@ class Mode:
                                          aux_kind=eps_kind_of(self.basis_epsilon_r.elem), elements=sel)
         return speed_of_light * epsilon_0 * o[0]
 
+    def calculate_intensity(self):
+        """Intensity 0.5 Re(E x H*)_z projected onto discontinuous P1 (waveguide.py:260-280).
+        Returns ``(basis2, intensity2)`` like the reference."""
+        from ..element import ElementDG
+
+        basis2 = self.basis.with_element(ElementDG(ElementTriP1()))
+        return basis2, _bind(self.basis).intensity(self.E, self.H)
+
     def calculate_pertubated_neff(self, delta_epsilon):
         return self.n_eff + self.calculate_coupling_coefficient(self, delta_epsilon) * epsilon_0 * speed_of_light * 0.5
 

@@ -159,6 +159,10 @@ int fw_functional(fw_handle* h, int32_t kind, const double* f0, const double* f1
                   const double* f3, int32_t aux_kind, int32_t aux_is_complex, const void* aux,
                   int32_t n_sel, const int32_t* elements, int32_t option, double* out);
 
+/* ---- a16: Mode.calculate_intensity (waveguide.py:260-280): 0.5 Re(Ex Hy* - Ey Hx*) at the quadrature points,
+ *      L2-projected onto discontinuous P1.  E, H [n_dofs] c128; out [3*Ne] f64, dof = 3*e + a.          */
+int fw_intensity(fw_handle* h, const double* E, const double* H, double* out);
+
 /* ---- whole path with HOST buffers (the call the Python shim makes for compute_modes) */
 typedef struct {
   double wavelength, mu_r, radius;

@@ -369,6 +369,20 @@ def confinement_factor(p, t, dofs, order, X, W, E, eps_q, subset):
     return SPEED_OF_LIGHT * EPSILON_0 * np.sum(val * dxw)
 
 
+def calculate_intensity(p, t, dofs, order, X, W, E, H):
+    """waveguide.py:260-280: 0.5 Re(Ex Hy* - Ey Hx*) at the quadrature points projected onto DG-P1
+    (basis2.project: per-element mass solve with the basis quadrature)."""
+    fns, _, dx = physical_basis(order, p, t, X)
+    dxw = dx * W[None, :]
+    et, _ = interpolate_mode(fns, dofs, E)
+    ht, _ = interpolate_mode(fns, dofs, np.conj(H))
+    inten = 0.5 * np.real(et[0] * ht[1] - et[1] * ht[0])  # (Ne, nq)
+    lam = np.stack([1 - X[0] - X[1], X[0], X[1]])  # (3, nq)
+    M = np.einsum("eq,aq,bq->eab", dxw, lam, lam)
+    b = np.einsum("eq,aq,eq->ea", dxw, lam, inten)
+    return np.linalg.solve(M, b[:, :, None])[:, :, 0].reshape(-1)
+
+
 # ----------------------------------------------------------------------------- driver
 @dataclass
 class OracleModes:

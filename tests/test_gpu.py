@@ -358,6 +358,11 @@ def test_hfield_and_functionals_match_oracle(ctx):
     cf = md.calculate_confinement_factor("core")
     assert abs(cf - cf_ref) < 1e-10 * abs(cf_ref)
     assert abs(md.calculate_pertubated_neff(deps) - md.n_eff) > 0
+    # a16: intensity projected onto DG-P1
+    basis2, inten = md.calculate_intensity()
+    inten_ref = fo.calculate_intensity(*args, md.E, md.H)
+    assert inten.shape == (3 * m.nelements,) and basis2.N == 3 * m.nelements
+    assert np.linalg.norm(inten - inten_ref) < 1e-10 * np.linalg.norm(inten_ref)
 
 
 def test_argument_validation(ctx):
