@@ -366,6 +366,7 @@ static void assemble_ab_typed(Handle& h, int eps_kind, const void* eps_host, dou
   make_b_lut(sp, lut);
   DevBuf<int> lut_dev;
   lut_dev.upload(lut.data(), lut.size(), s);
+  build_slot_list(h, h.pat, lut_dev.p, sp.ne);  // once per symbolic pattern
   const Pattern& pat = h.pat;
   for (Values* v : {&h.A, &h.B}) {
     v->is_complex = scalar_traits<S>::is_complex;
@@ -376,7 +377,8 @@ static void assemble_ab_typed(Handle& h, int eps_kind, const void* eps_host, dou
   {
     Timer tr(s);
     reduce_onto_pattern<S>(pat, bA, nullptr, 0, sp.ne, (S*)h.A.v.p, h.A.flag.p, s);
-    reduce_onto_pattern<S>(pat, bB, lut_dev.p, (int)lut.size(), sp.ne, (S*)h.B.v.p, h.B.flag.p, s);
+    reduce_onto_pattern<S>(pat, bB, lut_dev.p, (int)lut.size(), sp.ne, (S*)h.B.v.p, h.B.flag.p, s, pat.tt_slots.p,
+                           pat.n_tt);
     h.tim.reduce_ms = tr.stop();
     h.tim.kernel_launches += 2;
   }

@@ -15,6 +15,8 @@ struct Pattern {
   DevBuf<int> indices;    // [nnz]
   DevBuf<uint32_t> perm;  // [n_coo]  source COO index of sorted position
   DevBuf<uint32_t> seg;   // [nnz+1]  first sorted position of every CSR slot
+  DevBuf<int> tt_slots;   // slots of the Nedelec x Nedelec sub-pattern (built on first use)
+  int64_t n_tt = -1;
 };
 
 // values on a Pattern (+ "any non-zero contribution" flags for eliminate_zeros parity)
@@ -82,7 +84,8 @@ void build_pattern_from_keys(Pattern& pat, DevBuf<uint64_t>& keys, DevBuf<uint32
 void symbolic_space(Handle& h);
 template <class S>
 void reduce_onto_pattern(const Pattern& pat, const S* coo_vals, const int* lut, int lut_n, int64_t stride,
-                         S* out, uint8_t* flag, cudaStream_t s);
+                         S* out, uint8_t* flag, cudaStream_t s, const int* slots = nullptr, int64_t nslots = 0);
+void build_slot_list(Handle& h, Pattern& pat, const int* lut_dev, int64_t stride);
 int64_t count_kept(Handle& h, const Pattern& pat, Values& val);
 void export_compacted(Handle& h, const Pattern& pat, Values& val, int* indptr, int* indices, void* data);
 void coo_to_csr(Handle& h, int n_rows, int64_t n_entries, const int* rows, const int* cols, const void* data,
