@@ -32,8 +32,16 @@ struct Tables {
   int rows[2][MAXNB];  // local dofs of kind 0 (Nedelec) / 1 (Lagrange), in ascending order
   double vx[MAXNB][MAXQ], vy[MAXNB][MAXQ], sc[MAXNB][MAXQ];
   double X[MAXQ], Y[MAXQ], W[MAXQ];
+  int nrank[MAXNB];  // rank of a Nedelec dof among the Nedelec dofs
 };
 __constant__ Tables c_tab;
+
+// Quadrature sums of products of reference tables (constant-coefficient fast path, see k_element_blocks_const):
+//   T11 = sum_q W vx_i vx_j,  T12 = sum_q W (vx_i vy_j + vy_i vx_j),  T22 = sum_q W vy_i vy_j,  CC = sum_q W sc_i sc_j
+struct PairTables {
+  double T11[MAXNB][MAXNB], T12[MAXNB][MAXNB], T22[MAXNB][MAXNB], CC[MAXNB][MAXNB];
+};
+__constant__ PairTables c_pair;
 
 void upload_tables(Handle& h) {
   const Space& sp = h.sp;
@@ -56,9 +64,25 @@ void upload_tables(Handle& h) {
     t.Y[q] = sp.X[sp.nq + q];
     t.W[q] = sp.W[q];
   }
+  for (int l = 0, r = 0; l < sp.nb; ++l) t.nrank[l] = sp.kind[l] == 0 ? r++ : 0;
+  PairTables pt;
+  memset(&pt, 0, sizeof(pt));
+  for (int i = 0; i < sp.nb; ++i)
+    for (int j = 0; j < sp.nb; ++j) {
+      double s11 = 0, s12 = 0, s22 = 0, scc = 0;
+      for (int q = 0; q < sp.nq; ++q) {
+        const double w = t.W[q];
+        s11 += w * t.vx[i][q] * t.vx[j][q];
+        s12 += w * (t.vx[i][q] * t.vy[j][q] + t.vy[i][q] * t.vx[j][q]);
+        s22 += w * t.vy[i][q] * t.vy[j][q];
+        scc += w * t.sc[i][q] * t.sc[j][q];
+      }
+      pt.T11[i][j] = s11, pt.T12[i][j] = s12, pt.T22[i][j] = s22, pt.CC[i][j] = scc;
+    }
   // synchronous copy from a stack object: the stream is idle-ordered afterwards
   FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
   FW_CHECK_CUDA(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
+  FW_CHECK_CUDA(cudaMemcpyToSymbol(c_pair, &pt, sizeof(pt)));
 }
 
 enum { FORM_A = 0, FORM_B = 1, FORM_MASS = 2, FORM_C0 = 3, FORM_C1 = 4 };
@@ -260,6 +284,111 @@ __global__ void __launch_bounds__(128) k_element_blocks(int ne, int nv, const do
   }
 }
 
+// Constant-coefficient fast path of aform + bform: straight waveguide (radius = inf) and element-wise constant
+// permittivity (P0 or diagonal-anisotropic P0).  The weight of every term is then constant over the triangle and
+// the quadrature sums collapse to reference constants (c_pair):
+//     sum_q w_q (G v_i).v_j = |det| (G11 T11_ij + G12 T12_ij + G22 T22_ij) =: m_ij
+//   (N,N): A = c_curl |det| CC_ij - m^eps_ij        B = -m_ij / (mu k0^2)
+//   (N,P): A = m_ij / mu     (P,N): A = m^eps_ij    (P,P): A = -eps_z k0^2 |det| CC_ij
+// ~5 DFMA per entry instead of 2-3 per entry AND quadrature point: the kernel is purely store bound.  No
+// accumulators live across a loop, so a thread can write RPT rows of the block (grid.y = NB / RPT) with a
+// handful of registers; A and B (compact Nedelec block) are written by the same thread.
+template <int NB, class S, int EPSKIND, int RPT>
+__global__ void __launch_bounds__(128) k_element_blocks_const(int ne, int nv, const double* __restrict__ p,
+                                                              const int* __restrict__ t, const S* __restrict__ eps,
+                                                              double k0, double mu_r, S* __restrict__ outA,
+                                                              S* __restrict__ outB) {
+  constexpr int NT = (NB == 6) ? 3 : 8;
+  using T = scalar_traits<S>;
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  if (e >= ne) return;
+  const double ik02 = 1.0 / (k0 * k0);
+  const double imu = 1.0 / mu_r;
+  const int v0 = t[e], v1 = t[ne + e], v2 = t[2 * ne + e];
+  const double x0 = p[v0], y0 = p[nv + v0];
+  const double a11 = p[v1] - x0, a21 = p[nv + v1] - y0;
+  const double a12 = p[v2] - x0, a22 = p[nv + v2] - y0;
+  const double det = a11 * a22 - a12 * a21;
+  const double adet = fabs(det);
+  const double id2a = adet / (det * det);
+  // |det| G  (G = A^-1 A^-T)
+  const double h11 = id2a * (a22 * a22 + a12 * a12);
+  const double h12 = -id2a * (a22 * a21 + a12 * a11);
+  const double h22 = id2a * (a21 * a21 + a11 * a11);
+  const double ccurl = imu * ik02 * id2a;  // |det| / (mu k0^2 det^2)
+  S ex, ey, ez;
+  if (EPSKIND == FW_EPS_P0) {
+    ex = ey = ez = eps[e];
+  } else {
+    ex = eps[3 * (size_t)e], ey = eps[3 * (size_t)e + 1], ez = eps[3 * (size_t)e + 2];
+  }
+  // |det| G_eps = |det| A^-1 diag(eps_x, eps_y) A^-T
+  S he11, he12, he22;
+  if (EPSKIND == FW_EPS_VEC_P0) {
+    he11 = (ex * (a22 * a22) + ey * (a12 * a12)) * id2a;
+    he12 = (ex * (a22 * a21) + ey * (a12 * a11)) * (-id2a);
+    he22 = (ex * (a21 * a21) + ey * (a11 * a11)) * id2a;
+  } else {
+    he11 = ex * h11, he12 = ex * h12, he22 = ex * h22;
+  }
+  const S ezk = ez * (-k0 * k0 * adet);
+  const double cb = -imu * ik02;
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const int i = blockIdx.y * RPT + r;  // block-uniform local test dof
+    if (i >= NB) break;
+    const bool rowN = c_tab.kind[i] == 0;
+    const int ri = c_tab.nrank[i];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const double t11 = c_pair.T11[i][j], t12 = c_pair.T12[i][j], t22 = c_pair.T22[i][j], cc = c_pair.CC[i][j];
+      S a;
+      if (rowN) {
+        const double m = h11 * t11 + h12 * t12 + h22 * t22;
+        if (kind_of<NB>(j) == 0) {
+          const S me = he11 * t11 + he12 * t12 + he22 * t22;
+          a = T::from(ccurl * cc, 0.0) - me;
+          outB[(size_t)(ri * NT + nrank_of<NB>(j)) * ne + e] = T::from(cb * m, 0.0);
+        } else {
+          a = T::from(imu * m, 0.0);
+        }
+      } else {
+        if (kind_of<NB>(j) == 0)
+          a = he11 * t11 + he12 * t12 + he22 * t22;
+        else
+          a = ezk * cc;
+      }
+      outA[(size_t)(i * NB + j) * ne + e] = a;
+    }
+  }
+}
+
+template <int NB, class S, int EPSKIND, int RPT>
+static void launch_const_rpt(Handle& h, const S* eps_dev, double k0, double mu_r, S* bA, S* bB) {
+  const Space& sp = h.sp;
+  k_element_blocks_const<NB, S, EPSKIND, RPT><<<dim3(cdiv(sp.ne, 128), (NB + RPT - 1) / RPT), 128, 0, h.stream>>>(
+      sp.ne, sp.nv, sp.p.p, sp.t.p, eps_dev, k0, mu_r, bA, bB);
+  FW_CHECK_CUDA(cudaGetLastError());
+}
+
+template <int NB, class S, int EPSKIND>
+static void launch_const(Handle& h, const S* eps_dev, double k0, double mu_r, S* bA, S* bB) {
+  static const int rpt = getenv("FW_K1_RPT") ? atoi(getenv("FW_K1_RPT")) : NB / 2;  // measured: 1: 0.200, 2: 0.199, 7: 0.186, 14: 0.19 ms
+  switch (rpt) {
+    case 1:
+      launch_const_rpt<NB, S, EPSKIND, 1>(h, eps_dev, k0, mu_r, bA, bB);
+      break;
+    case NB / 2:
+      launch_const_rpt<NB, S, EPSKIND, NB / 2>(h, eps_dev, k0, mu_r, bA, bB);
+      break;
+    case NB:
+      launch_const_rpt<NB, S, EPSKIND, NB>(h, eps_dev, k0, mu_r, bA, bB);
+      break;
+    default:
+      launch_const_rpt<NB, S, EPSKIND, 2>(h, eps_dev, k0, mu_r, bA, bB);
+  }
+}
+
 template <int NB, int NQ, class S, int EPSKIND, int FORM>
 static void launch_form(Handle& h, const S* eps_dev, double k0, double mu_r, double inv_radius, S* blocks) {
   const Space& sp = h.sp;
@@ -350,7 +479,24 @@ static void assemble_ab_typed(Handle& h, int eps_kind, const void* eps_host, dou
   upload_tables(h);
   {
     Timer tk(s);
-    if (sp.nb == 6) {
+    static const bool no_fast = getenv("FW_K1_GENERIC") != nullptr;
+    const bool fast = inv_radius == 0.0 && eps_kind != FW_EPS_DG_P1 && !no_fast;
+    h.tim.element_kernel_launches = fast ? 1 : 3;
+    if (fast) {
+      // one launch writes the aform blocks and the compact bform blocks
+      const S* ed = (const S*)eps_dev.p;
+      if (sp.nb == 6) {
+        if (eps_kind == FW_EPS_P0)
+          launch_const<6, S, FW_EPS_P0>(h, ed, k0, mu_r, bA, bB);
+        else
+          launch_const<6, S, FW_EPS_VEC_P0>(h, ed, k0, mu_r, bA, bB);
+      } else {
+        if (eps_kind == FW_EPS_P0)
+          launch_const<14, S, FW_EPS_P0>(h, ed, k0, mu_r, bA, bB);
+        else
+          launch_const<14, S, FW_EPS_VEC_P0>(h, ed, k0, mu_r, bA, bB);
+      }
+    } else if (sp.nb == 6) {
       dispatch_eps<6, S, FORM_A>(h, eps_kind, (const S*)eps_dev.p, k0, mu_r, inv_radius, bA);
       dispatch_nq<6, S, FW_EPS_P0, FORM_B>(h, (const S*)eps_dev.p, k0, mu_r, inv_radius, bB);
     } else {
@@ -358,8 +504,8 @@ static void assemble_ab_typed(Handle& h, int eps_kind, const void* eps_host, dou
       dispatch_nq<14, S, FW_EPS_P0, FORM_B>(h, (const S*)eps_dev.p, k0, mu_r, inv_radius, bB);
     }
     h.tim.element_kernel_ms = tk.stop();
-    h.tim.element_kernel_launches = 3;  // aform: Nedelec rows + Lagrange rows; bform: Nedelec rows
-    h.tim.kernel_launches += 3;
+    // generic path: aform Nedelec rows + Lagrange rows, bform Nedelec rows
+    h.tim.kernel_launches += h.tim.element_kernel_launches;
   }
   // segmented reduce onto the structural pattern
   std::vector<int> lut;

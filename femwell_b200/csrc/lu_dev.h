@@ -7,11 +7,15 @@ namespace fw {
 
 constexpr int PW = 32;    // panel width
 constexpr int HWIN = 256; // pivot window height (rows eligible as pivots per panel)
+// tree levels whose largest pivot block exceeds CL_MIN_NS run their substitution chains on thread-block
+// clusters (lu_solve.cu); their fronts also get explicit inverses of the PW x PW diagonal blocks (dinv)
+constexpr int CL_MIN_NS = 384;
 
 struct FrontTab {
   const int *m, *ns, *own_start, *parent, *child0, *child1;
   const long long *front_off, *work_off, *blist_off;
   const int *blist, *rel;
+  const long long* dinv_off;  // per front: offset of its inverted diagonal blocks in LUDevice::dinv, or -1
 };
 
 struct LUDevice {
@@ -21,11 +25,17 @@ struct LUDevice {
   DevBuf<int> blist, rel, level_nodes;
   DevBuf<int> piv, rowperm;
   DevBuf<double> factors, work, xperm, scratch;
+  // inverses of the PW x PW diagonal blocks of L11 (unit lower) and U11 of the cluster-level fronts: per front
+  // npan column-major blocks of inv(L_kk) followed by npan blocks of inv(U_kk); ragged blocks identity-padded
+  DevBuf<long long> dinv_off;
+  DevBuf<double> dinv;
+  int64_t dinv_entries = 0;
+  bool dinv_valid = false;
   DevBuf<int> counters;
   DevBuf<uint8_t> active;
   FrontTab tab() const {
     return FrontTab{m.p, ns.p, own_start.p, parent.p, child0.p, child1.p, front_off.p, work_off.p, blist_off.p,
-                    blist.p, rel.p};
+                    blist.p, rel.p, dinv_off.p};
   }
 };
 

@@ -94,6 +94,23 @@ void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements
   d.piv.alloc((size_t)std::max(1, S.n_active));
   d.rowperm.alloc((size_t)std::max(1, S.n_active));
   d.counters.alloc(4);
+  {
+    // storage for the inverted diagonal blocks of the fronts on cluster levels
+    std::vector<int64_t> doff((size_t)std::max(1, S.n_nodes), -1);
+    int64_t tot = 0;
+    for (int lev = 0; lev < S.n_levels; ++lev) {
+      if (S.level_max_ns[lev] <= CL_MIN_NS) continue;
+      for (int q = S.level_start[lev]; q < S.level_start[lev + 1]; ++q) {
+        const int node = S.level_nodes[q];
+        const int npan = (S.ns[node] + PW - 1) / PW;
+        if (npan == 0) continue;
+        doff[node] = tot;
+        tot += (int64_t)2 * npan * PW * PW;
+      }
+    }
+    up64(d.dinv_off, doff, s);
+    d.dinv_entries = tot;
+  }
   FW_CHECK_CUDA(cudaStreamSynchronize(s));
   tr.mark("lu analyse: upload");
 }
@@ -502,6 +519,58 @@ __global__ void k_absmax(const S* __restrict__ v, int64_t n, double* __restrict_
   if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long*)out, (unsigned long long)__double_as_longlong(mx));
 }
 
+// ------------------------------------------------------------------------------ inverted diagonal blocks
+// One warp per (front, panel): X = inv(L_kk) (unit lower) and Y = inv(U_kk) of the PW x PW diagonal block,
+// lane c computes column c by substitution (the block is read from shared memory with broadcast loads, the
+// column lives in registers).  Written column-major to a side buffer -- the factors themselves stay untouched.
+// The cluster substitution kernels (lu_solve.cu) then replace the 32 dependent steps of every diagonal solve
+// by one 32 x 32 matrix-vector product.
+template <class S>
+__global__ void __launch_bounds__(32) k_lu_diag_inverse(FrontTab T, const int* __restrict__ nodes,
+                                                        const S* __restrict__ F, S* __restrict__ dinv) {
+  using Tr = scalar_traits<S>;
+  const int node = nodes[blockIdx.x];
+  const int ns = T.ns[node], m = T.m[node];
+  const int k0 = blockIdx.y * PW;
+  const long long off = T.dinv_off[node];
+  if (k0 >= ns || off < 0) return;
+  const int npan = (ns + PW - 1) / PW;
+  const int wd = min(PW, ns - k0);
+  const S* Fn = F + T.front_off[node];
+  __shared__ S D[PW][PW + 1];
+  __shared__ S R[PW];
+  const int lane = threadIdx.x;
+  for (int c = 0; c < PW; ++c)
+    D[lane][c] = (lane < wd && c < wd) ? Fn[(k0 + lane) + (long long)(k0 + c) * m] : (lane == c ? Tr::one() : Tr::zero());
+  __syncwarp();
+  R[lane] = Tr::one() / D[lane][lane];
+  __syncwarp();
+  const int c = lane;
+  S x[PW];
+  // inv(L): x_c = 1, x_i = -sum_{j<i} L_ij x_j
+#pragma unroll
+  for (int i = 0; i < PW; ++i) {
+    S sacc = Tr::zero();
+#pragma unroll
+    for (int j = 0; j < i; ++j) fnma_(sacc, D[i][j], x[j]);
+    x[i] = i < c ? Tr::zero() : (i == c ? Tr::one() : sacc);
+  }
+  S* outL = dinv + off + (long long)blockIdx.y * PW * PW + (long long)c * PW;
+#pragma unroll
+  for (int i = 0; i < PW; ++i) outL[i] = x[i];
+  // inv(U): y_c = 1/U_cc, y_i = -(sum_{j>i} U_ij y_j) / U_ii
+#pragma unroll
+  for (int i = PW - 1; i >= 0; --i) {
+    S sacc = Tr::zero();
+#pragma unroll
+    for (int j = i + 1; j < PW; ++j) fnma_(sacc, D[i][j], x[j]);
+    x[i] = i > c ? Tr::zero() : (i == c ? R[i] : sacc * R[i]);
+  }
+  S* outU = dinv + off + (long long)(npan + blockIdx.y) * PW * PW + (long long)c * PW;
+#pragma unroll
+  for (int i = 0; i < PW; ++i) outU[i] = x[i];
+}
+
 template <class S, class V>
 static void factor_typed(Handle& h, S alphaA, S alphaB) {
   LU& lu = *h.lu;
@@ -588,6 +657,19 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
   k_lu_compose_perm<<<cdiv(Sy.n_nodes, 64), 64, 0, s>>>(T, Sy.n_nodes, d.piv.p, d.rowperm.p);
   tr.mark("lu factor: compose perm");
   launches += 1;
+  d.dinv_valid = false;
+  if (d.dinv_entries > 0 && !scalar_traits<S>::is_complex) {
+    d.dinv.alloc((size_t)d.dinv_entries * wsc);
+    for (int lev = 0; lev < Sy.n_levels; ++lev) {
+      if (Sy.level_max_ns[lev] <= CL_MIN_NS) continue;
+      const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
+      const int npan = (Sy.level_max_ns[lev] + PW - 1) / PW;
+      k_lu_diag_inverse<S><<<dim3(nfront, npan), 32, 0, s>>>(T, d.level_nodes.p + Sy.level_start[lev], F, (S*)d.dinv.p);
+      ++launches;
+    }
+    d.dinv_valid = true;
+    tr.mark("lu factor: diagonal-block inverses");
+  }
   FW_CHECK_CUDA(cudaGetLastError());
   int cnt[4] = {0, 0, 0, 0};
   d.counters.download(cnt, 4, s);

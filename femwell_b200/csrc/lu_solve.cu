@@ -31,7 +31,6 @@ constexpr int UPD_ROWS = 128;
 constexpr int UPD_CHUNK = 256;
 constexpr int CL = 8;             // CTAs per cluster in the tall-front chain kernels
 constexpr int CL_THREADS = 512;
-constexpr int CL_MIN_NS = 384;    // levels whose largest pivot block exceeds this use the cluster kernels
 constexpr int DPT = 4;            // prefetched diagonal-block entries per thread (blockDim >= 256)
 
 template <class S>
@@ -381,6 +380,232 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
   bwd_chain_body<S, NRHS, SyncCluster>(T, nodes, F, work, work_stride, xp, na);
 }
 
+// ------------------------------------------------------------------------------ cluster chains, register resident
+// Chains of the tall fronts (f64, ns <= CL * CL_THREADS) with the inverted diagonal blocks of the factorisation
+// (LUDevice::dinv).  Every thread owns ONE row of the pivot block and keeps its entry of the right-hand side in
+// a register for the whole chain; warp g of the cluster therefore owns panel g.  Per 32-column step:
+//   owner warp : x_k = inv(D_kk) w_k as a 32 x 32 matrix-vector product (w_k gathered with shuffles, the
+//                inverse block was copied into shared memory with cp.async at kernel start), then stores x_k
+//                into the shared memory of all CTAs of the cluster (distributed shared memory);
+//   one hardware cluster barrier;
+//   all threads: acc -= L[row, panel k] . x_k with the 32 factor entries prefetched into registers one step
+//                earlier.
+// No global-memory access sits on the dependent path any more (the first version re-read w from L2 and ran a
+// 32-step shuffle substitution per panel: 4.8 us per step; see DESIGN.md for the measured effect).
+constexpr int INV_SMEM_BYTES = (CL_THREADS / 32) * PW * PW * 8;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+// TMA bulk prefetch of a contiguous global range into L2 (no destination, no completion tracking)
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, long long bytes) {
+  const unsigned long long a = (unsigned long long)p;
+  const unsigned long long a0 = a & ~15ull;
+  const long long nb = (bytes + (long long)(a - a0)) & ~15ll;
+  if (nb > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(a0), "r"((unsigned)nb) : "memory");
+}
+
+template <int NRHS>
+__device__ __forceinline__ void inv_block_matvec(const double* __restrict__ Dw, int lane, double (&acc)[NRHS]) {
+  // x_lane = sum_j Dinv[lane][j] acc_j  (column-major block: conflict-free)
+#pragma unroll
+  for (int r = 0; r < NRHS; ++r) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+    for (int j = 0; j < PW; j += 4) {
+      s0 = fma(Dw[(j + 0) * PW + lane], __shfl_sync(0xffffffffu, acc[r], j + 0), s0);
+      s1 = fma(Dw[(j + 1) * PW + lane], __shfl_sync(0xffffffffu, acc[r], j + 1), s1);
+      s2 = fma(Dw[(j + 2) * PW + lane], __shfl_sync(0xffffffffu, acc[r], j + 2), s2);
+      s3 = fma(Dw[(j + 3) * PW + lane], __shfl_sync(0xffffffffu, acc[r], j + 3), s3);
+    }
+    acc[r] = (s0 + s1) + (s2 + s3);
+  }
+}
+
+template <int NRHS>
+__device__ __forceinline__ void panel_dot_sub(double (&acc)[NRHS], const double (&ln)[PW], const double* xsb) {
+#pragma unroll
+  for (int r = 0; r < NRHS; ++r) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+    for (int j = 0; j < PW; j += 4) {
+      s0 = fma(ln[j + 0], xsb[r * PW + j + 0], s0);
+      s1 = fma(ln[j + 1], xsb[r * PW + j + 1], s1);
+      s2 = fma(ln[j + 2], xsb[r * PW + j + 2], s2);
+      s3 = fma(ln[j + 3], xsb[r * PW + j + 3], s3);
+    }
+    acc[r] -= (s0 + s1) + (s2 + s3);
+  }
+}
+
+template <int NRHS>
+__device__ __forceinline__ void bcast_to_cluster(double* xs_local, int buf, int lane, const double (&acc)[NRHS]) {
+  cg::cluster_group cl = cg::this_cluster();
+#pragma unroll
+  for (int c = 0; c < CL; ++c) {
+    double* remote = cl.map_shared_rank(xs_local, c);
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) remote[(buf * NRHS + r) * PW + lane] = acc[r];
+  }
+}
+
+template <int NRHS>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
+    k_fwd_chain_inv(FrontTab T, const int* __restrict__ nodes, const double* __restrict__ F,
+                    const double* __restrict__ dinv, const int* __restrict__ rowperm, double* work,
+                    int64_t work_stride, double* xp, int na) {
+  extern __shared__ __align__(16) double inv_smem[];
+  double* Dsm = inv_smem;                                  // [warps][PW*PW]
+  double* xs = inv_smem + (CL_THREADS / 32) * PW * PW;     // [2][NRHS][PW]
+  cg::cluster_group cl = cg::this_cluster();
+  const int node = nodes[blockIdx.x / CL];
+  const int m = T.m[node], ns = T.ns[node], os = T.own_start[node];
+  const double* Fn = F + T.front_off[node];
+  double* w[NRHS];
+#pragma unroll
+  for (int r = 0; r < NRHS; ++r) w[r] = work + (size_t)r * work_stride + T.work_off[node];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int nth = CL_THREADS * CL;
+  const int gt = (int)cl.block_rank() * CL_THREADS + t;
+  // panels are dealt round-robin to the CTAs of the cluster: the rows still active at any step are spread
+  // evenly over the 8 SMs (the chain is bound by the L2 -> SM fill bandwidth of the SMs that hold rows)
+  const int gw = wid * CL + (int)cl.block_rank();  // the panel owned by this warp
+  const int row0 = gw * PW + lane;
+  const int npan = (ns + PW - 1) / PW;
+  double* Dw = Dsm + wid * PW * PW;
+  if (gw < npan) {
+    const double* src = dinv + T.dinv_off[node] + (long long)gw * PW * PW;
+#pragma unroll
+    for (int q = 0; q < PW * PW / 2 / 32; ++q) cp_async16(Dw + 2 * (lane + 32 * q), src + 2 * (lane + 32 * q));
+  }
+  // The chain walks L11 panel by panel with one dependent step per panel: pull the whole lower triangle into
+  // L2 now (one bulk prefetch per column, issued by the thread that owns the row of the same index), so that
+  // the one-step-ahead register prefetch below is served by L2 instead of HBM.
+  if (row0 < ns) prefetch_l2_bulk(Fn + (long long)row0 * m + row0, (long long)(ns - row0) * 8);
+  double ln[PW];
+  if (row0 >= PW && row0 < ns) {
+#pragma unroll
+    for (int j = 0; j < PW; ++j) ln[j] = Fn[row0 + (long long)j * m];
+  }
+  // assemble w: own rhs entries + contributions of the children (same as the generic chain)
+  for (int i = gt; i < m; i += nth)
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) w[r][i] = i < ns ? xp[(size_t)r * na + os + i] : 0.0;
+  cl.sync();
+  for (int sl = 0; sl < 2; ++sl) {
+    const int c = sl ? T.child1[node] : T.child0[node];
+    if (c < 0) continue;
+    const int nsc = T.ns[c], nbc = T.m[c] - nsc;
+    const int* rel = T.rel + T.blist_off[c];
+    for (int i = gt; i < nbc; i += nth) {
+      const int ri = rel[i];
+#pragma unroll
+      for (int r = 0; r < NRHS; ++r) {
+        const double* wc = work + (size_t)r * work_stride + T.work_off[c];
+        w[r][ri] = w[r][ri] + wc[nsc + i];
+      }
+    }
+    cl.sync();
+  }
+  if (ns == 0) return;
+  for (int i = gt; i < ns; i += nth)
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) xp[(size_t)r * na + os + i] = w[r][i];
+  cl.sync();
+  double acc[NRHS];
+#pragma unroll
+  for (int r = 0; r < NRHS; ++r) acc[r] = row0 < ns ? xp[(size_t)r * na + os + rowperm[os + row0]] : 0.0;
+  cp_async_wait_all();
+  __syncwarp();
+  for (int k = 0; k < npan; ++k) {
+    const int k0 = k * PW, buf = k & 1;
+    if (gw == k) {
+      inv_block_matvec<NRHS>(Dw, lane, acc);
+      bcast_to_cluster<NRHS>(xs, buf, lane, acc);
+    }
+    cl.sync();
+    if (row0 >= k0 + PW && row0 < ns) {
+      panel_dot_sub<NRHS>(acc, ln, xs + buf * NRHS * PW);
+      if (row0 >= k0 + 2 * PW) {
+#pragma unroll
+        for (int j = 0; j < PW; ++j) ln[j] = Fn[row0 + (long long)(k0 + PW + j) * m];
+      }
+    }
+  }
+  if (row0 < ns) {
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) w[r][row0] = acc[r];
+  }
+}
+
+template <int NRHS>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
+    k_bwd_chain_inv(FrontTab T, const int* __restrict__ nodes, const double* __restrict__ F,
+                    const double* __restrict__ dinv, double* work, int64_t work_stride, double* xp, int na) {
+  extern __shared__ __align__(16) double inv_smem[];
+  double* Dsm = inv_smem;
+  double* xs = inv_smem + (CL_THREADS / 32) * PW * PW;
+  cg::cluster_group cl = cg::this_cluster();
+  const int node = nodes[blockIdx.x / CL];
+  const int m = T.m[node], ns = T.ns[node], os = T.own_start[node];
+  if (ns == 0) return;
+  const double* Fn = F + T.front_off[node];
+  double* w[NRHS];
+#pragma unroll
+  for (int r = 0; r < NRHS; ++r) w[r] = work + (size_t)r * work_stride + T.work_off[node];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int gt = (int)cl.block_rank() * CL_THREADS + t;
+  const int gw = wid * CL + (int)cl.block_rank();  // round-robin panel ownership (see k_fwd_chain_inv)
+  const int row0 = gw * PW + lane;
+  const int npan = (ns + PW - 1) / PW;
+  double* Dw = Dsm + wid * PW * PW;
+  if (gw < npan) {
+    const double* src = dinv + T.dinv_off[node] + (long long)(npan + gw) * PW * PW;
+#pragma unroll
+    for (int q = 0; q < PW * PW / 2 / 32; ++q) cp_async16(Dw + 2 * (lane + 32 * q), src + 2 * (lane + 32 * q));
+  }
+  // upper triangle of U11 into L2 (see k_fwd_chain_inv)
+  if (row0 < ns) prefetch_l2_bulk(Fn + (long long)row0 * m, (long long)(row0 + 1) * 8);
+  double un[PW];
+  {
+    // entries of the last (possibly ragged) panel for the rows above it
+    const int k0 = (npan - 1) * PW, wd = ns - k0;
+    if (row0 < k0) {
+#pragma unroll
+      for (int j = 0; j < PW; ++j) un[j] = j < wd ? Fn[row0 + (long long)(k0 + j) * m] : 0.0;
+    }
+  }
+  double acc[NRHS];
+#pragma unroll
+  for (int r = 0; r < NRHS; ++r) acc[r] = row0 < ns ? w[r][row0] : 0.0;
+  cp_async_wait_all();
+  __syncwarp();
+  for (int k = npan - 1; k >= 0; --k) {
+    const int k0 = k * PW, buf = k & 1;
+    if (gw == k) {
+      inv_block_matvec<NRHS>(Dw, lane, acc);
+      bcast_to_cluster<NRHS>(xs, buf, lane, acc);
+    }
+    cl.sync();
+    if (row0 < k0) {
+      panel_dot_sub<NRHS>(acc, un, xs + buf * NRHS * PW);
+      if (row0 < k0 - PW) {
+#pragma unroll
+        for (int j = 0; j < PW; ++j) un[j] = Fn[row0 + (long long)(k0 - PW + j) * m];
+      }
+    }
+  }
+  if (row0 < ns) {
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) {
+      w[r][row0] = acc[r];
+      xp[(size_t)r * na + os + row0] = acc[r];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ off-diagonal updates
 // block = UPD_ROWS rows x UPD_GROUPS column groups; group g handles the columns j = g (mod UPD_GROUPS) of a
 // chunk, the partial sums are combined through shared memory in a fixed order (deterministic).
@@ -537,6 +762,34 @@ static int chain_threads(int max_ns) {
 }
 
 template <class S, int NRHS>
+struct InvChain {
+  static void launch(bool, int, FrontTab, const int*, const S*, LUDevice&, S*, int64_t, S*, int, cudaStream_t) {}
+};
+template <int NRHS>
+struct InvChain<double, NRHS> {
+  static void launch(bool fwd, int nfront, FrontTab T, const int* nodes, const double* F, LUDevice& d, double* work,
+                     int64_t work_stride, double* xp, int na, cudaStream_t s) {
+    constexpr int smem = INV_SMEM_BYTES + 2 * NRHS * PW * 8;
+    static bool configured = false;
+    if (!configured) {
+      FW_CHECK_CUDA(cudaFuncSetAttribute(k_fwd_chain_inv<NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      FW_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_chain_inv<NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured = true;
+    }
+    if (fwd)
+      k_fwd_chain_inv<NRHS><<<nfront * CL, CL_THREADS, smem, s>>>(T, nodes, F, d.dinv.p, d.rowperm.p, work, work_stride,
+                                                               xp, na);
+    else
+      k_bwd_chain_inv<NRHS><<<nfront * CL, CL_THREADS, smem, s>>>(T, nodes, F, d.dinv.p, work, work_stride, xp, na);
+  }
+};
+template <class S, int NRHS>
+static void launch_inv_chain(bool fwd, int nfront, FrontTab T, const int* nodes, const S* F, LUDevice& d, S* work,
+                             int64_t work_stride, S* xp, int na, cudaStream_t s) {
+  InvChain<S, NRHS>::launch(fwd, nfront, T, nodes, F, d, work, work_stride, xp, na, s);
+}
+
+template <class S, int NRHS>
 static void solve_typed(Handle& h, const S* b, S* x) {
   LU& lu = *h.lu;
   LUDevice& d = *lu.dev;
@@ -554,13 +807,20 @@ static void solve_typed(Handle& h, const S* b, S* x) {
   const char* tenv = getenv("FW_TRACE");
   const bool trace2 = tenv && atoi(tenv) >= 2;
   const bool no_cluster = getenv("FW_NO_CLUSTER") != nullptr;
+  const bool no_inv = getenv("FW_NO_DINV") != nullptr;
+  auto use_inv = [&](int max_ns) {
+    return !scalar_traits<S>::is_complex && d.dinv_valid && !no_cluster && !no_inv && max_ns > CL_MIN_NS &&
+           max_ns <= CL * CL_THREADS;
+  };
   Trace tr(s);
   if (na > 0) k_lu_permute_in<S><<<cdiv(na, 256), 256, 0, s>>>(na, d.perm.p, b, n, NRHS, xp);
   for (int lev = Sy.n_levels - 1; lev >= 0; --lev) {
     const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
     const int* nodes = d.level_nodes.p + Sy.level_start[lev];
     const int max_ns = Sy.level_max_ns[lev];
-    if (max_ns > CL_MIN_NS && !no_cluster)
+    if (use_inv(max_ns))
+      launch_inv_chain<S, NRHS>(true, nfront, T, nodes, F, d, work, Sy.work_entries, xp, na, s);
+    else if (max_ns > CL_MIN_NS && !no_cluster)
       k_fwd_chain_cluster<S, NRHS><<<nfront * CL, CL_THREADS, 0, s>>>(T, nodes, F, d.rowperm.p, work,
                                                                       Sy.work_entries, xp, na);
     else
@@ -609,7 +869,9 @@ static void solve_typed(Handle& h, const S* b, S* x) {
       }
       if (trace2) tr.mark(("bwd update lev " + std::to_string(lev)).c_str());
     }
-    if (max_ns > CL_MIN_NS && !no_cluster)
+    if (use_inv(max_ns))
+      launch_inv_chain<S, NRHS>(false, nfront, T, nodes, F, d, work, Sy.work_entries, xp, na, s);
+    else if (max_ns > CL_MIN_NS && !no_cluster)
       k_bwd_chain_cluster<S, NRHS><<<nfront * CL, CL_THREADS, 0, s>>>(T, nodes, F, work, Sy.work_entries, xp, na);
     else
       k_bwd_chain<S, NRHS><<<nfront, chain_threads(max_ns), 0, s>>>(T, nodes, F, work, Sy.work_entries, xp, na);

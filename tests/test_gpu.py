@@ -143,6 +143,27 @@ def test_assembly_matches_oracle(ctx, order, n, jitter, eps_kind, cplx, radius, 
         assert A_ref.nnz <= A.nnz <= As.nnz
 
 
+@pytest.mark.parametrize("order,eps_kind,cplx", [(2, 0, False), (2, 2, True), (1, 0, True), (1, 2, False)])
+def test_constant_coefficient_kernel_matches_quadrature_kernel(ctx, order, eps_kind, cplx):
+    """radius = inf and element-wise constant eps take the pre-integrated K1 (k_element_blocks_const);
+    radius = 1e300 forces the quadrature-loop K1 on the same problem (bend factor 1 + x/R == 1 exactly)."""
+    m, _ = strip_problem(11, jitter=0.15)
+    b = Basis(m, ElementTriP0(), intorder=4).with_element(mode_element(order))
+    eps = _make_eps(m, eps_kind, cplx, seed=3)
+    k0 = 2 * np.pi / 1.31
+    ctx.set_space(b)
+    ctx.symbolic()
+    ctx.assemble(eps_kind, eps, k0, 1.0, np.inf)
+    assert ctx.timings()["element_kernel_launches"] == 1
+    A1, B1 = ctx.matrix(0, eliminate_zeros=False), ctx.matrix(1, eliminate_zeros=False)
+    ctx.assemble(eps_kind, eps, k0, 1.0, 1e300)
+    assert ctx.timings()["element_kernel_launches"] == 3
+    A2, B2 = ctx.matrix(0, eliminate_zeros=False), ctx.matrix(1, eliminate_zeros=False)
+    for x, y in ((A1, A2), (B1, B2)):
+        assert np.array_equal(x.indptr, y.indptr) and np.array_equal(x.indices, y.indices)
+        assert abs(x - y).max() < 1e-13 * abs(y).max()
+
+
 def test_assembly_golden_checksums(ctx):
     g = json.load(open(os.path.join(ROOT, "tests", "golden", "strip_n16.json")))
     m, eps = strip_problem(g["n"])
@@ -192,7 +213,10 @@ def test_spmv_matches_scipy(ctx, cplx_eps, cplx_x):
 # ----------------------------------------------------------------------------- sparse LU
 @pytest.mark.parametrize("order,n,cplx,dirichlet,leaf", [(2, 12, False, False, 0), (2, 24, False, True, 16),
                                                        (1, 30, False, False, 8), (2, 16, True, False, 0),
-                                                       (2, 40, False, False, 0)])
+                                                       (2, 40, False, False, 0),
+                                                       # top separators > 384 dofs: cluster chains (register-resident
+                                                       # f64 kernels with inverted diagonal blocks; c128 generic)
+                                                       (2, 110, False, False, 0), (2, 100, True, True, 0)])
 def test_lu_solve_matches_scipy(ctx, order, n, cplx, dirichlet, leaf):
     m, _ = strip_problem(n)
     b = Basis(m, ElementTriP0(), intorder=4).with_element(mode_element(order))
