@@ -258,22 +258,27 @@ def main():
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     achieved = alg_bytes / t_elem / 1e9
-    # DRAM traffic of the same three launches from the committed ncu --set full capture (bytes per solve)
+    # DRAM traffic of the same launch from the committed ncu --set full capture (bytes per launch)
     traffic = None
+    n_k1 = int(stats["timings"].get("element_kernel_launches", 1))
     try:
         import csv
 
-        rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", "ncu_r01_assembly_full.csv")))
+        rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", "ncu_r01c_assembly_full.csv")))
                 if r and not r[0].startswith("#")]
         hdr = rows[0]
         ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-        k1 = [r for r in rows[2:] if "k_element_blocks" in r[1]][:3]
-        traffic = sum(float(r[ir]) * 1e9 + float(r[iw]) * 1e6 for r in k1)
+        k1 = [r for r in rows[2:] if "k_element_blocks_const" in r[1]][:1]
+        if n_k1 == 1 and k1:
+            traffic = sum(float(r[ir]) * 1e9 + float(r[iw]) * 1e6 for r in k1)
     except Exception:
         pass
-    roofline = {"kernel": "k_element_blocks (K1: aform Nedelec rows + aform Lagrange rows + bform, 3 launches per solve)",
+    kname = ("k_element_blocks_const (K1: aform + bform local blocks of every triangle, 1 launch per solve)"
+             if n_k1 == 1 else "k_element_blocks (K1, quadrature-loop variant: 3 launches per solve)")
+    roofline = {"kernel": kname,
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic,
+                "traffic": traffic, "launches_per_solve": n_k1,
+                "algorithmic_bytes_per_launch": alg_bytes / n_k1, "seconds_per_launch": t_elem / n_k1,
                 "algorithmic_bytes_per_solve": alg_bytes, "seconds_per_solve": t_elem,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

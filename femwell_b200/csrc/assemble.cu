@@ -579,6 +579,10 @@ void assemble_aux(Handle& h) {
     v.valid = true;
     h.tim.kernel_launches += 3;
   }
+  // compact copy of the mass matrix (the cross blocks are structural zeros on the shared pattern)
+  h.MassC.nnz = compact_csr_dev(h, pat, h.Mass, 2, h.MassC.indptr, h.MassC.indices, h.MassC.vals);
+  h.MassC.valid = true;
+  h.tim.kernel_launches += 5;
 }
 
 }  // namespace fw

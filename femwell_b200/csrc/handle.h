@@ -57,6 +57,13 @@ struct Handle {
   bool has_symbolic = false;
   bool eliminate_zeros = true;  // export semantics of scipy's coo.eliminate_zeros()
   Values A, B, Mass, C0, C1;
+  // mass matrix without the structurally-zero cross blocks (own compact CSR; used by the PCG of the H field)
+  struct CompactCsr {
+    DevBuf<int> indptr, indices;
+    DevBuf<double> vals;
+    int64_t nnz = 0;
+    bool valid = false;
+  } MassC;
   Connectivity generic;  // set by fw_eigs_csr instead of a space
   DevBuf<double> blocks;  // scratch: local element blocks (SoA [entry][Ne])
   // generic COO->CSR result
@@ -65,6 +72,10 @@ struct Handle {
   // compacted export scratch
   DevBuf<uint32_t> scan_tmp, scan_tmp2;
   std::unique_ptr<LU> lu;
+  // big LU buffers live here so that they survive a new space / analysis (no 25 GB cudaFree + cudaMalloc per solve)
+  struct LUArena {
+    DevBuf<double> factors, work, xperm, scratch, dinv;
+  } lu_arena;
   // pinned staging ring for large device -> pageable-host copies (results E, H)
   void* pinned[2] = {nullptr, nullptr};
   cudaEvent_t pinned_ev[2] = {nullptr, nullptr};
@@ -88,6 +99,9 @@ void reduce_onto_pattern(const Pattern& pat, const S* coo_vals, const int* lut, 
 void build_slot_list(Handle& h, Pattern& pat, const int* lut_dev, int64_t stride);
 int64_t count_kept(Handle& h, const Pattern& pat, Values& val);
 void export_compacted(Handle& h, const Pattern& pat, Values& val, int* indptr, int* indices, void* data);
+// device-side compaction: keeps the slots whose flag has a bit of `mask` set; returns the number kept
+int64_t compact_csr_dev(Handle& h, const Pattern& pat, Values& val, uint8_t mask, DevBuf<int>& oip, DevBuf<int>& oind,
+                        DevBuf<double>& oval);
 void coo_to_csr(Handle& h, int n_rows, int64_t n_entries, const int* rows, const int* cols, const void* data,
                 bool is_complex);
 

@@ -24,15 +24,17 @@ struct LUDevice {
   DevBuf<long long> front_off, work_off, blist_off;
   DevBuf<int> blist, rel, level_nodes;
   DevBuf<int> piv, rowperm;
-  DevBuf<double> factors, work, xperm, scratch;
+  DevBuf<double>&factors, &work, &xperm, &scratch;  // Handle::lu_arena
   // inverses of the PW x PW diagonal blocks of L11 (unit lower) and U11 of the cluster-level fronts: per front
   // npan column-major blocks of inv(L_kk) followed by npan blocks of inv(U_kk); ragged blocks identity-padded
   DevBuf<long long> dinv_off;
-  DevBuf<double> dinv;
+  DevBuf<double>& dinv;
   int64_t dinv_entries = 0;
   bool dinv_valid = false;
   DevBuf<int> counters;
   DevBuf<uint8_t> active;
+  explicit LUDevice(Handle::LUArena& a)
+      : factors(a.factors), work(a.work), xperm(a.xperm), scratch(a.scratch), dinv(a.dinv) {}
   FrontTab tab() const {
     return FrontTab{m.p, ns.p, own_start.p, parent.p, child0.p, child1.p, front_off.p, work_off.p, blist_off.p,
                     blist.p, rel.p, dinv_off.p};

@@ -66,7 +66,7 @@ void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements
                       leaf_elements);
   }
   tr.mark("lu analyse: host symbolic");
-  lu.dev.reset(new LUDevice());
+  lu.dev.reset(new LUDevice(h.lu_arena));
   LUDevice& d = *lu.dev;
   const LUSymbolic& S = lu.sym;
   cudaStream_t s = h.stream;

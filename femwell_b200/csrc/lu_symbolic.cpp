@@ -12,6 +12,8 @@
 #include <numeric>
 #include <thread>
 
+#include <climits>
+
 #include "lu.h"
 
 namespace fw {
@@ -124,43 +126,39 @@ void lu_symbolic_build(LUSymbolic& S, int n, int nb, int ne, const int* edofs, c
       for (int i = node_lo[v]; i < node_hi[v]; ++i) leaf_of[eperm[i]] = v;
   mark("kd-tree");
 
-  // ---- 2. owner of every dof = LCA of the leaves of its elements
+  // ---- 2. owner of every dof = LCA of the leaves of its elements.  Threads own contiguous dof ranges: every
+  // thread streams the whole connectivity and folds only its own dofs (no atomics, deterministic).
   std::vector<int> owner(n, -1);
   const std::vector<int>& par = S.parent;
   const std::vector<int>& dep = S.depth;
-  for (int e = 0; e < ne; ++e) {
-    const int lf = leaf_of[e];
+  parallel_chunks(n, 1 << 18, [&](int da, int db, int) {
     for (int l = 0; l < nb; ++l) {
-      const int d = edofs[(size_t)l * ne + e];
-      if (!active[d]) continue;
-      int a = owner[d];
-      if (a < 0) {
-        owner[d] = lf;
-        continue;
+      const int* row = edofs + (size_t)l * ne;
+      for (int e = 0; e < ne; ++e) {
+        const int d = row[e];
+        if (d < da || d >= db || !active[d]) continue;
+        const int lf = leaf_of[e];
+        int a = owner[d];
+        if (a < 0) {
+          owner[d] = lf;
+          continue;
+        }
+        int b = lf;
+        while (a != b) {
+          if (dep[a] > dep[b])
+            a = par[a];
+          else if (dep[b] > dep[a])
+            b = par[b];
+          else
+            a = par[a], b = par[b];
+        }
+        owner[d] = a;
       }
-      int b = lf;
-      while (a != b) {
-        if (dep[a] > dep[b])
-          a = par[a];
-        else if (dep[b] > dep[a])
-          b = par[b];
-        else
-          a = par[a], b = par[b];
-      }
-      owner[d] = a;
     }
-  }
+  });
   mark("owners (LCA)");
 
-  // ---- 3. postorder numbering
-  S.ns.assign(nn, 0);
-  int n_active = 0;
-  for (int d = 0; d < n; ++d)
-    if (owner[d] >= 0) {
-      S.ns[owner[d]]++;
-      n_active++;
-    }
-  S.n_active = n_active;
+  // ---- 3. postorder numbering (dofs of a node in ascending original order)
   std::vector<int> post;
   post.reserve(nn);
   {
@@ -187,27 +185,51 @@ void lu_symbolic_build(LUSymbolic& S, int n, int nb, int ne, const int* edofs, c
       }
     }
   }
-  S.own_start.assign(nn, 0);
   {
-    int run = 0;
-    for (int v : post) {
-      S.own_start[v] = run;
-      run += S.ns[v];
+    // per-thread histograms over contiguous dof chunks -> deterministic positions without a serial sweep
+    const int min_per = 1 << 16;
+    const int nt = std::min(worker_count(), std::max(1, n / min_per));
+    std::vector<std::vector<int>> cnt(nt, std::vector<int>(nn, 0));
+    parallel_chunks(n, min_per, [&](int da, int db, int tid) {
+      std::vector<int>& c = cnt[tid];
+      for (int d = da; d < db; ++d)
+        if (owner[d] >= 0) c[owner[d]]++;
+    });
+    S.ns.assign(nn, 0);
+    int n_active = 0;
+    for (int v = 0; v < nn; ++v) {
+      int run = 0;
+      for (int t = 0; t < nt; ++t) {
+        const int c = cnt[t][v];
+        cnt[t][v] = run;  // offset of thread t inside node v
+        run += c;
+      }
+      S.ns[v] = run;
+      n_active += run;
     }
-  }
-  S.perm.assign(n_active, -1);
-  S.iperm.assign(n, -1);
-  S.node_of.assign(n_active, -1);
-  {
-    std::vector<int> fill(nn, 0);
-    for (int d = 0; d < n; ++d) {
-      int o = owner[d];
-      if (o < 0) continue;
-      int ni = S.own_start[o] + fill[o]++;
-      S.perm[ni] = d;
-      S.iperm[d] = ni;
-      S.node_of[ni] = o;
+    S.n_active = n_active;
+    S.own_start.assign(nn, 0);
+    {
+      int run = 0;
+      for (int v : post) {
+        S.own_start[v] = run;
+        run += S.ns[v];
+      }
     }
+    S.perm.assign(n_active, -1);
+    S.iperm.assign(n, -1);
+    S.node_of.assign(n_active, -1);
+    parallel_chunks(n, min_per, [&](int da, int db, int tid) {
+      std::vector<int>& c = cnt[tid];
+      for (int d = da; d < db; ++d) {
+        const int o = owner[d];
+        if (o < 0) continue;
+        const int ni = S.own_start[o] + c[o]++;
+        S.perm[ni] = d;
+        S.iperm[d] = ni;
+        S.node_of[ni] = o;
+      }
+    });
   }
   mark("numbering");
 

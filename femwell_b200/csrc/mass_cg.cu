@@ -3,9 +3,14 @@
 //
 // The mass matrix (block diagonal: Nedelec mass + Lagrange mass) is real SPD and mode independent, the
 // right-hand sides are the k complex vectors C(beta_i) e_i.  All k systems advance together so that the
-// matrix is streamed once per iteration for all modes (SpMV with k vectors), and every CG scalar
-// (alpha, beta, residual norms) lives in device memory -- the host only looks at the residuals every
-// few iterations.  HBM-bound: nnz*(8+4) + k*N*16*~8 bytes per iteration.
+// matrix is streamed once per iteration for all modes, and every CG scalar (alpha, beta, residual norms)
+// lives in device memory -- the host only looks at the residuals every few iterations.
+//
+// Layout: the CG vectors are INTERLEAVED, v[i*k + r] (dof i, system r): the SpMV gather of one matrix entry
+// then reads k consecutive complex values (64 B for k = 4, two full sectors) instead of k scattered 16 B
+// pieces, which halves the L2 -> SM traffic of the dominant kernel.  The matrix is the compact copy without the
+// structurally-zero Nedelec x Lagrange blocks of the shared pattern (Handle::MassC).  The <p, M p> partial
+// sums are produced by the SpMV itself.  HBM-bound: nnz*12 + ~9 k N 16 bytes per iteration, 5 launches.
 #include <algorithm>
 
 #include "solver.h"
@@ -13,50 +18,6 @@
 namespace fw {
 
 constexpr int CG_MAXK = 8;
-
-// y[r][row] = sum_c M[row,c] x[r][c], 8 lanes per row, all k vectors per matrix pass
-__global__ void __launch_bounds__(256) k_spmv_multi(int n, int k, const int* __restrict__ indptr,
-                                                    const int* __restrict__ indices, const double* __restrict__ vals,
-                                                    const cplx* __restrict__ x, cplx* __restrict__ y) {
-  constexpr int TPR = 8;
-  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int row = (int)(gt / TPR), l = (int)(gt % TPR);
-  cplx acc[CG_MAXK];
-#pragma unroll
-  for (int r = 0; r < CG_MAXK; ++r) acc[r] = cplx{0.0, 0.0};
-  if (row < n) {
-    const int a = indptr[row], b = indptr[row + 1];
-    for (int e = a + l; e < b; e += TPR) {
-      const double v = vals[e];
-      if (v == 0.0) continue;  // structural zeros of the cross blocks on the shared pattern
-      const int c = indices[e];
-#pragma unroll
-      for (int r = 0; r < CG_MAXK; ++r)
-        if (r < k) fma_(acc[r], v, x[(size_t)r * n + c]);
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < CG_MAXK; ++r) {
-    if (r < k) {
-#pragma unroll
-      for (int o = TPR / 2; o > 0; o >>= 1) {
-        acc[r].re += __shfl_xor_sync(0xffffffffu, acc[r].re, o);
-        acc[r].im += __shfl_xor_sync(0xffffffffu, acc[r].im, o);
-      }
-      if (l == 0 && row < n) y[(size_t)r * n + row] = acc[r];
-    }
-  }
-}
-
-__global__ void k_cg_diag(int n, const int* __restrict__ indptr, const int* __restrict__ indices,
-                          const double* __restrict__ vals, double* __restrict__ idiag) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  double d = 0;
-  for (int e = indptr[r]; e < indptr[r + 1]; ++e)
-    if (indices[e] == r) d = vals[e];
-  idiag[r] = d != 0.0 ? 1.0 / d : 0.0;
-}
 
 __device__ inline double block_sum_256(double s, double* red) {
 #pragma unroll
@@ -70,27 +31,62 @@ __device__ inline double block_sum_256(double s, double* red) {
   return q;  // valid in thread 0
 }
 
-// partial[(r*2+0)*nblk + b] = Re<a_r, b_r> over the rows of block b (slot `which` of 2)
-__global__ void __launch_bounds__(256) k_cg_dot(int n, int k, const cplx* __restrict__ a, const cplx* __restrict__ b,
-                                                double* __restrict__ partial, int nblk) {
-  __shared__ double red[8];
-  const int64_t base = (int64_t)blockIdx.x * 1024;
-  for (int r = 0; r < k; ++r) {
-    double s = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      int64_t i = base + q * 256 + threadIdx.x;
-      if (i < n) {
-        const cplx u = a[(size_t)r * n + i], v = b[(size_t)r * n + i];
-        s += u.re * v.re + u.im * v.im;
-      }
+// q[row] = sum_c M[row,c] p[c] for all K systems; part_pq[r][block] = sum_rows Re(conj(p_r[row]) q_r[row]).
+// The matrix is real, so the K complex systems are 2K independent real columns: 2K lanes per row, lane c owns
+// real component c of the interleaved vectors and walks all entries of the row.  The lanes of a row read the
+// same (value, column) pair (one broadcast sector each) and 16 K contiguous bytes of p -- no shuffle reduction.
+template <int K>
+__global__ void __launch_bounds__(256) k_spmv_multi(int n, const int* __restrict__ indptr,
+                                                    const int* __restrict__ indices, const double* __restrict__ vals,
+                                                    const double* __restrict__ x, double* __restrict__ y,
+                                                    double* __restrict__ part_pq, int nblk) {
+  constexpr int C = 2 * K;            // real components per dof
+  constexpr int RPB = 256 / C;        // rows per block
+  __shared__ double red[8][C];
+  const int g = threadIdx.x / C, c = threadIdx.x % C;
+  const int row = blockIdx.x * RPB + g;
+  double acc = 0.0, dot = 0.0;
+  if (row < n) {
+    const int a = indptr[row], b = indptr[row + 1];
+    int e = a;
+    for (; e + 4 <= b; e += 4) {
+      const double v0 = vals[e], v1 = vals[e + 1], v2 = vals[e + 2], v3 = vals[e + 3];
+      const int c0 = indices[e], c1 = indices[e + 1], c2 = indices[e + 2], c3 = indices[e + 3];
+      const double x0 = x[(size_t)c0 * C + c], x1 = x[(size_t)c1 * C + c], x2 = x[(size_t)c2 * C + c],
+                   x3 = x[(size_t)c3 * C + c];
+      acc = fma(v0, x0, acc);
+      acc = fma(v1, x1, acc);
+      acc = fma(v2, x2, acc);
+      acc = fma(v3, x3, acc);
     }
-    double t = block_sum_256(s, red);
-    if (threadIdx.x == 0) partial[(size_t)r * nblk + blockIdx.x] = t;
+    for (; e < b; ++e) acc = fma(vals[e], x[(size_t)indices[e] * C + c], acc);
+    y[(size_t)row * C + c] = acc;
+    dot = x[(size_t)row * C + c] * acc;
+  }
+  // per-component block sums: lanes with equal c sit C apart
+#pragma unroll
+  for (int o = 16; o >= C; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane < C) red[wid][lane] = dot;
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w][2 * threadIdx.x] + red[w][2 * threadIdx.x + 1];
+    part_pq[(size_t)threadIdx.x * nblk + blockIdx.x] = t;
   }
 }
 
-// out[r] = sum_b partial[r*nblk + b]  (one block per (r, slot))
+__global__ void k_cg_diag(int n, const int* __restrict__ indptr, const int* __restrict__ indices,
+                          const double* __restrict__ vals, double* __restrict__ idiag) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double d = 0;
+  for (int e = indptr[r]; e < indptr[r + 1]; ++e)
+    if (indices[e] == r) d = vals[e];
+  idiag[r] = d != 0.0 ? 1.0 / d : 0.0;
+}
+
+// out[r] = sum_b partial[r*nblk + b]  (one block per system)
 __global__ void __launch_bounds__(256) k_cg_reduce(const double* __restrict__ partial, int nblk,
                                                    double* __restrict__ out) {
   __shared__ double sh[256];
@@ -105,142 +101,192 @@ __global__ void __launch_bounds__(256) k_cg_reduce(const double* __restrict__ pa
   }
   if (t == 0) out[r] = sh[0];
 }
+// the two reductions that follow k_cg_step in one launch: blockIdx.y selects (rr, rz)
+__global__ void __launch_bounds__(256) k_cg_reduce2(const double* __restrict__ pa, double* __restrict__ oa,
+                                                    const double* __restrict__ pb, double* __restrict__ ob, int nblk) {
+  __shared__ double sh[256];
+  const double* partial = blockIdx.y ? pb : pa;
+  double* out = blockIdx.y ? ob : oa;
+  const int r = blockIdx.x, t = threadIdx.x;
+  double s = 0;
+  for (int b = t; b < nblk; b += 256) s += partial[(size_t)r * nblk + b];
+  sh[t] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) sh[t] += sh[t + o];
+    __syncthreads();
+  }
+  if (t == 0) out[r] = sh[0];
+}
 
 // x += alpha p ; r -= alpha q ; z = r / diag ; partials of <r,r> and <r,z>     (alpha_r = rz_r / pq_r)
-__global__ void __launch_bounds__(256) k_cg_step(int n, int k, cplx* __restrict__ x, cplx* __restrict__ rv,
-                                                 const cplx* __restrict__ p, const cplx* __restrict__ q,
-                                                 cplx* __restrict__ z, const double* __restrict__ idiag,
+// INIT: only z and the partials (x = 0, r = b).  Flat, fully coalesced 16-byte accesses over the interleaved
+// vectors: element o = i*K + r, and because 256 % K == 0 a thread always meets the same system r.
+template <int K, bool INIT>
+__global__ void __launch_bounds__(256) k_cg_step(int n, double2* __restrict__ x, double2* __restrict__ rv,
+                                                 const double2* __restrict__ p, const double2* __restrict__ q,
+                                                 double2* __restrict__ z, const double* __restrict__ idiag,
                                                  const double* __restrict__ rz, const double* __restrict__ pq,
                                                  double* __restrict__ part_rr, double* __restrict__ part_rz,
                                                  int nblk) {
-  __shared__ double red[8];
+  __shared__ double red[2][8][K];
+  const int64_t total = (int64_t)n * K;
   const int64_t base = (int64_t)blockIdx.x * 1024;
-  for (int r = 0; r < k; ++r) {
+  const int r = threadIdx.x & (K - 1);
+  double alpha = 0.0;
+  if (!INIT) {
     const double den = pq[r];
-    const double alpha = (den != 0.0 && isfinite(den)) ? rz[r] / den : 0.0;
-    double s_rr = 0, s_rz = 0;
+    alpha = (den != 0.0 && isfinite(den)) ? rz[r] / den : 0.0;
+  }
+  double s_rr = 0.0, s_rz = 0.0;
 #pragma unroll
-    for (int qq = 0; qq < 4; ++qq) {
-      int64_t i = base + qq * 256 + threadIdx.x;
-      if (i < n) {
-        const size_t o = (size_t)r * n + i;
-        x[o] = x[o] + p[o] * alpha;
-        const cplx res = rv[o] - q[o] * alpha;
+  for (int qq = 0; qq < 4; ++qq) {
+    const int64_t o = base + qq * 256 + threadIdx.x;
+    if (o < total) {
+      const double id = idiag[o / K];
+      double2 res = rv[o];
+      if (!INIT) {
+        const double2 xo = x[o], po = p[o], qo = q[o];
+        x[o] = make_double2(fma(alpha, po.x, xo.x), fma(alpha, po.y, xo.y));
+        res = make_double2(fma(-alpha, qo.x, res.x), fma(-alpha, qo.y, res.y));
         rv[o] = res;
-        const cplx zz = res * idiag[i];
-        z[o] = zz;
-        s_rr += res.re * res.re + res.im * res.im;
-        s_rz += res.re * zz.re + res.im * zz.im;
       }
+      const double2 zz = make_double2(res.x * id, res.y * id);
+      z[o] = zz;
+      s_rr += res.x * res.x + res.y * res.y;
+      s_rz += res.x * zz.x + res.y * zz.y;
     }
-    double t1 = block_sum_256(s_rr, red);
-    double t2 = block_sum_256(s_rz, red);
-    if (threadIdx.x == 0) {
-      part_rr[(size_t)r * nblk + blockIdx.x] = t1;
-      part_rz[(size_t)r * nblk + blockIdx.x] = t2;
-    }
+  }
+#pragma unroll
+  for (int o = 16; o >= K; o >>= 1) {
+    s_rr += __shfl_xor_sync(0xffffffffu, s_rr, o);
+    s_rz += __shfl_xor_sync(0xffffffffu, s_rz, o);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane < K) red[0][wid][lane] = s_rr, red[1][wid][lane] = s_rz;
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double t1 = 0, t2 = 0;
+    for (int w = 0; w < 8; ++w) t1 += red[0][w][threadIdx.x], t2 += red[1][w][threadIdx.x];
+    part_rr[(size_t)threadIdx.x * nblk + blockIdx.x] = t1;
+    part_rz[(size_t)threadIdx.x * nblk + blockIdx.x] = t2;
   }
 }
 
 // p = z + (rz_new / rz_old) p
-__global__ void k_cg_direction(int n, int k, cplx* __restrict__ p, const cplx* __restrict__ z,
-                               const double* __restrict__ rz_new, const double* __restrict__ rz_old) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+template <int K>
+__global__ void __launch_bounds__(256) k_cg_direction(int n, double2* __restrict__ p, const double2* __restrict__ z,
+                                                      const double* __restrict__ rz_new,
+                                                      const double* __restrict__ rz_old) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= (int64_t)n * K) return;
+  const int r = threadIdx.x & (K - 1);
+  const double den = rz_old[r];
+  const double beta = (den != 0.0 && isfinite(den)) ? rz_new[r] / den : 0.0;
+  const double2 zo = z[o], po = p[o];
+  p[o] = make_double2(fma(beta, po.x, zo.x), fma(beta, po.y, zo.y));
+}
+
+// [k][n] <-> interleaved [n][K]
+template <int K>
+__global__ void k_cg_interleave(int n, const cplx* __restrict__ in, cplx* __restrict__ out, bool to_interleaved) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  for (int r = 0; r < k; ++r) {
-    const double den = rz_old[r];
-    const double beta = (den != 0.0 && isfinite(den)) ? rz_new[r] / den : 0.0;
-    const size_t o = (size_t)r * n + i;
-    p[o] = z[o] + p[o] * beta;
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+    if (to_interleaved)
+      out[(size_t)i * K + r] = in[(size_t)r * n + i];
+    else
+      out[(size_t)r * n + i] = in[(size_t)i * K + r];
   }
 }
 
-// z = r / diag, partials of <r,r>, <r,z>  (initialisation)
-__global__ void __launch_bounds__(256) k_cg_init(int n, int k, const cplx* __restrict__ rv, cplx* __restrict__ z,
-                                                 const double* __restrict__ idiag, double* __restrict__ part_rr,
-                                                 double* __restrict__ part_rz, int nblk) {
-  __shared__ double red[8];
-  const int64_t base = (int64_t)blockIdx.x * 1024;
-  for (int r = 0; r < k; ++r) {
-    double s_rr = 0, s_rz = 0;
-#pragma unroll
-    for (int qq = 0; qq < 4; ++qq) {
-      int64_t i = base + qq * 256 + threadIdx.x;
-      if (i < n) {
-        const size_t o = (size_t)r * n + i;
-        const cplx res = rv[o];
-        const cplx zz = res * idiag[i];
-        z[o] = zz;
-        s_rr += res.re * res.re + res.im * res.im;
-        s_rz += res.re * zz.re + res.im * zz.im;
-      }
-    }
-    double t1 = block_sum_256(s_rr, red);
-    double t2 = block_sum_256(s_rz, red);
-    if (threadIdx.x == 0) {
-      part_rr[(size_t)r * nblk + blockIdx.x] = t1;
-      part_rz[(size_t)r * nblk + blockIdx.x] = t2;
+template <int K>
+static void mass_solve_k(Handle& h, const cplx* B, cplx* X) {
+  const int n = h.sp.n;
+  cudaStream_t s = h.stream;
+  const Handle::CompactCsr& M = h.MassC;
+  const int nblk = cdiv((int64_t)n * K, 1024);
+  const int nblk_mv = cdiv(n, 256 / (2 * K));
+  const size_t vec = (size_t)K * n * 2;
+  DevBuf<double> idiag, part, scal, xb, r, z, p, q;
+  idiag.alloc(n);
+  part.alloc((size_t)2 * K * nblk + (size_t)K * nblk_mv);
+  scal.alloc((size_t)5 * CG_MAXK);
+  xb.alloc(vec), r.alloc(vec), z.alloc(vec), p.alloc(vec), q.alloc(vec);
+  cplx *xv = (cplx*)xb.p, *rv = (cplx*)r.p, *zv = (cplx*)z.p, *pv = (cplx*)p.p, *qv = (cplx*)q.p;
+  double* part_rr = part.p;
+  double* part_rz = part.p + (size_t)K * nblk;
+  double* part_pq = part.p + (size_t)2 * K * nblk;
+  double* d_rr = scal.p;  // [K]
+  double* d_rz[2] = {scal.p + CG_MAXK, scal.p + 2 * CG_MAXK};
+  double* d_pq = scal.p + 3 * CG_MAXK;
+  const int g256 = cdiv(n, 256);
+  Trace tr(s);
+  tr.mark("    mass PCG: workspace");
+  k_cg_diag<<<g256, 256, 0, s>>>(n, M.indptr.p, M.indices.p, M.vals.p, idiag.p);
+  FW_CHECK_CUDA(cudaMemsetAsync(xv, 0, vec * sizeof(double), s));
+  k_cg_interleave<K><<<g256, 256, 0, s>>>(n, B, rv, true);
+  k_cg_step<K, true><<<nblk, 256, 0, s>>>(n, (double2*)xv, (double2*)rv, (const double2*)pv, (const double2*)qv, (double2*)zv,
+                                          idiag.p, nullptr, nullptr, part_rr, part_rz, nblk);
+  k_cg_reduce2<<<dim3(K, 2), 256, 0, s>>>(part_rr, d_rr, part_rz, d_rz[0], nblk);
+  FW_CHECK_CUDA(cudaMemcpyAsync(pv, zv, vec * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  double bnorm2[CG_MAXK], rr[CG_MAXK];
+  FW_CHECK_CUDA(cudaMemcpyAsync(bnorm2, d_rr, sizeof(double) * K, cudaMemcpyDeviceToHost, s));
+  FW_CHECK_CUDA(cudaStreamSynchronize(s));
+  tr.mark("    mass PCG: init");
+  int64_t launches = 5;
+  int cur = 0, it = 0;
+  const int check_every = 4;
+  for (; it < 600; ++it) {
+    k_spmv_multi<K><<<nblk_mv, 256, 0, s>>>(n, M.indptr.p, M.indices.p, M.vals.p, (const double*)pv, (double*)qv, part_pq,
+                                            nblk_mv);
+    k_cg_reduce<<<K, 256, 0, s>>>(part_pq, nblk_mv, d_pq);
+    k_cg_step<K, false><<<nblk, 256, 0, s>>>(n, (double2*)xv, (double2*)rv, (const double2*)pv, (const double2*)qv,
+                                             (double2*)zv, idiag.p, d_rz[cur], d_pq, part_rr, part_rz, nblk);
+    k_cg_reduce2<<<dim3(K, 2), 256, 0, s>>>(part_rr, d_rr, part_rz, d_rz[cur ^ 1], nblk);
+    k_cg_direction<K><<<cdiv((int64_t)n * K, 256), 256, 0, s>>>(n, (double2*)pv, (const double2*)zv, d_rz[cur ^ 1], d_rz[cur]);
+    cur ^= 1;
+    launches += 5;
+    if ((it + 1) % check_every == 0) {
+      FW_CHECK_CUDA(cudaMemcpyAsync(rr, d_rr, sizeof(double) * K, cudaMemcpyDeviceToHost, s));
+      FW_CHECK_CUDA(cudaStreamSynchronize(s));
+      bool done = true;
+      for (int i = 0; i < K; ++i)
+        if (!(rr[i] <= 1e-26 * bnorm2[i])) done = false;  // ||r|| <= 1e-13 ||b|| (the reference's H carries complex64 rounding, 1e-7)
+      if (done) break;
     }
   }
+  tr.mark("    mass PCG: iterations");
+  k_cg_interleave<K><<<g256, 256, 0, s>>>(n, xv, X, false);
+  ++launches;
+  FW_CHECK_CUDA(cudaGetLastError());
+  h.tim.kernel_launches += launches;
+  if (getenv("FW_TRACE"))
+    fprintf(stderr, "[fw-trace]   mass PCG: %d rhs, %d iterations, %lld kernel launches, mass nnz %lld\n", K, it + 1,
+            (long long)launches, (long long)M.nnz);
 }
 
 // Mass X = B for k <= CG_MAXK complex right-hand sides ([k][n] each); X overwritten.
 void mass_solve_multi(Handle& h, int k, const cplx* B, cplx* X) {
   FW_REQUIRE(k >= 1 && k <= CG_MAXK, "mass_solve_multi: 1 <= k <= 8");
-  FW_REQUIRE(h.Mass.valid, "mass matrix missing");
-  const int n = h.sp.n;
-  cudaStream_t s = h.stream;
-  const Pattern& pat = h.pat;
-  const int nblk = cdiv(n, 1024);
-  const size_t vec = (size_t)k * n * 2;
-  DevBuf<double> idiag, part, scal, r, z, p, q;
-  idiag.alloc(n);
-  part.alloc((size_t)3 * k * nblk);
-  scal.alloc((size_t)5 * CG_MAXK);
-  r.alloc(vec), z.alloc(vec), p.alloc(vec), q.alloc(vec);
-  cplx *rv = (cplx*)r.p, *zv = (cplx*)z.p, *pv = (cplx*)p.p, *qv = (cplx*)q.p;
-  double* part_rr = part.p;
-  double* part_rz = part.p + (size_t)k * nblk;
-  double* part_pq = part.p + (size_t)2 * k * nblk;
-  double* d_rr = scal.p;                 // [k]
-  double* d_rz[2] = {scal.p + CG_MAXK, scal.p + 2 * CG_MAXK};
-  double* d_pq = scal.p + 3 * CG_MAXK;
-  const int g256 = cdiv(n, 256);
-  k_cg_diag<<<g256, 256, 0, s>>>(n, pat.indptr.p, pat.indices.p, h.Mass.v.p, idiag.p);
-  FW_CHECK_CUDA(cudaMemsetAsync(X, 0, vec * sizeof(double), s));
-  FW_CHECK_CUDA(cudaMemcpyAsync(rv, B, vec * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  k_cg_init<<<nblk, 256, 0, s>>>(n, k, rv, zv, idiag.p, part_rr, part_rz, nblk);
-  k_cg_reduce<<<k, 256, 0, s>>>(part_rr, nblk, d_rr);
-  k_cg_reduce<<<k, 256, 0, s>>>(part_rz, nblk, d_rz[0]);
-  FW_CHECK_CUDA(cudaMemcpyAsync(pv, zv, vec * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  double bnorm2[CG_MAXK], rr[CG_MAXK];
-  FW_CHECK_CUDA(cudaMemcpyAsync(bnorm2, d_rr, sizeof(double) * k, cudaMemcpyDeviceToHost, s));
-  FW_CHECK_CUDA(cudaStreamSynchronize(s));
-  int64_t launches = 4;
-  int cur = 0;
-  const int check_every = 4;
-  for (int it = 0; it < 600; ++it) {
-    k_spmv_multi<<<cdiv((int64_t)n * 8, 256), 256, 0, s>>>(n, k, pat.indptr.p, pat.indices.p, h.Mass.v.p, pv, qv);
-    k_cg_dot<<<nblk, 256, 0, s>>>(n, k, pv, qv, part_pq, nblk);
-    k_cg_reduce<<<k, 256, 0, s>>>(part_pq, nblk, d_pq);
-    k_cg_step<<<nblk, 256, 0, s>>>(n, k, X, rv, pv, qv, zv, idiag.p, d_rz[cur], d_pq, part_rr, part_rz, nblk);
-    k_cg_reduce<<<k, 256, 0, s>>>(part_rr, nblk, d_rr);
-    k_cg_reduce<<<k, 256, 0, s>>>(part_rz, nblk, d_rz[cur ^ 1]);
-    k_cg_direction<<<g256, 256, 0, s>>>(n, k, pv, zv, d_rz[cur ^ 1], d_rz[cur]);
-    cur ^= 1;
-    launches += 7;
-    if ((it + 1) % check_every == 0) {
-      FW_CHECK_CUDA(cudaMemcpyAsync(rr, d_rr, sizeof(double) * k, cudaMemcpyDeviceToHost, s));
-      FW_CHECK_CUDA(cudaStreamSynchronize(s));
-      bool done = true;
-      for (int i = 0; i < k; ++i)
-        if (!(rr[i] <= 1e-26 * bnorm2[i])) done = false;  // ||r|| <= 1e-13 ||b|| (the reference's H carries complex64 rounding, 1e-7)
-      if (done) break;
+  FW_REQUIRE(h.Mass.valid && h.MassC.valid, "mass matrix missing");
+  const size_t n = (size_t)h.sp.n;
+  // systems are solved in groups of 4 / 2 / 1 (compile-time interleave factor)
+  int done = 0;
+  while (done < k) {
+    const int left = k - done;
+    if (left >= 4) {
+      mass_solve_k<4>(h, B + done * n, X + done * n);
+      done += 4;
+    } else if (left >= 2) {
+      mass_solve_k<2>(h, B + done * n, X + done * n);
+      done += 2;
+    } else {
+      mass_solve_k<1>(h, B + done * n, X + done * n);
+      done += 1;
     }
   }
-  FW_CHECK_CUDA(cudaGetLastError());
-  h.tim.kernel_launches += launches;
-  if (getenv("FW_TRACE")) fprintf(stderr, "[fw-trace]   mass PCG: %d rhs, %lld kernel launches (7 per iteration)\n", k, (long long)launches);
 }
 
 }  // namespace fw

@@ -330,7 +330,7 @@ void symbolic_space(Handle& h) {
   tr.mark("symbolic: pattern");
   h.has_symbolic = true;
   h.pat.n_tt = -1;
-  h.A.valid = h.B.valid = h.Mass.valid = h.C0.valid = h.C1.valid = false;
+  h.A.valid = h.B.valid = h.Mass.valid = h.C0.valid = h.C1.valid = h.MassC.valid = false;
 }
 
 // ------------------------------------------------------------------------------ segmented reduce
@@ -492,14 +492,10 @@ __global__ void k_compact_indptr(const int* __restrict__ indptr, int n, const ui
   out[i] = (a >= nnz) ? (int)kept : (int)pos[a];
 }
 
-int64_t count_kept(Handle& h, const Pattern& pat, Values& val) {
+static int64_t count_kept_mask(Handle& h, const Pattern& pat, Values& val, uint8_t mask) {
   cudaStream_t s = h.stream;
-  if (pat.nnz == 0) {
-    val.nnz_kept = 0;
-    return 0;
-  }
+  if (pat.nnz == 0) return 0;
   h.scan_tmp2.alloc((size_t)pat.nnz);
-  const uint8_t mask = h.eliminate_zeros ? 2 : 1;
   k_flag_to_u32<<<cdiv(pat.nnz, 256), 256, 0, s>>>(val.flag.p, pat.nnz, mask, h.scan_tmp2.p);
   exclusive_scan_u32(h.scan_tmp2.p, h.scan_tmp2.p, pat.nnz, h.scan_tmp, s);
   uint32_t last_scan = 0;
@@ -507,20 +503,22 @@ int64_t count_kept(Handle& h, const Pattern& pat, Values& val) {
   FW_CHECK_CUDA(cudaMemcpyAsync(&last_scan, h.scan_tmp2.p + (pat.nnz - 1), 4, cudaMemcpyDeviceToHost, s));
   FW_CHECK_CUDA(cudaMemcpyAsync(&last_flag, val.flag.p + (pat.nnz - 1), 1, cudaMemcpyDeviceToHost, s));
   FW_CHECK_CUDA(cudaStreamSynchronize(s));
-  val.nnz_kept = (int64_t)last_scan + ((last_flag & mask) ? 1 : 0);
+  return (int64_t)last_scan + ((last_flag & mask) ? 1 : 0);
+}
+
+int64_t count_kept(Handle& h, const Pattern& pat, Values& val) {
+  val.nnz_kept = count_kept_mask(h, pat, val, h.eliminate_zeros ? 2 : 1);
   return val.nnz_kept;
 }
 
-void export_compacted(Handle& h, const Pattern& pat, Values& val, int* indptr, int* indices, void* data) {
+int64_t compact_csr_dev(Handle& h, const Pattern& pat, Values& val, uint8_t mask, DevBuf<int>& oip, DevBuf<int>& oind,
+                        DevBuf<double>& oval) {
   cudaStream_t s = h.stream;
-  int64_t kept = count_kept(h, pat, val);  // leaves the scanned positions in scan_tmp2
-  DevBuf<int> oip, oind;
-  DevBuf<double> oval;
+  const int64_t kept = count_kept_mask(h, pat, val, mask);  // leaves the scanned positions in scan_tmp2
   oip.alloc((size_t)pat.n + 1);
   oind.alloc((size_t)(kept ? kept : 1));
-  size_t w = val.is_complex ? 2 : 1;
+  const size_t w = val.is_complex ? 2 : 1;
   oval.alloc((size_t)(kept ? kept : 1) * w);
-  const uint8_t mask = h.eliminate_zeros ? 2 : 1;
   if (pat.nnz) {
     if (val.is_complex)
       k_compact<cplx><<<cdiv(pat.nnz, 256), 256, 0, s>>>(val.flag.p, mask, h.scan_tmp2.p, pat.nnz, pat.indices.p,
@@ -533,6 +531,16 @@ void export_compacted(Handle& h, const Pattern& pat, Values& val, int* indptr, i
     k_fill_empty_indptr<<<cdiv(pat.n + 1, 256), 256, 0, s>>>(oip.p, pat.n);
   }
   FW_CHECK_CUDA(cudaGetLastError());
+  return kept;
+}
+
+void export_compacted(Handle& h, const Pattern& pat, Values& val, int* indptr, int* indices, void* data) {
+  cudaStream_t s = h.stream;
+  DevBuf<int> oip, oind;
+  DevBuf<double> oval;
+  const int64_t kept = compact_csr_dev(h, pat, val, h.eliminate_zeros ? 2 : 1, oip, oind, oval);
+  val.nnz_kept = kept;
+  const size_t w = val.is_complex ? 2 : 1;
   oip.download(indptr, (size_t)pat.n + 1, s);
   oind.download(indices, (size_t)kept, s);
   oval.download((double*)data, (size_t)kept * w, s);

@@ -11,7 +11,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 500
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 m, eps = strip_problem(n, slab_h=0.11)
 b0 = Basis(m, ElementTriP0(), intorder=4)
-for ncv in [0, 20, 24, 28, 32, 40]:
+ncvs = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else [0, 20, 24, 28, 32, 40]
+for ncv in ncvs:
     opts = {} if ncv == 0 else {"ncv": ncv}
     t0 = time.time()
     modes = compute_modes(b0, eps, 1.55, num_modes=k, order=2, solver_options=opts)
