@@ -29,6 +29,18 @@ from .element import (
 from .mesh import MeshTri
 
 
+def _dg_count(elem) -> int:
+    """dofs per element of the element-local (P0 / discontinuous / vector-valued) spaces"""
+    name = type(elem).__name__
+    if name == "ElementTriP0":
+        return 1
+    if name == "ElementDG":
+        return {"ElementTriP0": 1, "ElementTriP1": 3, "ElementTriP2": 6}[type(elem.elem).__name__]
+    if name == "ElementVector":
+        return elem.dim * _dg_count(elem.elem)
+    raise NotImplementedError(f"no dof count for {elem!r}")
+
+
 class Basis:
     def __init__(self, mesh: MeshTri, elem, intorder: Optional[int] = None, elements=None, quadrature=None):
         self.mesh = mesh
@@ -87,8 +99,7 @@ class Basis:
             if self.elem.order == 1:
                 return m.nvertices + m.nfacets
             return m.nvertices + 3 * m.nfacets + 2 * m.nelements
-        kind = eps_kind_of(self.elem)
-        return m.nelements if kind == EPS_P0 else 3 * m.nelements
+        return _dg_count(self.elem) * m.nelements
 
     @property
     def element_dofs(self) -> np.ndarray:

@@ -41,8 +41,9 @@ class Context:
             pass
 
     # ---------------------------------------------------------------- space / symbolic
-    def set_space(self, basis: Basis):
-        """Upload mesh + FE space (a1).  ``basis`` must carry the mixed N x P element."""
+    @staticmethod
+    def _space_struct(basis: Basis):
+        """fw_space of a mode basis + the arrays that must stay alive while it is used"""
         tb = basis.tables()
         m = basis.mesh
         ed = basis.element_dofs
@@ -53,6 +54,12 @@ class Context:
         keep = [L.as_f64(m.p), L.as_i32(m.t), L.as_i32(ed), L.as_i32(tb.kind), L.as_f64(tb.vec), L.as_f64(tb.sc),
                 L.as_f64(tb.X), L.as_f64(tb.W)]
         (s.p, s.t, s.element_dofs, s.kind, s.vec, s.sc, s.X, s.W) = [a.ctypes.data for a in keep]
+        return s, keep, tb
+
+    def set_space(self, basis: Basis):
+        """Upload mesh + FE space (a1).  ``basis`` must carry the mixed N x P element."""
+        s, keep, tb = self._space_struct(basis)
+        m = basis.mesh
         L.check(self.lib.fw_set_space(self._h, C.byref(s)))
         self.basis = basis
         self.n = basis.N
@@ -199,6 +206,30 @@ class Context:
         E, H = L.as_c128(E), L.as_c128(H)
         out = np.empty(3 * self.basis.mesh.nelements, dtype=np.float64)
         L.check(self.lib.fw_intensity(self._h, L.ptr(E), L.ptr(H), L.ptr(out)))
+        return out
+
+    def overlap_cross(self, basis_j: Basis, E_i, H_i, E_j, H_j, mode=0, elements=None):
+        """Cross-mesh overlap / scalar product (waveguide.py:737-782); the current space is basis_i."""
+        s, keep, _ = self._space_struct(basis_j)
+        f = [None if a is None else L.as_c128(a) for a in (E_i, H_i, E_j, H_j)]
+        sel = None if elements is None else L.as_i32(elements)
+        out = np.zeros(2)
+        L.check(self.lib.fw_overlap_cross(self._h, C.byref(s), L.ptr(f[0]), L.ptr(f[1]), L.ptr(f[2]), L.ptr(f[3]),
+                                          int(mode), 0 if sel is None else sel.size, L.ptr(sel), L.ptr(out)))
+        return complex(out[0], out[1])
+
+    def poynting(self, E, H):
+        """complex128 [n_elements * 3 * nl], dof = e*3*nl + a*3 + c (waveguide.py:74-95)."""
+        E, H = L.as_c128(E), L.as_c128(H)
+        nl = 3 if self.basis.elem.order == 1 else 6
+        out = np.empty(self.basis.mesh.nelements * 3 * nl, dtype=np.complex128)
+        L.check(self.lib.fw_poynting(self._h, L.ptr(E), L.ptr(H), L.ptr(out)))
+        return out
+
+    def energy_current_density(self, xs):
+        xs = L.as_c128(xs)
+        out = np.empty(self.basis.mesh.nelements, dtype=np.complex128)
+        L.check(self.lib.fw_energy_current_density(self._h, L.ptr(xs), L.ptr(out)))
         return out
 
     def functional(self, kind, fields, aux=None, aux_kind=0, elements=None, option=0):

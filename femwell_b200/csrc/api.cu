@@ -473,6 +473,64 @@ int fw_intensity(fw_handle* hh, const double* E, const double* H, double* out) {
   FW_API_END
 }
 
+int fw_overlap_cross(fw_handle* hh, const fw_space* space_j, const double* E_i, const double* H_i, const double* E_j,
+                     const double* H_j, int32_t mode, int32_t n_sel, const int32_t* elements, double* out) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && space_j && E_i && H_j && out, "NULL argument");
+  FW_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (overlap) or 1 (scalar product)");
+  FW_REQUIRE(mode == 1 || (H_i && E_j), "the overlap needs all four fields");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  const Space& sp = h.sp;
+  FW_REQUIRE(sp.valid, "fw_set_space must be called first");
+  cudaStream_t s = h.stream;
+  DevBuf<double> dEi, dHi;
+  dEi.upload(E_i, (size_t)sp.n * 2, s);
+  if (H_i) dHi.upload(H_i, (size_t)sp.n * 2, s);
+  DevBuf<int> dsel;
+  if (elements) {
+    for (int i = 0; i < n_sel; ++i) FW_REQUIRE(elements[i] >= 0 && elements[i] < sp.ne, "element index out of range");
+    dsel.upload(elements, (size_t)n_sel, s);
+  }
+  const std::complex<double> r = overlap_cross_dev(h, *space_j, (const cplx*)dEi.p, H_i ? (const cplx*)dHi.p : nullptr,
+                                                   E_j, H_j, mode, n_sel, elements ? dsel.p : nullptr);
+  out[0] = r.real(), out[1] = r.imag();
+  FW_API_END
+}
+
+int fw_poynting(fw_handle* hh, const double* E, const double* H, double* out) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && E && H && out, "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  FW_REQUIRE(h.sp.valid, "space missing");
+  const size_t cnt = (size_t)h.sp.n * 2;
+  const size_t nout = (size_t)h.sp.ne * 3 * (h.sp.nb == 6 ? 3 : 6) * 2;
+  DevBuf<double> dE, dH, dout;
+  dE.upload(E, cnt, h.stream);
+  dH.upload(H, cnt, h.stream);
+  dout.alloc(nout);
+  poynting_dev(h, (const cplx*)dE.p, (const cplx*)dH.p, (cplx*)dout.p);
+  dout.download(out, nout, h.stream);
+  FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
+  FW_API_END
+}
+
+int fw_energy_current_density(fw_handle* hh, const double* xs, double* out) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && xs && out, "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  FW_REQUIRE(h.sp.valid, "space missing");
+  DevBuf<double> dE, dout;
+  dE.upload(xs, (size_t)h.sp.n * 2, h.stream);
+  dout.alloc((size_t)h.sp.ne * 2);
+  energy_density_dev(h, (const cplx*)dE.p, (cplx*)dout.p);
+  dout.download(out, (size_t)h.sp.ne * 2, h.stream);
+  FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
+  FW_API_END
+}
+
 int fw_functional(fw_handle* hh, int32_t kind, const double* f0, const double* f1, const double* f2,
                   const double* f3, int32_t aux_kind, int32_t aux_is_complex, const void* aux, int32_t n_sel,
                   const int32_t* elements, int32_t option, double* out) {

@@ -99,6 +99,8 @@ void reduce_onto_pattern(const Pattern& pat, const S* coo_vals, const int* lut, 
 void build_slot_list(Handle& h, Pattern& pat, const int* lut_dev, int64_t stride);
 int64_t count_kept(Handle& h, const Pattern& pat, Values& val);
 void export_compacted(Handle& h, const Pattern& pat, Values& val, int* indptr, int* indices, void* data);
+void coo_to_csr_dev(Handle& h, int n_rows, int64_t n_entries, DevBuf<int>& dr, DevBuf<int>& dc, DevBuf<double>& dv,
+                    bool is_complex);
 // device-side compaction: keeps the slots whose flag has a bit of `mask` set; returns the number kept
 int64_t compact_csr_dev(Handle& h, const Pattern& pat, Values& val, uint8_t mask, DevBuf<int>& oip, DevBuf<int>& oind,
                         DevBuf<double>& oval);

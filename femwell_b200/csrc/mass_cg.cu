@@ -201,11 +201,15 @@ __global__ void k_cg_interleave(int n, const cplx* __restrict__ in, cplx* __rest
   }
 }
 
+struct CsrView {
+  const int *indptr, *indices;
+  const double* vals;
+  int64_t nnz;
+};
+
 template <int K>
-static void mass_solve_k(Handle& h, const cplx* B, cplx* X) {
-  const int n = h.sp.n;
+static void mass_solve_k(Handle& h, int n, const CsrView& M, const cplx* B, cplx* X) {
   cudaStream_t s = h.stream;
-  const Handle::CompactCsr& M = h.MassC;
   const int nblk = cdiv((int64_t)n * K, 1024);
   const int nblk_mv = cdiv(n, 256 / (2 * K));
   const size_t vec = (size_t)K * n * 2;
@@ -224,7 +228,7 @@ static void mass_solve_k(Handle& h, const cplx* B, cplx* X) {
   const int g256 = cdiv(n, 256);
   Trace tr(s);
   tr.mark("    mass PCG: workspace");
-  k_cg_diag<<<g256, 256, 0, s>>>(n, M.indptr.p, M.indices.p, M.vals.p, idiag.p);
+  k_cg_diag<<<g256, 256, 0, s>>>(n, M.indptr, M.indices, M.vals, idiag.p);
   FW_CHECK_CUDA(cudaMemsetAsync(xv, 0, vec * sizeof(double), s));
   k_cg_interleave<K><<<g256, 256, 0, s>>>(n, B, rv, true);
   k_cg_step<K, true><<<nblk, 256, 0, s>>>(n, (double2*)xv, (double2*)rv, (const double2*)pv, (const double2*)qv, (double2*)zv,
@@ -239,7 +243,7 @@ static void mass_solve_k(Handle& h, const cplx* B, cplx* X) {
   int cur = 0, it = 0;
   const int check_every = 4;
   for (; it < 600; ++it) {
-    k_spmv_multi<K><<<nblk_mv, 256, 0, s>>>(n, M.indptr.p, M.indices.p, M.vals.p, (const double*)pv, (double*)qv, part_pq,
+    k_spmv_multi<K><<<nblk_mv, 256, 0, s>>>(n, M.indptr, M.indices, M.vals, (const double*)pv, (double*)qv, part_pq,
                                             nblk_mv);
     k_cg_reduce<<<K, 256, 0, s>>>(part_pq, nblk_mv, d_pq);
     k_cg_step<K, false><<<nblk, 256, 0, s>>>(n, (double2*)xv, (double2*)rv, (const double2*)pv, (const double2*)qv,
@@ -267,23 +271,32 @@ static void mass_solve_k(Handle& h, const cplx* B, cplx* X) {
             (long long)launches, (long long)M.nnz);
 }
 
-// Mass X = B for k <= CG_MAXK complex right-hand sides ([k][n] each); X overwritten.
+// M X = B for a real SPD CSR matrix and k <= CG_MAXK complex right-hand sides ([k][n] each); X overwritten.
+void pcg_solve_multi(Handle& h, int n_rows, const int* indptr, const int* indices, const double* vals, int64_t nnz,
+                     int k, const cplx* B, cplx* X);
+
 void mass_solve_multi(Handle& h, int k, const cplx* B, cplx* X) {
-  FW_REQUIRE(k >= 1 && k <= CG_MAXK, "mass_solve_multi: 1 <= k <= 8");
   FW_REQUIRE(h.Mass.valid && h.MassC.valid, "mass matrix missing");
-  const size_t n = (size_t)h.sp.n;
+  pcg_solve_multi(h, h.sp.n, h.MassC.indptr.p, h.MassC.indices.p, h.MassC.vals.p, h.MassC.nnz, k, B, X);
+}
+
+void pcg_solve_multi(Handle& h, int n_rows, const int* indptr, const int* indices, const double* vals, int64_t nnz,
+                     int k, const cplx* B, cplx* X) {
+  FW_REQUIRE(k >= 1 && k <= CG_MAXK, "pcg_solve_multi: 1 <= k <= 8");
+  const size_t n = (size_t)n_rows;
+  const CsrView V{indptr, indices, vals, nnz};
   // systems are solved in groups of 4 / 2 / 1 (compile-time interleave factor)
   int done = 0;
   while (done < k) {
     const int left = k - done;
     if (left >= 4) {
-      mass_solve_k<4>(h, B + done * n, X + done * n);
+      mass_solve_k<4>(h, n_rows, V, B + done * n, X + done * n);
       done += 4;
     } else if (left >= 2) {
-      mass_solve_k<2>(h, B + done * n, X + done * n);
+      mass_solve_k<2>(h, n_rows, V, B + done * n, X + done * n);
       done += 2;
     } else {
-      mass_solve_k<1>(h, B + done * n, X + done * n);
+      mass_solve_k<1>(h, n_rows, V, B + done * n, X + done * n);
       done += 1;
     }
   }

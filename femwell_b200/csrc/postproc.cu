@@ -498,6 +498,173 @@ void intensity_dev(Handle& h, const cplx* E, const cplx* Hf, double* out) {
   h.tim.kernel_launches += 1;
 }
 
+// ------------------------------------------------------------------------------ Poynting vector (a16)
+// Mode.poynting (waveguide.py:74-95): P = E x H (no conjugation) at the quadrature points, every component
+// L2-projected onto the discontinuous Lagrange space of the E_z field.  The local mass matrix is |det| times a
+// reference matrix, so the projection is u = Mref^-1 sum_q W phi_a P(q): Mref^-1 (nl x nl, built from the
+// basis quadrature like basis.project does) sits in constant memory.
+__constant__ double c_minv[6][6];
+
+template <int NB>
+__global__ void __launch_bounds__(128) k_poynting(int ne, int nv, const double* __restrict__ p,
+                                                  const int* __restrict__ t, const int* __restrict__ edofs,
+                                                  const cplx* __restrict__ E, const cplx* __restrict__ Hf,
+                                                  cplx* __restrict__ out) {
+  constexpr int NL = NB == 6 ? 3 : 6;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int v0 = t[e], v1 = t[ne + e], v2 = t[2 * ne + e];
+  const double x0 = p[v0], y0 = p[nv + v0];
+  const double a11 = p[v1] - x0, a21 = p[nv + v1] - y0;
+  const double a12 = p[v2] - x0, a22 = p[nv + v2] - y0;
+  const double det = a11 * a22 - a12 * a21;
+  const double idet = 1.0 / det;
+  cplx ce[NB], ch[NB];
+#pragma unroll
+  for (int l = 0; l < NB; ++l) {
+    const int d = edofs[(size_t)l * ne + e];
+    ce[l] = E[d];
+    ch[l] = Hf[d];
+  }
+  cplx rhs[NL][3];
+#pragma unroll
+  for (int a = 0; a < NL; ++a) rhs[a][0] = rhs[a][1] = rhs[a][2] = cplx{0, 0};
+  const int nq = c_ptab.nq;
+  for (int q = 0; q < nq; ++q) {
+    cplx sx{0, 0}, sy{0, 0}, ez{0, 0}, tx{0, 0}, ty{0, 0}, hz{0, 0};
+#pragma unroll
+    for (int l = 0; l < NB; ++l) {
+      if (c_ptab.kind[l] == 0) {
+        fma_(sx, ce[l], c_ptab.vx[l][q]);
+        fma_(sy, ce[l], c_ptab.vy[l][q]);
+        fma_(tx, ch[l], c_ptab.vx[l][q]);
+        fma_(ty, ch[l], c_ptab.vy[l][q]);
+      } else {
+        fma_(ez, ce[l], c_ptab.sc[l][q]);
+        fma_(hz, ch[l], c_ptab.sc[l][q]);
+      }
+    }
+    const cplx ex = (sx * a22 - sy * a21) * idet, ey = (sy * a11 - sx * a12) * idet;
+    const cplx hx = (tx * a22 - ty * a21) * idet, hy = (ty * a11 - tx * a12) * idet;
+    const cplx P[3] = {ey * hz - ez * hy, ez * hx - ex * hz, ex * hy - ey * hx};
+    int a = 0;
+#pragma unroll
+    for (int l = 0; l < NB; ++l) {
+      if (c_ptab.kind[l] == 1) {
+        const double wphi = c_ptab.W[q] * c_ptab.sc[l][q];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) fma_(rhs[a][c], P[c], wphi);
+        ++a;
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NL; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      cplx u{0, 0};
+#pragma unroll
+      for (int b = 0; b < NL; ++b) fma_(u, rhs[b][c], c_minv[a][b]);
+      out[(size_t)e * (3 * NL) + a * 3 + c] = u;
+    }
+}
+
+void poynting_dev(Handle& h, const cplx* E, const cplx* Hf, cplx* out) {
+  const Space& sp = h.sp;
+  FW_REQUIRE(sp.valid, "space missing");
+  upload_ptab(h);
+  // reference mass matrix of the Lagrange functions with the basis quadrature, inverted by Gauss-Jordan
+  const int nl = sp.nb == 6 ? 3 : 6;
+  std::vector<int> lag;
+  for (int l = 0; l < sp.nb; ++l)
+    if (sp.kind[l] == 1) lag.push_back(l);
+  double M[6][12];
+  for (int a = 0; a < nl; ++a)
+    for (int b = 0; b < 2 * nl; ++b) M[a][b] = 0.0;
+  for (int a = 0; a < nl; ++a) {
+    for (int b = 0; b < nl; ++b)
+      for (int q = 0; q < sp.nq; ++q)
+        M[a][b] += sp.W[q] * sp.sc[(size_t)lag[a] * sp.nq + q] * sp.sc[(size_t)lag[b] * sp.nq + q];
+    M[a][nl + a] = 1.0;
+  }
+  for (int c = 0; c < nl; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < nl; ++r)
+      if (fabs(M[r][c]) > fabs(M[piv][c])) piv = r;
+    FW_REQUIRE(fabs(M[piv][c]) > 1e-14, "the basis quadrature cannot resolve the Lagrange mass matrix (singular projection)");
+    if (piv != c)
+      for (int b = 0; b < 2 * nl; ++b) std::swap(M[c][b], M[piv][b]);
+    const double inv = 1.0 / M[c][c];
+    for (int b = 0; b < 2 * nl; ++b) M[c][b] *= inv;
+    for (int r = 0; r < nl; ++r) {
+      if (r == c) continue;
+      const double f = M[r][c];
+      if (f != 0.0)
+        for (int b = 0; b < 2 * nl; ++b) M[r][b] -= f * M[c][b];
+    }
+  }
+  double minv[6][6];
+  memset(minv, 0, sizeof(minv));
+  for (int a = 0; a < nl; ++a)
+    for (int b = 0; b < nl; ++b) minv[a][b] = M[a][nl + b];
+  FW_CHECK_CUDA(cudaMemcpyToSymbol(c_minv, minv, sizeof(minv)));
+  if (sp.nb == 6)
+    k_poynting<6><<<cdiv(sp.ne, 128), 128, 0, h.stream>>>(sp.ne, sp.nv, sp.p.p, sp.t.p, sp.edofs.p, E, Hf, out);
+  else
+    k_poynting<14><<<cdiv(sp.ne, 128), 128, 0, h.stream>>>(sp.ne, sp.nv, sp.p.p, sp.t.p, sp.edofs.p, E, Hf, out);
+  FW_CHECK_CUDA(cudaGetLastError());
+  h.tim.kernel_launches += 1;
+}
+
+// ------------------------------------------------------------------------------ energy current density (a16)
+// calculate_energy_current_density (waveguide.py:680-696): P0 projection of |e_x|^2 + |e_y|^2 + |e_z| (sic: the
+// reference does not square e_z); the P0 mass matrix is diag(area), so the value is sum_q W f / sum_q W.
+template <int NB>
+__global__ void __launch_bounds__(128) k_energy_density(int ne, int nv, const double* __restrict__ p,
+                                                        const int* __restrict__ t, const int* __restrict__ edofs,
+                                                        const cplx* __restrict__ E, cplx* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int v0 = t[e], v1 = t[ne + e], v2 = t[2 * ne + e];
+  const double x0 = p[v0], y0 = p[nv + v0];
+  const double a11 = p[v1] - x0, a21 = p[nv + v1] - y0;
+  const double a12 = p[v2] - x0, a22 = p[nv + v2] - y0;
+  const double idet = 1.0 / (a11 * a22 - a12 * a21);
+  cplx ce[NB];
+#pragma unroll
+  for (int l = 0; l < NB; ++l) ce[l] = E[edofs[(size_t)l * ne + e]];
+  double num = 0.0, den = 0.0;
+  const int nq = c_ptab.nq;
+  for (int q = 0; q < nq; ++q) {
+    cplx sx{0, 0}, sy{0, 0}, ez{0, 0};
+#pragma unroll
+    for (int l = 0; l < NB; ++l) {
+      if (c_ptab.kind[l] == 0) {
+        fma_(sx, ce[l], c_ptab.vx[l][q]);
+        fma_(sy, ce[l], c_ptab.vy[l][q]);
+      } else {
+        fma_(ez, ce[l], c_ptab.sc[l][q]);
+      }
+    }
+    const cplx ex = (sx * a22 - sy * a21) * idet, ey = (sy * a11 - sx * a12) * idet;
+    num += c_ptab.W[q] * (abs2_(ex) + abs2_(ey) + absv_(ez));
+    den += c_ptab.W[q];
+  }
+  out[e] = cplx{num / den, 0.0};
+}
+
+void energy_density_dev(Handle& h, const cplx* E, cplx* out) {
+  const Space& sp = h.sp;
+  FW_REQUIRE(sp.valid, "space missing");
+  upload_ptab(h);
+  if (sp.nb == 6)
+    k_energy_density<6><<<cdiv(sp.ne, 128), 128, 0, h.stream>>>(sp.ne, sp.nv, sp.p.p, sp.t.p, sp.edofs.p, E, out);
+  else
+    k_energy_density<14><<<cdiv(sp.ne, 128), 128, 0, h.stream>>>(sp.ne, sp.nv, sp.p.p, sp.t.p, sp.edofs.p, E, out);
+  FW_CHECK_CUDA(cudaGetLastError());
+  h.tim.kernel_launches += 1;
+}
+
 // waveguide.py:627-639: un-scale E_z, recover H, power-normalise
 void postprocess_modes_dev(Handle& h, int k, const cd* lams, const double* X_dev, double k0, double omega, double mu0,
                            double* E_dev, double* H_dev, cd* powers) {

@@ -21,7 +21,13 @@ void postprocess_modes_dev(Handle& h, int k, const std::complex<double>* lams, c
 void hfield_dev(Handle& h, const cplx* E_dev, cplx beta, double omega, double mu0, cplx* H_dev);
 void hfield_multi_dev(Handle& h, int k, const cplx* E_dev, const cplx* betas, double omega, double mu0, cplx* H_dev);
 void mass_solve_multi(Handle& h, int k, const cplx* B, cplx* X);
+void pcg_solve_multi(Handle& h, int n_rows, const int* indptr, const int* indices, const double* vals, int64_t nnz,
+                     int k, const cplx* B, cplx* X);
+std::complex<double> overlap_cross_dev(Handle& h, const fw_space& sj, const cplx* Ei, const cplx* Hi, const double* Ej_host,
+                                       const double* Hj_host, int mode, int n_sel, const int* elements_dev);
 void intensity_dev(Handle& h, const cplx* E, const cplx* Hf, double* out);
+void poynting_dev(Handle& h, const cplx* E, const cplx* Hf, cplx* out);
+void energy_density_dev(Handle& h, const cplx* E, cplx* out);
 void setup_generic_csr(Handle& h, int n, const int* Kp, const int* Ki, const void* Kx, const int* Mp, const int* Mi,
                        const void* Mx, bool is_complex, const double* coords);
 void functional_dev(Handle& h, int kind, const cplx* f0, const cplx* f1, const cplx* f2, const cplx* f3, int aux_kind,

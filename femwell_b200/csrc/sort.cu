@@ -571,6 +571,15 @@ void coo_to_csr(Handle& h, int n_rows, int64_t n_entries, const int* rows, const
   dr.upload(rows, (size_t)n_entries, s);
   dc.upload(cols, (size_t)n_entries, s);
   dv.upload((const double*)data, (size_t)n_entries * w, s);
+  coo_to_csr_dev(h, n_rows, n_entries, dr, dc, dv, is_complex);
+}
+
+// the same on device-resident triplets (result in h.coo_pat / h.coo_val)
+void coo_to_csr_dev(Handle& h, int n_rows, int64_t n_entries, DevBuf<int>& dr, DevBuf<int>& dc, DevBuf<double>& dv,
+                    bool is_complex) {
+  cudaStream_t s = h.stream;
+  FW_REQUIRE(n_entries < (int64_t)0xffffffffll, "too many COO entries");
+  size_t w = is_complex ? 2 : 1;
   int cb = bit_length(n_rows);  // n_rows < 2^cb strictly, so the sentinel row n_rows fits
   DevBuf<uint64_t> ka, kb;
   DevBuf<uint32_t> pa, pb, hist;

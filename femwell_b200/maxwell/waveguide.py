@@ -93,6 +93,36 @@ class Mode:
         return None if elements is None else self.basis.mesh.normalize_elements(elements)
 
     @cached_property
+    def poynting(self):
+        """Poynting vector E x H projected onto ElementVector(ElementDG(Lagrange), 3) (waveguide.py:74-95).
+        Returns ``(poynting_basis, P_proj)`` like the reference."""
+        from ..element import ElementDG, ElementTriP1, ElementTriP2, ElementVector
+
+        lag = ElementTriP1() if self.basis.elem.order == 1 else ElementTriP2()
+        pbasis = self.basis.with_element(ElementVector(ElementDG(lag), 3))
+        return pbasis, _bind(self.basis).poynting(self.E, self.H)
+
+    def _poynting_component(self, c):
+        from ..element import ElementDG, ElementTriP1, ElementTriP2
+
+        _, P = self.poynting
+        lag = ElementTriP1() if self.basis.elem.order == 1 else ElementTriP2()
+        return self.basis.with_element(ElementDG(lag)), P[c::3]
+
+    @property
+    def Sx(self):
+        """waveguide.py:97-100"""
+        return self._poynting_component(0)
+
+    @property
+    def Sy(self):
+        return self._poynting_component(1)
+
+    @property
+    def Sz(self):
+        return self._poynting_component(2)
+
+    @cached_property
     def te_fraction(self):
         """waveguide.py:112-127"""
         o = _bind(self.basis).functional(FUN_EX2_EY2, [self.E], elements=self.basis.tind)
@@ -257,9 +287,31 @@ def calculate_hfield(basis, xs, beta, omega):
     return _bind(basis).hfield(xs, beta, omega, mu_0)
 
 
+def calculate_energy_current_density(basis, xs):
+    """waveguide.py:680-696; returns ``(basis_energy, values)`` on the P0 basis."""
+    from ..element import ElementTriP0
+
+    return basis.with_element(ElementTriP0()), _bind(basis).energy_current_density(xs)
+
+
+def _same_quadrature_space(basis_i, basis_j):
+    """the reference's same-basis test (waveguide.py:729-731): equal bases, or equal quadrature on one mesh"""
+    return basis_i.mesh is basis_j.mesh and basis_i.elem == basis_j.elem and np.array_equal(basis_i.X, basis_j.X) \
+        and np.array_equal(basis_i.W, basis_j.W)
+
+
 def calculate_overlap(basis_i, E_i, H_i, basis_j, E_j, H_j):
-    """Same-basis branch of waveguide.py:699-736 (same mesh & quadrature)."""
-    if not (basis_i.mesh is basis_j.mesh and np.array_equal(basis_i.X, basis_j.X)
-            and np.array_equal(basis_i.W, basis_j.W)):
-        raise NotImplementedError("cross-mesh overlap (waveguide.py:737-759) is a 'next' row (SURVEY.md 8f)")
-    return _bind(basis_i).functional(FUN_OVERLAP, [E_i, H_i, E_j, H_j], elements=basis_i.tind)[0]
+    """waveguide.py:699-759: same-basis Functional, or (different meshes) P1 projection of mode j on its own mesh
+    evaluated at the quadrature points of basis_i."""
+    if _same_quadrature_space(basis_i, basis_j):
+        return _bind(basis_i).functional(FUN_OVERLAP, [E_i, H_i, E_j, H_j], elements=basis_i.tind)[0]
+    return _bind(basis_i).overlap_cross(basis_j, E_i, H_i, E_j, H_j, mode=0, elements=basis_i.tind)
+
+
+def calculate_scalar_product(basis_i, E_i, basis_j, H_j):
+    """waveguide.py:762-782: int conj(E_i) x H_j (transverse parts)."""
+    if _same_quadrature_space(basis_i, basis_j):
+        # FUN_OVERLAP = 0.5 (conj(E_i) x H_j + E_j x conj(H_i)) with H_i = 0
+        zero = np.zeros(basis_i.N, dtype=np.complex128)
+        return 2 * _bind(basis_i).functional(FUN_OVERLAP, [E_i, zero, zero, H_j], elements=basis_i.tind)[0]
+    return _bind(basis_i).overlap_cross(basis_j, E_i, None, None, H_j, mode=1, elements=basis_i.tind)

@@ -163,6 +163,25 @@ int fw_functional(fw_handle* h, int32_t kind, const double* f0, const double* f1
  *      L2-projected onto discontinuous P1.  E, H [n_dofs] c128; out [3*Ne] f64, dof = 3*e + a.          */
 int fw_intensity(fw_handle* h, const double* E, const double* H, double* out);
 
+/* Cross-mesh branch of calculate_overlap (femwell/maxwell/waveguide.py:737-759) and calculate_scalar_product
+ * (:762-782).  basis_i is the current space of the handle, basis_j is passed as a second space description; its mesh may
+ * differ.  The transverse parts of E_j, H_j are L2-projected onto continuous P1 on mesh j and evaluated at the
+ * quadrature points of mesh i.  mode 0: 0.5 int [conj(E_i) x H_j + E_j x conj(H_i)];
+ * mode 1: int conj(E_i) x H_j (H_i, E_j may be NULL).  elements: optional element subset of basis_i.
+ * Fields complex128 [n_dofs of their basis]; out: complex128 [1].  A quadrature point of mesh i outside mesh j
+ * is an error ("Point is outside of the mesh.").                                                          */
+int fw_overlap_cross(fw_handle* h, const fw_space* space_j, const double* E_i, const double* H_i, const double* E_j,
+                     const double* H_j, int32_t mode, int32_t n_sel, const int32_t* elements, double* out);
+
+/* Mode.poynting (femwell/maxwell/waveguide.py:74-95): P = E x H at the quadrature points projected onto
+ * ElementVector(ElementDG(P1 | P2), 3) (per-element mass solve).  E, H: complex128 [n_dofs];
+ * out: complex128 [n_elements * 3 * nl] with nl = 3 (order 1) or 6 (order 2), dof = e*3*nl + a*3 + c. */
+int fw_poynting(fw_handle* h, const double* E, const double* H, double* out);
+
+/* calculate_energy_current_density (femwell/maxwell/waveguide.py:680-696): P0 projection of
+ * |e_x|^2 + |e_y|^2 + |e_z|.  xs: complex128 [n_dofs]; out: complex128 [n_elements]. */
+int fw_energy_current_density(fw_handle* h, const double* xs, double* out);
+
 /* ---- whole path with HOST buffers (the call the Python shim makes for compute_modes) */
 typedef struct {
   double wavelength, mu_r, radius;

@@ -383,6 +383,96 @@ def calculate_intensity(p, t, dofs, order, X, W, E, H):
     return np.linalg.solve(M, b[:, :, None])[:, :, 0].reshape(-1)
 
 
+def poynting(p, t, dofs, order, X, W, E, H):
+    """waveguide.py:74-95: P = E x H (no conjugation) at the quadrature points, L2-projected component-wise onto
+    ElementVector(ElementDG(Lagrange_order), 3) with the basis quadrature; dof = e*(3*nl) + a*3 + c
+    (scikit-fem ElementVector interleaves the components, ElementDG keeps the local Lagrange order)."""
+    fns, _, dx = physical_basis(order, p, t, X)
+    dxw = dx * W[None, :]
+    (ex, ey), ez = interpolate_mode(fns, dofs, E)
+    (hx, hy), hz = interpolate_mode(fns, dofs, H)
+    P = np.stack([ey * hz - ez * hy, ez * hx - ex * hz, ex * hy - ey * hx])  # (3, Ne, nq)
+    lag = np.stack([f.z for f in fns if f.kind == 1])  # (nl, Ne, nq)
+    M = np.einsum("eq,aeq,beq->eab", dxw, lag, lag)
+    b = np.einsum("eq,aeq,ceq->eac", dxw, lag, P)
+    u = np.linalg.solve(M.astype(complex), b)  # (Ne, nl, 3)
+    return u.reshape(-1)
+
+
+def project_transverse_p1(p, t, dofs, order, X, W, x):
+    """basis.with_element(ElementVector(ElementTriP1())).project(E_t) (waveguide.py:739-746): global L2
+    projection of the transverse field onto continuous P1, component-wise.  Returns (2, Nv) complex."""
+    fns, _, dx = physical_basis(order, p, t, X)
+    dxw = dx * W[None, :]
+    et, _ = interpolate_mode(fns, dofs, x)
+    lam = np.stack([1 - X[0] - X[1], X[0], X[1]])
+    nv = p.shape[1]
+    Ml = np.einsum("eq,aq,bq->abe", dxw, lam, lam)
+    rows = np.repeat(t[:, None, :], 3, axis=1).ravel()
+    cols = np.repeat(t[None, :, :], 3, axis=0).ravel()
+    M = sp.coo_matrix((Ml.ravel(), (rows, cols)), shape=(nv, nv)).tocsc()
+    lu = spla.splu(M)
+    out = np.zeros((2, nv), dtype=complex)
+    for c in range(2):
+        b = np.zeros(nv, dtype=complex)
+        bl = np.einsum("eq,aq,eq->ae", dxw, lam, et[c])
+        np.add.at(b, t.ravel(), bl.ravel())
+        out[c] = lu.solve(b.real) + 1j * lu.solve(b.imag)
+    return out
+
+
+def locate_points(p, t, pts):
+    """index of a triangle containing every point (smallest index), barycentric coordinates (brute force)."""
+    v0 = p[:, t[0]]
+    e1, e2 = p[:, t[1]] - v0, p[:, t[2]] - v0
+    det = e1[0] * e2[1] - e1[1] * e2[0]
+    tri = np.full(pts.shape[1], -1)
+    l1o, l2o = np.zeros(pts.shape[1]), np.zeros(pts.shape[1])
+    for i in range(pts.shape[1]):
+        dxp, dyp = pts[0, i] - v0[0], pts[1, i] - v0[1]
+        l1 = (dxp * e2[1] - dyp * e2[0]) / det
+        l2 = (dyp * e1[0] - dxp * e1[1]) / det
+        ok = np.nonzero((l1 >= -1e-10) & (l2 >= -1e-10) & (l1 + l2 <= 1 + 1e-10))[0]
+        if ok.size == 0:
+            raise ValueError("Point is outside of the mesh.")
+        tri[i], l1o[i], l2o[i] = ok[0], l1[ok[0]], l2[ok[0]]
+    return tri, l1o, l2o
+
+
+def overlap_cross(pi, ti, dofs_i, order_i, Xi, Wi, E_i, H_i, pj, tj, dofs_j, order_j, Xj, Wj, E_j, H_j, mode=0):
+    """Different-mesh branch of calculate_overlap (waveguide.py:737-759; mode 0) and of
+    calculate_scalar_product (:762-782; mode 1)."""
+    fns, xq, dx = physical_basis(order_i, pi, ti, Xi)
+    dxw = dx * Wi[None, :]
+    ei, _ = interpolate_mode(fns, dofs_i, E_i)
+    Hp = project_transverse_p1(pj, tj, dofs_j, order_j, Xj, Wj, H_j)
+    pts = xq.reshape(2, -1)
+    tri, l1, l2 = locate_points(pj, tj, pts)
+    l0 = 1 - l1 - l2
+
+    def at_points(U):
+        v = U[:, tj[0, tri]] * l0 + U[:, tj[1, tri]] * l1 + U[:, tj[2, tri]] * l2
+        return v.reshape(2, *xq.shape[1:])
+
+    hj = at_points(Hp)
+    val = np.conj(ei[0]) * hj[1] - np.conj(ei[1]) * hj[0]
+    if mode == 0:
+        hi, _ = interpolate_mode(fns, dofs_i, H_i)
+        ej = at_points(project_transverse_p1(pj, tj, dofs_j, order_j, Xj, Wj, E_j))
+        val = 0.5 * (val + ej[0] * np.conj(hi[1]) - ej[1] * np.conj(hi[0]))
+    return np.sum(val * dxw)
+
+
+def energy_current_density(p, t, dofs, order, X, W, xs):
+    """waveguide.py:680-696: P0 mass solve of the linear form |e_x|^2 + |e_y|^2 + |e_z| (e_z not squared)."""
+    fns, _, dx = physical_basis(order, p, t, X)
+    dxw = dx * W[None, :]
+    (ex, ey), ez = interpolate_mode(fns, dofs, xs)
+    a = np.sum(dxw * (np.abs(ex) ** 2 + np.abs(ey) ** 2 + np.abs(ez)), axis=1).astype(complex)
+    b = np.sum(dxw, axis=1)
+    return a / b
+
+
 # ----------------------------------------------------------------------------- driver
 @dataclass
 class OracleModes:

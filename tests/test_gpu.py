@@ -389,6 +389,76 @@ def test_hfield_and_functionals_match_oracle(ctx):
     assert np.linalg.norm(inten - inten_ref) < 1e-10 * np.linalg.norm(inten_ref)
 
 
+@pytest.mark.parametrize("order", [1, 2])
+def test_poynting_matches_oracle(ctx, order):
+    """Mode.poynting / Sx, Sy, Sz (waveguide.py:74-110): DG projection of E x H."""
+    from femwell_b200.maxwell.waveguide import Mode
+
+    m, eps = strip_problem(9, jitter=0.15)
+    b = Basis(m, ElementTriP0(), intorder=4).with_element(mode_element(order))
+    rng = np.random.default_rng(11)
+    E = rng.standard_normal(b.N) + 1j * rng.standard_normal(b.N)
+    H = rng.standard_normal(b.N) + 1j * rng.standard_normal(b.N)
+    ref = fo.poynting(m.p, m.t.astype(np.int64), b.element_dofs.astype(np.int64), order, b.X, b.W, E, H)
+    mode = Mode(frequency=1.0, k=1.0, basis_epsilon_r=b.with_element(ElementTriP0()), epsilon_r=eps, basis=b, E=E, H=H)
+    pb, P = mode.poynting
+    nl = 3 if order == 1 else 6
+    assert P.shape == (m.nelements * 3 * nl,) and pb.N == P.size
+    assert np.abs(P - ref).max() < 1e-11 * np.abs(ref).max()
+    for c, (bc, S) in enumerate((mode.Sx, mode.Sy, mode.Sz)):
+        assert bc.N == S.size == m.nelements * nl
+        assert np.array_equal(S, P[c::3])
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_energy_current_density_matches_oracle(ctx, order):
+    from femwell_b200.maxwell.waveguide import calculate_energy_current_density
+
+    m, _ = strip_problem(9, jitter=0.15)
+    b = Basis(m, ElementTriP0(), intorder=4).with_element(mode_element(order))
+    rng = np.random.default_rng(12)
+    xs = rng.standard_normal(b.N) + 1j * rng.standard_normal(b.N)
+    ref = fo.energy_current_density(m.p, m.t.astype(np.int64), b.element_dofs.astype(np.int64), order, b.X, b.W, xs)
+    be, got = calculate_energy_current_density(b, xs)
+    assert be.N == got.size == m.nelements
+    assert np.abs(got - ref).max() < 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("order_i,order_j", [(2, 2), (1, 2), (2, 1)])
+def test_cross_mesh_overlap_matches_oracle(ctx, order_i, order_j):
+    """calculate_overlap / calculate_scalar_product between modes on DIFFERENT meshes (waveguide.py:737-782)."""
+    from femwell_b200.maxwell.waveguide import calculate_overlap, calculate_scalar_product
+
+    mi, _ = strip_problem(9, jitter=0.15)
+    mj, _ = strip_problem(12, jitter=0.1)
+    bi = Basis(mi, ElementTriP0(), intorder=4).with_element(mode_element(order_i))
+    bj = Basis(mj, ElementTriP0(), intorder=4).with_element(mode_element(order_j))
+    rng = np.random.default_rng(21)
+
+    def smooth(b):
+        # smooth-ish fields: low-order random combination so that the P1 projection is well resolved
+        return rng.standard_normal(b.N) + 1j * rng.standard_normal(b.N)
+
+    E_i, H_i, E_j, H_j = smooth(bi), smooth(bi), smooth(bj), smooth(bj)
+    args = (mi.p, mi.t.astype(np.int64), bi.element_dofs.astype(np.int64), order_i, bi.X, bi.W, E_i, H_i,
+            mj.p, mj.t.astype(np.int64), bj.element_dofs.astype(np.int64), order_j, bj.X, bj.W, E_j, H_j)
+    ref = fo.overlap_cross(*args, mode=0)
+    got = calculate_overlap(bi, E_i, H_i, bj, E_j, H_j)
+    assert abs(got - ref) < 1e-10 * abs(ref), (got, ref)
+    ref1 = fo.overlap_cross(*args, mode=1)
+    got1 = calculate_scalar_product(bi, E_i, bj, H_j)
+    assert abs(got1 - ref1) < 1e-10 * abs(ref1), (got1, ref1)
+    # same basis: the scalar product reduces to the Functional on one mesh
+    same = calculate_scalar_product(bi, E_i, bi, H_i)
+    full = calculate_overlap(bi, E_i, H_i, bi, E_i, H_i)
+    assert abs(0.5 * (same + np.conj(same)) - full) < 1e-12 * abs(full)
+    # a foreign mesh that does not cover basis_i is an error, like scikit-fem's element finder
+    mk = MeshTri(mj.p * 0.5, mj.t)
+    bk = Basis(mk, ElementTriP0(), intorder=4).with_element(mode_element(order_j))
+    with pytest.raises(Exception, match="outside of the mesh"):
+        calculate_overlap(bi, E_i, H_i, bk, E_j, H_j)
+
+
 def test_argument_validation(ctx):
     from femwell_b200.maxwell.waveguide import compute_modes
 
