@@ -234,3 +234,47 @@ def test_bridge_extracts_arrays_from_duck_typed_basis():
 
     kind, vec, sc = bridge.tables_from_lbasis(FakeElem(), X, 2)
     assert np.array_equal(kind, tb.kind) and np.allclose(vec, tb.vec) and np.allclose(sc, tb.sc)
+
+
+# ----------------------------------------------------------------------------- oracle: analytic pins of the widened rows
+def _constant_field_dofs(m, b, c):
+    """order-1 dofs of the constant transverse field c (Whitney dofs are tangential line integrals)."""
+    x = np.zeros(b.N, dtype=complex)
+    lo, hi = m.facets
+    x[m.nvertices:] = c[0] * (m.p[0, hi] - m.p[0, lo]) + c[1] * (m.p[1, hi] - m.p[1, lo])
+    return x
+
+
+def test_oracle_cross_mesh_overlap_and_poynting_of_constant_fields():
+    """Constant transverse fields are in the N1 space and in P1: the cross-mesh overlap (P1 projection on mesh j,
+    point location, quadrature on mesh i) must return the analytic value c x c' * area; E x H is constant too."""
+    mi, _ = strip_problem(5, jitter=0.15)
+    mj, _ = strip_problem(7, jitter=0.1)
+    bi = Basis(mi, ElementTriP0(), intorder=4).with_element(mode_element(1))
+    bj = Basis(mj, ElementTriP0(), intorder=4).with_element(mode_element(1))
+    cEi, cHi = np.array([1.0 + 0.5j, -2.0j]), np.array([0.3, 1.0 - 1.0j])
+    cEj, cHj = np.array([0.7j, 1.5]), np.array([-1.0 + 0.2j, 0.4])
+    E_i, H_i = _constant_field_dofs(mi, bi, cEi), _constant_field_dofs(mi, bi, cHi)
+    E_j, H_j = _constant_field_dofs(mj, bj, cEj), _constant_field_dofs(mj, bj, cHj)
+    ti, tj = mi.t.astype(np.int64), mj.t.astype(np.int64)
+    di, dj = bi.element_dofs.astype(np.int64), bj.element_dofs.astype(np.int64)
+    U = fo.project_transverse_p1(mj.p, tj, dj, 1, bj.X, bj.W, H_j)
+    assert np.abs(U - cHj[:, None]).max() < 1e-12
+    e1 = mi.p[:, ti[1]] - mi.p[:, ti[0]]
+    e2 = mi.p[:, ti[2]] - mi.p[:, ti[0]]
+    area = 0.5 * np.abs(e1[0] * e2[1] - e1[1] * e2[0]).sum()
+    cross = lambda a, b: a[0] * b[1] - a[1] * b[0]
+    got = fo.overlap_cross(mi.p, ti, di, 1, bi.X, bi.W, E_i, H_i, mj.p, tj, dj, 1, bj.X, bj.W, E_j, H_j, mode=0)
+    want = 0.5 * (cross(np.conj(cEi), cHj) + cross(cEj, np.conj(cHi))) * area
+    assert abs(got - want) < 1e-12 * abs(want)
+    got1 = fo.overlap_cross(mi.p, ti, di, 1, bi.X, bi.W, E_i, None, mj.p, tj, dj, 1, bj.X, bj.W, None, H_j, mode=1)
+    assert abs(got1 - cross(np.conj(cEi), cHj) * area) < 1e-12 * abs(want)
+    # same mesh: the cross-mesh formula with identical meshes equals the one-mesh Functional for P1-exact fields
+    same = fo.calculate_overlap(mi.p, ti, di, 1, bi.X, bi.W, E_i, H_i, E_i, H_i)
+    assert abs(same - 0.5 * (cross(np.conj(cEi), cHi) + cross(cEi, np.conj(cHi))) * area) < 1e-12 * abs(same)
+    # Poynting vector of constant transverse fields: only P_z = Ex Hy - Ey Hx, constant in every DG dof
+    P = fo.poynting(mi.p, ti, di, 1, bi.X, bi.W, E_i, H_i).reshape(-1, 3, 3)
+    assert np.abs(P[:, :, 2] - cross(cEi, cHi)).max() < 1e-12 and np.abs(P[:, :, :2]).max() < 1e-12
+    # energy density |ex|^2 + |ey|^2 (+ |ez| = 0)
+    ed = fo.energy_current_density(mi.p, ti, di, 1, bi.X, bi.W, E_i)
+    assert np.abs(ed - (abs(cEi[0]) ** 2 + abs(cEi[1]) ** 2)).max() < 1e-12
