@@ -126,7 +126,9 @@ __device__ __forceinline__ void diag_commit(S (*D)[PW + 1], const S (&dn)[DPT], 
 }
 
 // ------------------------------------------------------------------------------ forward chain
-template <class S, int NRHS, class SY>
+// FUSE: the CTA also updates the boundary rows (w2 -= L21 x1) panel by panel, so the level needs no k_fwd_update
+// launch (levels of many small fronts: one contiguous pass over the L panel, no second kernel, no tail).
+template <class S, int NRHS, class SY, bool FUSE = false>
 __device__ __forceinline__ void fwd_chain_body(FrontTab T, const int* __restrict__ nodes, const S* __restrict__ F,
                                                const int* __restrict__ rowperm, S* work, int64_t work_stride, S* xp,
                                                int na) {
@@ -185,6 +187,7 @@ __device__ __forceinline__ void fwd_chain_body(FrontTab T, const int* __restrict
     for (int r = 0; r < NRHS; ++r) w[r][i] = xp[(size_t)r * na + os + src];
   }
   SY::sync();
+  const int rlim = FUSE ? m : ns;  // rows folded by this kernel
   for (int k0 = 0; k0 < ns; k0 += PW) {
     const int wd = min(PW, ns - k0);
     if (pipelined) {
@@ -237,7 +240,7 @@ __device__ __forceinline__ void fwd_chain_body(FrontTab T, const int* __restrict
       }
     } else {
       const int first = (pipelined && wd == PW) ? row0 + nth : k0 + wd + gt;
-      for (int row = first; row < ns; row += nth) {
+      for (int row = first; row < rlim; row += nth) {
         if (row < k0 + wd) continue;
         S acc[NRHS];
 #pragma unroll
@@ -266,6 +269,13 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_fwd_chain(FrontTab T, con
   fwd_chain_body<S, NRHS, SyncCta>(T, nodes, F, rowperm, work, work_stride, xp, na);
 }
 template <class S, int NRHS>
+__global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_fwd_chain_fused(FrontTab T, const int* __restrict__ nodes,
+                                                                       const S* __restrict__ F,
+                                                                       const int* __restrict__ rowperm, S* work,
+                                                                       int64_t work_stride, S* xp, int na) {
+  fwd_chain_body<S, NRHS, SyncCta, true>(T, nodes, F, rowperm, work, work_stride, xp, na);
+}
+template <class S, int NRHS>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
     k_fwd_chain_cluster(FrontTab T, const int* __restrict__ nodes, const S* __restrict__ F,
                         const int* __restrict__ rowperm, S* work, int64_t work_stride, S* xp, int na) {
@@ -273,20 +283,52 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
 }
 
 // ------------------------------------------------------------------------------ backward chain (right-looking)
-template <class S, int NRHS, class SY>
+constexpr int FUSE_CHUNK = 128;  // boundary columns staged per step of the fused backward update
+
+// FUSE: the CTA first gathers x2 from the parent and folds it into the own rows (w1 -= U12 x2), so the level needs
+// no k_bwd_update launch.
+template <class S, int NRHS, class SY, bool FUSE = false>
 __device__ __forceinline__ void bwd_chain_body(FrontTab T, const int* __restrict__ nodes, const S* __restrict__ F,
                                                S* work, int64_t work_stride, S* xp, int na) {
   __shared__ S D[PW][PW + 1];
   __shared__ S xs[NRHS][PW];
+  __shared__ S x2[FUSE ? NRHS : 1][FUSE ? FUSE_CHUNK : 1];
   const int node = nodes[SY::front(blockIdx.x)];
   const int m = T.m[node], ns = T.ns[node], os = T.own_start[node];
-  if (ns == 0) return;
   const S* Fn = F + T.front_off[node];
   S* w[NRHS];
 #pragma unroll
   for (int r = 0; r < NRHS; ++r) w[r] = work + (size_t)r * work_stride + T.work_off[node];
   const int t = threadIdx.x;
   const int nthr = blockDim.x;
+  if constexpr (FUSE) if (m > ns) {
+    const int p = T.parent[node];
+    const int nbd = m - ns;
+    const int* rel = T.rel + T.blist_off[node];
+    for (int c0 = 0; c0 < nbd; c0 += FUSE_CHUNK) {
+      const int cn = min(FUSE_CHUNK, nbd - c0);
+      for (int c = t; c < cn; c += nthr) {
+        const int ri = rel[c0 + c];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+          const S v = work[(size_t)r * work_stride + T.work_off[p] + ri];
+          x2[r][c] = v;
+          w[r][ns + c0 + c] = v;  // the children of this front gather from here
+        }
+      }
+      __syncthreads();
+      for (int row = t; row < ns; row += nthr) {
+        S acc[NRHS];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) acc[r] = w[r][row];
+        row_dot_sub<S, NRHS, FUSE_CHUNK>(acc, Fn + row + (long long)(ns + c0) * m, m, cn, x2);
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) w[r][row] = acc[r];
+      }
+      __syncthreads();
+    }
+  }
+  if (ns == 0) return;
   const int nth = nthr * SY::nctas();
   const int gt = SY::rank() * nthr + t;
   const int npan = (ns + PW - 1) / PW;
@@ -372,6 +414,12 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_bwd_chain(FrontTab T, con
                                                                  const S* __restrict__ F, S* work,
                                                                  int64_t work_stride, S* xp, int na) {
   bwd_chain_body<S, NRHS, SyncCta>(T, nodes, F, work, work_stride, xp, na);
+}
+template <class S, int NRHS>
+__global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_bwd_chain_fused(FrontTab T, const int* __restrict__ nodes,
+                                                                       const S* __restrict__ F, S* work,
+                                                                       int64_t work_stride, S* xp, int na) {
+  bwd_chain_body<S, NRHS, SyncCta, true>(T, nodes, F, work, work_stride, xp, na);
 }
 template <class S, int NRHS>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
@@ -808,6 +856,8 @@ static void solve_typed(Handle& h, const S* b, S* x) {
   const bool trace2 = tenv && atoi(tenv) >= 2;
   const bool no_cluster = getenv("FW_NO_CLUSTER") != nullptr;
   const bool no_inv = getenv("FW_NO_DINV") != nullptr;
+  // levels of many small fronts: chain and off-diagonal update in one kernel (FW_FUSE_MAX_M=0 disables)
+  static const int fuse_max_m = getenv("FW_FUSE_MAX_M") ? atoi(getenv("FW_FUSE_MAX_M")) : 512;
   auto use_inv = [&](int max_ns) {
     return !scalar_traits<S>::is_complex && d.dinv_valid && !no_cluster && !no_inv && max_ns > CL_MIN_NS &&
            max_ns <= CL * CL_THREADS;
@@ -818,7 +868,12 @@ static void solve_typed(Handle& h, const S* b, S* x) {
     const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
     const int* nodes = d.level_nodes.p + Sy.level_start[lev];
     const int max_ns = Sy.level_max_ns[lev];
-    if (use_inv(max_ns))
+    // measured (500k triangles): forward fusion pays only when the pivot block spans several panels
+    const bool fuse = Sy.level_max_m[lev] <= fuse_max_m && nfront >= 296 && max_ns >= 64;
+    if (fuse)
+      k_fwd_chain_fused<S, NRHS><<<nfront, chain_threads(Sy.level_max_m[lev]), 0, s>>>(T, nodes, F, d.rowperm.p, work,
+                                                                                    Sy.work_entries, xp, na);
+    else if (use_inv(max_ns))
       launch_inv_chain<S, NRHS>(true, nfront, T, nodes, F, d, work, Sy.work_entries, xp, na, s);
     else if (max_ns > CL_MIN_NS && !no_cluster)
       k_fwd_chain_cluster<S, NRHS><<<nfront * CL, CL_THREADS, 0, s>>>(T, nodes, F, d.rowperm.p, work,
@@ -830,7 +885,7 @@ static void solve_typed(Handle& h, const S* b, S* x) {
     if (trace2)
       tr.mark(("fwd chain  lev " + std::to_string(lev) + " fronts " + std::to_string(nfront) + " max_ns " +
                std::to_string(max_ns)).c_str());
-    const int tiles = (Sy.level_max_nb[lev] + UPD_ROWS - 1) / UPD_ROWS;
+    const int tiles = fuse ? 0 : (Sy.level_max_nb[lev] + UPD_ROWS - 1) / UPD_ROWS;
     if (tiles > 0) {
       const int nz = upd_splits(nfront, tiles, max_ns);
       if (nz > 1) d.scratch.alloc((size_t)std::max<int64_t>(1, Sy.work_entries) * 16 * 2 * wsc);
@@ -852,7 +907,8 @@ static void solve_typed(Handle& h, const S* b, S* x) {
     const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
     const int* nodes = d.level_nodes.p + Sy.level_start[lev];
     const int max_ns = Sy.level_max_ns[lev];
-    if (Sy.level_max_nb[lev] > 0) {
+    const bool fuse = Sy.level_max_m[lev] <= fuse_max_m && nfront >= 296;
+    if (Sy.level_max_nb[lev] > 0 && !fuse) {
       const int tiles = std::max(1, (max_ns + UPD_ROWS - 1) / UPD_ROWS);
       const int max_nb = Sy.level_max_nb[lev];
       const int nz = upd_splits(nfront, tiles, max_nb);
@@ -869,7 +925,10 @@ static void solve_typed(Handle& h, const S* b, S* x) {
       }
       if (trace2) tr.mark(("bwd update lev " + std::to_string(lev)).c_str());
     }
-    if (use_inv(max_ns))
+    if (fuse)
+      k_bwd_chain_fused<S, NRHS><<<nfront, chain_threads(std::max(max_ns, 64)), 0, s>>>(T, nodes, F, work, Sy.work_entries,
+                                                                                     xp, na);
+    else if (use_inv(max_ns))
       launch_inv_chain<S, NRHS>(false, nfront, T, nodes, F, d, work, Sy.work_entries, xp, na, s);
     else if (max_ns > CL_MIN_NS && !no_cluster)
       k_bwd_chain_cluster<S, NRHS><<<nfront * CL, CL_THREADS, 0, s>>>(T, nodes, F, work, Sy.work_entries, xp, na);

@@ -56,7 +56,7 @@ void parallel_chunks(int n, int min_per_thread, F&& f) {
 
 void lu_symbolic_build(LUSymbolic& S, int n, int nb, int ne, const int* edofs, const double* cx, const double* cy,
                        const uint8_t* active, int leaf_elements) {
-  if (leaf_elements <= 0) leaf_elements = 32;
+  if (leaf_elements <= 0) leaf_elements = 16;  // measured at 500k triangles: 8: 6.0, 16: 5.75, 32: 6.4 ms per solve
   S = LUSymbolic();
   S.n = n;
   const bool trace = getenv("FW_TRACE") != nullptr;
