@@ -54,6 +54,8 @@ class ClockSampler:
         self.rows, self.proc, self.gpu = [], None, gpu_index
 
     def start(self):
+        if os.environ.get("FW_BENCH_NO_SAMPLER"):  # diagnostics only: is the polling itself perturbing the run?
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
@@ -223,6 +225,9 @@ def main():
         modes, dt = one_step()
         tim = modes.stats["timings"]
         dev_ms.append(tim["total_ms"])
+        if rank == 0:
+            print("[bench] step stages (ms): " + ", ".join(f"{k[:-3]} {v:.1f}" for k, v in tim.items() if k.endswith("_ms")),
+                  file=sys.stderr, flush=True)
         elem_ms.append(tim["element_kernel_ms"])
         e2e_s.append(dt)
         launches += tim["kernel_launches"]
@@ -290,6 +295,7 @@ def main():
             "stages_ms": {kk: vv for kk, vv in stats["timings"].items()},
             "solver": {kk: vv for kk, vv in stats.items() if kk != "timings"},
             "n_eff": [float(x.real) for x in modes.n_effs],
+            "step_ms": [float(x) for x in dev_ms],
             "assembly_nnz_per_s": None}
     # assembly nnz/s (BASELINE.json metric 2): structural nnz(A)+nnz(B_tt) / (element kernel + reduce)
     try:

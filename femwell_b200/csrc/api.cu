@@ -29,6 +29,8 @@ struct fw_handle {
 namespace fw {
 Handle::Handle() {}
 Handle::~Handle() {
+  lu_prefetch.reset();
+  if (stream) cudaStreamSynchronize(stream);
   lu.reset();
   for (int i = 0; i < 2; ++i) {
     if (pinned[i]) cudaFreeHost(pinned[i]);
@@ -73,6 +75,41 @@ void download_staged(Handle& h, void* host_dst, const void* dev_src, size_t byte
     memcpy(dst, src, len / nthreads);
     for (auto& th : team) th.join();
   }
+}
+// The mirror image for large pageable-host -> device copies (mesh arrays, LU analysis tables): a thread team fills
+// one pinned buffer while the other one is on the bus.
+void upload_staged(Handle& h, void* dev_dst, const void* host_src, size_t bytes) {
+  constexpr size_t CHUNK = (size_t)32 << 20;
+  if (bytes == 0) return;
+  if (bytes < ((size_t)4 << 20)) {
+    FW_CHECK_CUDA(cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, h.stream));
+    return;
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (!h.pinned[i]) FW_CHECK_CUDA(cudaHostAlloc(&h.pinned[i], CHUNK, cudaHostAllocDefault));
+    if (!h.pinned_ev[i]) FW_CHECK_CUDA(cudaEventCreateWithFlags(&h.pinned_ev[i], cudaEventDisableTiming));
+  }
+  // pending device->host use of the ring (download_staged) has been synchronised by its caller
+  const size_t nchunk = (bytes + CHUNK - 1) / CHUNK;
+  const int nthreads = 4;
+  for (size_t c = 0; c < nchunk; ++c) {
+    const int b = (int)(c & 1);
+    if (c >= 2) FW_CHECK_CUDA(cudaEventSynchronize(h.pinned_ev[b]));  // the DMA out of this buffer has finished
+    const size_t off = c * CHUNK, len = std::min(CHUNK, bytes - off);
+    const char* src = (const char*)host_src + off;
+    char* dst = (char*)h.pinned[b];
+    std::vector<std::thread> team;
+    for (int t = 1; t < nthreads; ++t) {
+      const size_t a = len * t / nthreads, e = len * (t + 1) / nthreads;
+      team.emplace_back([=] { memcpy(dst + a, src + a, e - a); });
+    }
+    memcpy(dst, src, len / nthreads);
+    for (auto& th : team) th.join();
+    FW_CHECK_CUDA(cudaMemcpyAsync((char*)dev_dst + off, h.pinned[b], len, cudaMemcpyHostToDevice, h.stream));
+    FW_CHECK_CUDA(cudaEventRecord(h.pinned_ev[b], h.stream));
+  }
+  // the ring may be reused by the next staged copy only after these DMAs: wait here (the host data may also go away)
+  FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
 }
 }  // namespace fw
 
@@ -136,6 +173,7 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
   FW_REQUIRE(hh && s, "NULL argument");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   FW_REQUIRE(s->order == 1 || s->order == 2, "Only order 1 and 2 implemented by now.");
   const int nb = s->order == 1 ? 6 : 14;
   FW_REQUIRE(s->nbfun == nb, "nbfun does not match order");
@@ -143,6 +181,7 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
   FW_REQUIRE(s->n_vertices > 0 && s->n_elements > 0 && s->n_dofs > 0, "empty mesh");
   FW_REQUIRE(s->p && s->t && s->element_dofs && s->kind && s->vec && s->sc && s->X && s->W, "NULL array");
   Space& sp = h.sp;
+  h.lu_prefetch.reset();  // joins a pending analysis before the host arrays change
   Timer tu(h.stream);
   sp.order = s->order;
   sp.nv = s->n_vertices;
@@ -165,19 +204,50 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
   sp.h_p.assign(s->p, s->p + (size_t)2 * sp.nv);
   sp.h_t.assign(s->t, s->t + (size_t)3 * sp.ne);
   sp.h_edofs.assign(s->element_dofs, s->element_dofs + (size_t)nb * sp.ne);
-  // validate indices on the host (cheap, avoids device faults on bad input)
-  for (size_t i = 0; i < sp.h_t.size(); ++i) FW_REQUIRE(sp.h_t[i] >= 0 && sp.h_t[i] < sp.nv, "t out of range");
+  // validate indices on the host (avoids device faults on bad input) and mark the Lagrange dofs; a few threads,
+  // the connectivity has 14 x Ne entries
   std::vector<uint8_t> isz((size_t)sp.n, 0);
-  for (int l = 0; l < nb; ++l)
-    for (int e = 0; e < sp.ne; ++e) {
-      int d = sp.h_edofs[(size_t)l * sp.ne + e];
-      FW_REQUIRE(d >= 0 && d < sp.n, "element_dofs out of range");
-      if (sp.kind[l] == 1) isz[d] = 1;
+  {
+    const int nthr = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    std::vector<int> bad(nthr, 0);
+    std::vector<std::thread> team;
+    uint8_t* iszp = isz.data();
+    for (int w = 0; w < nthr; ++w) {
+      team.emplace_back([&, w] {
+        const int ea = (int)((int64_t)sp.ne * w / nthr), eb = (int)((int64_t)sp.ne * (w + 1) / nthr);
+        int b = 0;
+        for (int a = 0; a < 3; ++a)
+          for (int e = ea; e < eb; ++e) {
+            const int v = sp.h_t[(size_t)a * sp.ne + e];
+            b |= (v < 0 || v >= sp.nv) ? 1 : 0;
+          }
+        for (int l = 0; l < nb; ++l) {
+          const bool z = sp.kind[l] == 1;
+          for (int e = ea; e < eb; ++e) {
+            const int d = sp.h_edofs[(size_t)l * sp.ne + e];
+            if (d < 0 || d >= sp.n)
+              b |= 2;
+            else if (z)
+              iszp[d] = 1;  // benign race: every writer stores the same value
+          }
+        }
+        bad[w] = b;
+      });
     }
-  sp.p.upload(sp.h_p.data(), sp.h_p.size(), h.stream);
-  sp.t.upload(sp.h_t.data(), sp.h_t.size(), h.stream);
-  sp.edofs.upload(sp.h_edofs.data(), sp.h_edofs.size(), h.stream);
-  sp.is_z.upload(isz.data(), isz.size(), h.stream);
+    for (auto& th : team) th.join();
+    int b = 0;
+    for (int v : bad) b |= v;
+    FW_REQUIRE(!(b & 1), "t out of range");
+    FW_REQUIRE(!(b & 2), "element_dofs out of range");
+  }
+  sp.p.alloc(sp.h_p.size());
+  sp.t.alloc(sp.h_t.size());
+  sp.edofs.alloc(sp.h_edofs.size());
+  sp.is_z.alloc(isz.size());
+  upload_staged(h, sp.p.p, sp.h_p.data(), sp.h_p.size() * sizeof(double));
+  upload_staged(h, sp.t.p, sp.h_t.data(), sp.h_t.size() * sizeof(int));
+  upload_staged(h, sp.edofs.p, sp.h_edofs.data(), sp.h_edofs.size() * sizeof(int));
+  upload_staged(h, sp.is_z.p, isz.data(), isz.size());
   FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
   sp.valid = true;
   h.generic.valid = false;
@@ -207,6 +277,7 @@ int fw_symbolic(fw_handle* hh, int64_t* nnz) {
   FW_REQUIRE(hh, "handle is NULL");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   Timer t(h.stream);
   symbolic_space(h);
   h.tim.symbolic_ms = t.stop();
@@ -220,6 +291,7 @@ int fw_assemble_waveguide(fw_handle* hh, int32_t eps_kind, int32_t eps_is_comple
   FW_REQUIRE(hh, "handle is NULL");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   assemble_waveguide(h, eps_kind, eps_is_complex != 0, eps, k0, mu_r, radius);
   FW_API_END
 }
@@ -229,6 +301,7 @@ int fw_matrix_nnz(fw_handle* hh, int32_t which, int64_t* nnz, int32_t* is_comple
   FW_REQUIRE(hh && nnz, "NULL argument");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   if (which >= FW_MAT_MASS) assemble_aux(h);
   Values& v = pick(h, which);
   FW_REQUIRE(v.valid, "matrix has not been assembled");
@@ -242,6 +315,7 @@ int fw_matrix_export(fw_handle* hh, int32_t which, int32_t* indptr, int32_t* ind
   FW_REQUIRE(hh && indptr && indices && data, "NULL argument");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   if (which >= FW_MAT_MASS) assemble_aux(h);
   Values& v = pick(h, which);
   FW_REQUIRE(v.valid, "matrix has not been assembled");
@@ -257,6 +331,7 @@ int fw_coo_to_csr(fw_handle* hh, int32_t n_rows, int64_t n_entries, const int32_
   FW_REQUIRE(n_entries == 0 || (rows && cols && data), "NULL array");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   for (int64_t i = 0; i < n_entries; ++i)
     FW_REQUIRE(rows[i] >= 0 && rows[i] < n_rows && cols[i] >= 0 && cols[i] < n_rows, "COO index out of range");
   coo_to_csr(h, n_rows, n_entries, rows, cols, data, is_complex != 0);
@@ -269,6 +344,7 @@ int fw_coo_to_csr_export(fw_handle* hh, int32_t* indptr, int32_t* indices, void*
   FW_REQUIRE(hh && indptr && indices && data, "NULL argument");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   FW_REQUIRE(h.coo_val.valid, "fw_coo_to_csr has not been called");
   export_compacted(h, h.coo_pat, h.coo_val, indptr, indices, data);
   FW_API_END
@@ -279,6 +355,7 @@ int fw_matrix_spmv(fw_handle* hh, int32_t which, int32_t x_is_complex, const voi
   FW_REQUIRE(hh && x && y, "NULL argument");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   if (which >= FW_MAT_MASS) assemble_aux(h);
   Values& v = pick(h, which);
   FW_REQUIRE(v.valid, "matrix has not been assembled");
@@ -312,6 +389,7 @@ int fw_eigs(fw_handle* hh, const fw_eigs_params* prm, double* lams, double* X, f
   FW_REQUIRE(hh && prm && lams && X, "NULL argument");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   DevBuf<double> Xd;
   eigs_shift_invert(h, *prm, (std::complex<double>*)lams, Xd, st);
   Xd.download(X, (size_t)prm->k * h.sp.n * 2, h.stream);
@@ -326,6 +404,7 @@ int fw_eigs_csr(fw_handle* hh, int32_t n, const int32_t* K_indptr, const int32_t
   FW_REQUIRE(hh && prm && lams && X, "NULL argument");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   h.tim = fw_timings{};
   {
     Timer t(h.stream);
@@ -345,6 +424,7 @@ int fw_lu_factor_shifted(fw_handle* hh, double sigma_re, double sigma_im, int32_
   FW_REQUIRE(hh, "handle is NULL");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   FW_REQUIRE(h.A.valid && h.B.valid, "assemble A and B first");
   std::vector<uint8_t> active((size_t)h.sp.n, 1);
   for (int i = 0; i < n_dirichlet; ++i) {
@@ -371,6 +451,7 @@ int fw_lu_solve(fw_handle* hh, int32_t rhs_is_complex, const void* b, void* x, i
   FW_REQUIRE(hh && b && x, "NULL argument");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   FW_REQUIRE(h.lu && h.lu->factored, "fw_lu_factor_shifted must be called first");
   (void)refine;
   const int n = h.sp.n;
@@ -425,6 +506,7 @@ int fw_postprocess_modes(fw_handle* hh, int32_t k, const double* lams, const dou
   FW_REQUIRE(hh && lams && X && E && H && powers && k >= 1, "bad argument");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   FW_REQUIRE(h.sp.valid && h.has_symbolic, "space/symbolic missing");
   const size_t cnt = (size_t)k * h.sp.n * 2;
   DevBuf<double> dE, dH;
@@ -445,6 +527,7 @@ int fw_hfield(fw_handle* hh, const double* E, double beta_re, double beta_im, do
   FW_REQUIRE(hh && E && H, "NULL argument");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   FW_REQUIRE(h.sp.valid && h.has_symbolic, "space/symbolic missing");
   const size_t cnt = (size_t)h.sp.n * 2;
   DevBuf<double> dE, dH;
@@ -461,6 +544,7 @@ int fw_intensity(fw_handle* hh, const double* E, const double* H, double* out) {
   FW_REQUIRE(hh && E && H && out, "NULL argument");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   FW_REQUIRE(h.sp.valid, "space missing");
   const size_t cnt = (size_t)h.sp.n * 2;
   DevBuf<double> dE, dH, dout;
@@ -481,6 +565,7 @@ int fw_overlap_cross(fw_handle* hh, const fw_space* space_j, const double* E_i, 
   FW_REQUIRE(mode == 1 || (H_i && E_j), "the overlap needs all four fields");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   const Space& sp = h.sp;
   FW_REQUIRE(sp.valid, "fw_set_space must be called first");
   cudaStream_t s = h.stream;
@@ -503,6 +588,7 @@ int fw_poynting(fw_handle* hh, const double* E, const double* H, double* out) {
   FW_REQUIRE(hh && E && H && out, "NULL argument");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   FW_REQUIRE(h.sp.valid, "space missing");
   const size_t cnt = (size_t)h.sp.n * 2;
   const size_t nout = (size_t)h.sp.ne * 3 * (h.sp.nb == 6 ? 3 : 6) * 2;
@@ -521,6 +607,7 @@ int fw_energy_current_density(fw_handle* hh, const double* xs, double* out) {
   FW_REQUIRE(hh && xs && out, "NULL argument");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   FW_REQUIRE(h.sp.valid, "space missing");
   DevBuf<double> dE, dout;
   dE.upload(xs, (size_t)h.sp.n * 2, h.stream);
@@ -538,6 +625,7 @@ int fw_functional(fw_handle* hh, int32_t kind, const double* f0, const double* f
   FW_REQUIRE(hh && f0 && out, "NULL argument");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   FW_REQUIRE(h.sp.valid, "space missing");
   const Space& sp = h.sp;
   cudaStream_t s = h.stream;
@@ -581,6 +669,7 @@ int fw_compute_modes(fw_handle* hh, const fw_modes_params* prm, double* lams, do
   FW_REQUIRE(hh && prm && lams && E && H && powers, "NULL argument");
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
   FW_REQUIRE(h.sp.valid, "fw_set_space must be called first");
   cudaStream_t s = h.stream;
   const double keep_upload = h.tim.upload_ms;
@@ -589,6 +678,17 @@ int fw_compute_modes(fw_handle* hh, const fw_modes_params* prm, double* lams, do
   h.tim.upload_ms = keep_upload;
   h.tim.symbolic_ms = keep_symbolic;
   Timer total(s);
+  {
+    // the host analysis of the sparse LU only needs the mesh and the Dirichlet set: start it now, it runs on worker
+    // threads while the GPU sorts the COO keys and assembles
+    std::vector<uint8_t> active((size_t)h.sp.n, 1);
+    for (int i = 0; i < prm->eigs.n_dirichlet; ++i) {
+      const int d = prm->eigs.dirichlet[i];
+      FW_REQUIRE(d >= 0 && d < h.sp.n, "dirichlet dof out of range");
+      active[d] = 0;
+    }
+    lu_analyse_prefetch(h, active, prm->eigs.leaf_elements);
+  }
   if (!(prm->reuse_symbolic && h.has_symbolic)) {
     Timer t(s);
     symbolic_space(h);
@@ -675,6 +775,7 @@ int fw_debug_lu_get(fw_handle* hh, int32_t which, void* out) {
   FW_API_BEGIN
   FW_REQUIRE(hh && out, "NULL argument");
   FW_CHECK_CUDA(cudaSetDevice(hh->h.device));
+  current_pool() = &hh->h.pool;
   lu_debug_download(hh->h, which, out);
   FW_API_END
 }

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <ctime>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -127,34 +128,91 @@ struct scalar_traits<cplx> {
 };
 
 // ------------------------------------------------------------------------------ device memory
+// Device buffers are recycled through an exact-size free list owned by the handle the calling thread works for.
+// A solve allocates and frees ~40 work buffers (sort keys 2.4 GB, Krylov basis 0.6 GB, PCG vectors 1.1 GB, ...);
+// cudaMalloc / cudaFree of such blocks cost a device synchronisation plus physical (un)mapping -- measured as
+// sporadic 100-800 ms stalls of exactly the stages that allocate (the factorisation, whose arena is persistent, never
+// stalled).  In steady state every request finds the block of the previous solve: no driver call at all.
+// One handle <-> one stream, so reuse is ordered by the stream.
+struct DevPool {
+  std::multimap<size_t, void*> free_;
+  size_t cached = 0;
+  static constexpr size_t LIMIT = (size_t)24 << 30;  // cached bytes above which everything is handed back
+  void* get(size_t bytes) {
+    auto it = free_.find(bytes);
+    if (it != free_.end()) {
+      void* p = it->second;
+      free_.erase(it);
+      cached -= bytes;
+      return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      trim();
+      e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess)
+      throw Error(FW_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(bytes) + ") -> " + cudaGetErrorString(e));
+    return p;
+  }
+  void put(void* p, size_t bytes) {
+    free_.emplace(bytes, p);
+    cached += bytes;
+    if (cached > LIMIT) trim();
+  }
+  void trim() {
+    for (auto& kv : free_) cudaFree(kv.second);
+    free_.clear();
+    cached = 0;
+  }
+  ~DevPool() { trim(); }
+};
+inline DevPool*& current_pool() {
+  static thread_local DevPool* p = nullptr;
+  return p;
+}
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  DevPool* pool = nullptr;  // where the block goes back to
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr, o.n = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), pool(o.pool) { o.p = nullptr, o.n = 0, o.pool = nullptr; }
   DevBuf& operator=(DevBuf&& o) noexcept {
     if (this != &o) {
       release();
-      p = o.p, n = o.n;
-      o.p = nullptr, o.n = 0;
+      p = o.p, n = o.n, pool = o.pool;
+      o.p = nullptr, o.n = 0, o.pool = nullptr;
     }
     return *this;
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (pool)
+        pool->put(p, n * sizeof(T));
+      else
+        cudaFree(p);
+    }
     p = nullptr;
     n = 0;
+    pool = nullptr;
   }
   // (re)allocate when the capacity is insufficient; contents are NOT preserved
   void alloc(size_t count) {
     if (count <= n && p) return;
     release();
     if (count == 0) return;
-    FW_CHECK_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    pool = current_pool();
+    if (pool)
+      p = (T*)pool->get(count * sizeof(T));
+    else
+      FW_CHECK_CUDA(cudaMalloc(&p, count * sizeof(T)));
     n = count;
   }
   void upload(const T* host, size_t count, cudaStream_t s) {

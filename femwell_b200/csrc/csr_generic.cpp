@@ -44,6 +44,7 @@ void bfs(int n, const std::vector<int>& ap, const std::vector<int>& ai, int src,
 void setup_generic_csr(Handle& h, int n, const int* Kp, const int* Ki, const void* Kx, const int* Mp, const int* Mi,
                        const void* Mx, bool is_complex, const double* coords) {
   FW_REQUIRE(n > 0 && Kp && Ki && Kx && Mp && Mi && Mx, "bad CSR arguments");
+  h.lu_prefetch.reset();  // joins a pending analysis of the previous space
   const int w = is_complex ? 2 : 1;
   cudaStream_t s = h.stream;
   // ---- union pattern, A = -K, B = -M on it

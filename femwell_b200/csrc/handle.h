@@ -4,7 +4,8 @@
 
 namespace fw {
 
-struct LU;  // sparse multifrontal factorisation (lu.h)
+struct LU;          // sparse multifrontal factorisation (lu.h)
+struct LUPrefetch;  // host analysis running on a worker thread (lu.h)
 
 // structural CSR pattern + the sorted-COO bookkeeping that produced it
 struct Pattern {
@@ -50,6 +51,7 @@ struct Connectivity {
 };
 
 struct Handle {
+  DevPool pool;  // first member: destroyed last, after every buffer has gone back to it
   int device = 0;
   cudaStream_t stream = nullptr;
   Space sp;
@@ -72,6 +74,7 @@ struct Handle {
   // compacted export scratch
   DevBuf<uint32_t> scan_tmp, scan_tmp2;
   std::unique_ptr<LU> lu;
+  std::unique_ptr<LUPrefetch> lu_prefetch;
   // big LU buffers live here so that they survive a new space / analysis (no 25 GB cudaFree + cudaMalloc per solve)
   struct LUArena {
     DevBuf<double> factors, work, xperm, scratch, dinv;
@@ -87,6 +90,7 @@ struct Handle {
 
 // device -> pageable host through the pinned ring, chunk copies overlapped with a threaded host memcpy (api.cu)
 void download_staged(Handle& h, void* host_dst, const void* dev_src, size_t bytes);
+void upload_staged(Handle& h, void* dev_dst, const void* host_src, size_t bytes);
 
 // ---- scan / sort / COO->CSR (sort.cu)
 void exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, DevBuf<uint32_t>& tmp, cudaStream_t s);

@@ -9,6 +9,8 @@
 // windowed partial pivoting, hand-written FP64/C128 TRSM + GEMM kernels, and level-batched
 // forward/backward substitution.
 #pragma once
+#include <thread>
+
 #include "handle.h"
 
 namespace fw {
@@ -53,6 +55,18 @@ struct LU {
   LU();
   ~LU();
 };
+
+// host analysis started ahead of time on a worker thread (fw_compute_modes: it overlaps the COO sort, the
+// element kernels and the reduce on the GPU); lu_analyse joins it
+struct LUPrefetch {
+  std::unique_ptr<LU> lu;
+  std::thread th;
+  std::string err;
+  ~LUPrefetch() {
+    if (th.joinable()) th.join();
+  }
+};
+void lu_analyse_prefetch(Handle& h, const std::vector<uint8_t>& active, int leaf_elements);
 
 // factor OP = alphaA * A + alphaB * B (values on the structural pattern h.pat)
 void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements);

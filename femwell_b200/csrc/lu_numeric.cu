@@ -29,32 +29,35 @@ template <>
 __device__ inline cplx to_<cplx, cplx>(cplx v) { return v; }
 
 // ------------------------------------------------------------------------------ analysis upload
+// large tables go through the pinned staging ring (pageable cudaMemcpy runs at a few GB/s)
+static thread_local Handle* g_up_handle = nullptr;
+struct UpGuard {
+  explicit UpGuard(Handle* h) { g_up_handle = h; }
+  ~UpGuard() { g_up_handle = nullptr; }
+};
 template <class T>
 static void up(DevBuf<T>& d, const std::vector<T>& v, cudaStream_t s) {
-  d.upload(v.data(), v.size(), s);
+  d.alloc(v.size());
+  if (g_up_handle)
+    upload_staged(*g_up_handle, d.p, v.data(), v.size() * sizeof(T));
+  else
+    d.upload(v.data(), v.size(), s);
 }
 static void up64(DevBuf<long long>& d, const std::vector<int64_t>& v, cudaStream_t s) {
   static_assert(sizeof(long long) == sizeof(int64_t), "");
-  d.upload((const long long*)v.data(), v.size(), s);
+  d.alloc(v.size());
+  if (g_up_handle)
+    upload_staged(*g_up_handle, d.p, v.data(), v.size() * sizeof(int64_t));
+  else
+    d.upload((const long long*)v.data(), v.size(), s);
 }
 
-void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements) {
+static void lu_host_analysis(const Handle& h, LU& lu) {
   const Space& sp = h.sp;
-  FW_REQUIRE(sp.valid || h.generic.valid, "space missing");
-  if (h.lu && h.lu->dev && h.lu->leaf_key == leaf_elements && h.lu->active_key == active) {
-    // same mesh (fw_set_space / fw_eigs_csr reset h.lu), same Dirichlet set: wavelength / epsilon sweeps
-    h.lu->factored = false;
-    return;
-  }
-  h.lu.reset(new LU());
-  LU& lu = *h.lu;
-  lu.active_key = active;
-  lu.leaf_key = leaf_elements;
-  Trace tr(h.stream);
   if (h.generic.valid) {
     const Connectivity& c = h.generic;
-    lu_symbolic_build(lu.sym, c.n, c.nb, c.ne, c.edofs.data(), c.cx.data(), c.cy.data(), active.data(),
-                      leaf_elements);
+    lu_symbolic_build(lu.sym, c.n, c.nb, c.ne, c.edofs.data(), c.cx.data(), c.cy.data(), lu.active_key.data(),
+                      lu.leaf_key);
   } else {
     std::vector<double> cx(sp.ne), cy(sp.ne);
     for (int e = 0; e < sp.ne; ++e) {
@@ -62,14 +65,63 @@ void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements
       cx[e] = (sp.h_p[a] + sp.h_p[b] + sp.h_p[c]) / 3.0;
       cy[e] = (sp.h_p[sp.nv + a] + sp.h_p[sp.nv + b] + sp.h_p[sp.nv + c]) / 3.0;
     }
-    lu_symbolic_build(lu.sym, sp.n, sp.nb, sp.ne, sp.h_edofs.data(), cx.data(), cy.data(), active.data(),
-                      leaf_elements);
+    lu_symbolic_build(lu.sym, sp.n, sp.nb, sp.ne, sp.h_edofs.data(), cx.data(), cy.data(), lu.active_key.data(),
+                      lu.leaf_key);
   }
+}
+
+static bool lu_reusable(const Handle& h, const std::vector<uint8_t>& active, int leaf_elements) {
+  return h.lu && h.lu->dev && h.lu->leaf_key == leaf_elements && h.lu->active_key == active;
+}
+
+void lu_analyse_prefetch(Handle& h, const std::vector<uint8_t>& active, int leaf_elements) {
+  h.lu_prefetch.reset();
+  if (lu_reusable(h, active, leaf_elements)) return;
+  if (getenv("FW_NO_PREFETCH")) return;
+  FW_REQUIRE(h.sp.valid || h.generic.valid, "space missing");
+  h.lu_prefetch.reset(new LUPrefetch());
+  LUPrefetch* pf = h.lu_prefetch.get();
+  pf->lu.reset(new LU());
+  pf->lu->active_key = active;
+  pf->lu->leaf_key = leaf_elements;
+  const Handle* hp = &h;
+  pf->th = std::thread([pf, hp] {
+    try {
+      lu_host_analysis(*hp, *pf->lu);
+    } catch (const std::exception& e) {
+      pf->err = e.what();
+      if (pf->err.empty()) pf->err = "analysis failed";
+    }
+  });
+}
+
+void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements) {
+  const Space& sp = h.sp;
+  FW_REQUIRE(sp.valid || h.generic.valid, "space missing");
+  std::unique_ptr<LUPrefetch> pf = std::move(h.lu_prefetch);
+  if (pf && pf->th.joinable()) pf->th.join();
+  if (lu_reusable(h, active, leaf_elements)) {
+    // same mesh (fw_set_space / fw_eigs_csr reset h.lu), same Dirichlet set: wavelength / epsilon sweeps
+    h.lu->factored = false;
+    return;
+  }
+  Trace tr(h.stream);
+  if (pf && pf->lu && pf->lu->leaf_key == leaf_elements && pf->lu->active_key == active) {
+    if (!pf->err.empty()) throw Error(FW_ERR_INTERNAL, pf->err);
+    h.lu = std::move(pf->lu);
+  } else {
+    h.lu.reset(new LU());
+    h.lu->active_key = active;
+    h.lu->leaf_key = leaf_elements;
+    lu_host_analysis(h, *h.lu);
+  }
+  LU& lu = *h.lu;
   tr.mark("lu analyse: host symbolic");
   lu.dev.reset(new LUDevice(h.lu_arena));
   LUDevice& d = *lu.dev;
   const LUSymbolic& S = lu.sym;
   cudaStream_t s = h.stream;
+  UpGuard up_guard(&h);
   up(d.iperm, S.iperm, s);
   up(d.perm, S.perm, s);
   up(d.node_of, S.node_of, s);
