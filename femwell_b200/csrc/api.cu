@@ -59,7 +59,7 @@ void download_staged(Handle& h, void* host_dst, const void* dev_src, size_t byte
     FW_CHECK_CUDA(cudaMemcpyAsync(h.pinned[c & 1], (const char*)dev_src + off, len, cudaMemcpyDeviceToHost, h.stream));
     FW_CHECK_CUDA(cudaEventRecord(h.pinned_ev[c & 1], h.stream));
   };
-  const int nthreads = 4;
+  const int nthreads = 8;
   issue(0);
   for (size_t c = 0; c < nchunk; ++c) {
     FW_CHECK_CUDA(cudaEventSynchronize(h.pinned_ev[c & 1]));

@@ -249,6 +249,24 @@ __global__ void k_mask_real_to(const double* __restrict__ src, const uint8_t* __
   if (i < n) dst[i] = cplx{active[i] ? src[i] : 0.0, 0.0};
 }
 
+// default start vector: uniform(-1, 1) from a splitmix64 stream indexed by the dof (the same numbers on every run
+// and every device; ARPACK's default is a uniform(-1, 1) vector as well, scipy arpack.py:361-364)
+__device__ __host__ inline double start_value(int i) {
+  uint64_t x = 0x9E3779B97F4A7C15ull * (uint64_t)(i + 2);
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (double)(x >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+__global__ void k_start_vector(const uint8_t* __restrict__ active, int n, double* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = active[i] ? start_value(i) : 0.0;
+}
+__global__ void k_start_vector(const uint8_t* __restrict__ active, int n, cplx* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = cplx{active[i] ? start_value(i) : 0.0, 0.0};
+}
+
 // ------------------------------------------------------------------------------ host helpers
 namespace {
 
@@ -345,23 +363,13 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
 
   // ---- start vector (ARPACK forces it into range(OP) with one application)
   {
-    std::vector<double> v0((size_t)n);
-    if (prm.v0) {
-      std::copy(prm.v0, prm.v0 + n, v0.begin());
-    } else {
-      uint64_t z = 0x9E3779B97F4A7C15ull;
-      for (int i = 0; i < n; ++i) {
-        z += 0x9E3779B97F4A7C15ull;
-        uint64_t x = z;
-        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-        x ^= x >> 31;
-        v0[i] = (double)(x >> 11) * (2.0 / 9007199254740992.0) - 1.0;
-      }
-    }
     DevBuf<double> v0d;
-    v0d.upload(v0.data(), v0.size(), s);
-    k_mask_real_to<<<cdiv(n, 256), 256, 0, s>>>(v0d.p, act.p, n, w);
+    if (prm.v0) {
+      v0d.upload(prm.v0, (size_t)n, s);
+      k_mask_real_to<<<cdiv(n, 256), 256, 0, s>>>(v0d.p, act.p, n, w);
+    } else {
+      k_start_vector<<<cdiv(n, 256), 256, 0, s>>>(act.p, n, w);
+    }
     FW_CHECK_CUDA(cudaStreamSynchronize(s));
     apply_op(w, Vb);
     double nv = dev_norm<T>(h, Vb, n, W);
