@@ -8,6 +8,8 @@
 //                   and U_kk^-1 TRSM for the rows below the window
 //   k_lu_gemm       rank-32 trailing update, 64x64 tiles, 4x4 register micro-tiles
 // followed by the extend-add of the Schur complements into the parents.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 #include "lu.h"
@@ -385,6 +387,134 @@ __global__ void __launch_bounds__(TALL_THREADS) k_lu_panel_tall(FrontTab T, cons
   }
 }
 
+// ------------------------------------------------------------------------------ tall panel on a thread-block cluster
+// f64 panels of 256 < h <= 4096 rows: 8 CTAs x 512 threads, every thread owns ONE row of the panel and keeps its
+// 32 entries in registers for the whole panel (the global-memory kernel above re-reads and re-writes the trailing
+// columns for every pivot: ~200 us per panel at h = 2000 on one SM).  Per pivot column: block arg-max, candidates
+// exchanged through distributed shared memory, cluster barrier, the pivot row (and the row it swaps with) broadcast
+// to all CTAs, cluster barrier, rank-1 update in registers.  Same pivot choice as k_lu_panel_tall (largest |.|, lowest
+// row on ties), same arithmetic per entry => identical factors.
+namespace cgp = cooperative_groups;
+constexpr int PCL = 8, PCL_THREADS = 512;
+
+__global__ void __cluster_dims__(PCL, 1, 1) __launch_bounds__(PCL_THREADS)
+    k_lu_panel_cluster(FrontTab T, const int* __restrict__ nodes, int kstep, double* __restrict__ F,
+                       int* __restrict__ piv, double thr, int* __restrict__ counters) {
+  __shared__ double prow[PW], jrow[PW], stage[2][PW];
+  __shared__ double cand_v[PCL];
+  __shared__ int cand_i[PCL];
+  __shared__ double red_v[PCL_THREADS / 32];
+  __shared__ int red_i[PCL_THREADS / 32];
+  cgp::cluster_group cl = cgp::this_cluster();
+  const int rank = (int)cl.block_rank();
+  const int node = nodes[blockIdx.x / PCL];
+  const int m = T.m[node], ns = T.ns[node];
+  const int k0 = kstep * PW;
+  const int h = ns - k0;
+  if (k0 >= ns || h <= HWIN || h > PCL * PCL_THREADS) return;  // uniform over the cluster
+  const int w = min(PW, h);
+  double* P = F + T.front_off[node] + k0 + (long long)k0 * m;  // P[r + c*m]
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int r = rank * PCL_THREADS + t;  // the row of the panel owned by this thread
+  const bool live = r < h;
+  double a[PW];
+#pragma unroll
+  for (int c = 0; c < PW; ++c) a[c] = (live && c < w) ? P[r + (long long)c * m] : 0.0;
+  for (int j = 0; j < w; ++j) {
+    // ---- arg-max of |a[j]| over the rows j..h-1
+    double aj = 0.0;
+#pragma unroll
+    for (int c = 0; c < PW; ++c)
+      if (c == j) aj = a[c];
+    double v = (live && r >= j) ? fabs(aj) : -1.0;
+    int idx = r;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, v, o);
+      const int oi = __shfl_down_sync(0xffffffffu, idx, o);
+      if (ov > v || (ov == v && oi < idx)) v = ov, idx = oi;
+    }
+    if (lane == 0) red_v[wid] = v, red_i[wid] = idx;
+    __syncthreads();
+    if (t == 0) {
+      double bv = red_v[0];
+      int bi = red_i[0];
+      for (int q = 1; q < PCL_THREADS / 32; ++q)
+        if (red_v[q] > bv || (red_v[q] == bv && red_i[q] < bi)) bv = red_v[q], bi = red_i[q];
+      for (int c = 0; c < PCL; ++c) {
+        cl.map_shared_rank(cand_v, c)[rank] = bv;
+        cl.map_shared_rank(cand_i, c)[rank] = bi;
+      }
+    }
+    cl.sync();
+    double bv = cand_v[0];
+    int pr = cand_i[0];
+#pragma unroll
+    for (int q = 1; q < PCL; ++q)
+      if (cand_v[q] > bv || (cand_v[q] == bv && cand_i[q] < pr)) bv = cand_v[q], pr = cand_i[q];
+    const bool tiny = !(bv >= thr);
+    if (rank == 0 && t == 0) {
+      piv[T.own_start[node] + k0 + j] = k0 + pr;
+      if (tiny) atomicAdd(&counters[0], 1);
+    }
+    // ---- broadcast the pivot row and row j (their owners stage the registers in shared memory, the owner's
+    //      warp copies the 32 values into every CTA)
+    const int own_pr_warp = (pr % PCL_THREADS) >> 5, own_pr_rank = pr / PCL_THREADS;
+    const int own_j_warp = (j % PCL_THREADS) >> 5, own_j_rank = j / PCL_THREADS;
+    if (r == pr) {
+      // static pivot perturbation (tiny / exactly singular pivot); corrected by iterative refinement
+#pragma unroll
+      for (int c = 0; c < PW; ++c) stage[0][c] = (tiny && c == j) ? thr : a[c];
+    }
+    if (r == j) {
+#pragma unroll
+      for (int c = 0; c < PW; ++c) stage[1][c] = a[c];
+    }
+    __syncwarp();
+    if (rank == own_pr_rank && wid == own_pr_warp) {
+      const double x = stage[0][lane];
+#pragma unroll
+      for (int c = 0; c < PCL; ++c) cl.map_shared_rank(prow, c)[lane] = x;
+    }
+    if (rank == own_j_rank && wid == own_j_warp) {
+      const double x = stage[1][lane];
+#pragma unroll
+      for (int c = 0; c < PCL; ++c) cl.map_shared_rank(jrow, c)[lane] = x;
+    }
+    cl.sync();
+    // ---- interchange + rank-1 update in registers
+    if (pr != j) {
+      if (r == pr) {
+#pragma unroll
+        for (int c = 0; c < PW; ++c) a[c] = jrow[c];
+      } else if (r == j) {
+#pragma unroll
+        for (int c = 0; c < PW; ++c) a[c] = prow[c];
+      }
+    } else if (r == j && tiny) {
+#pragma unroll
+      for (int c = 0; c < PW; ++c) a[c] = prow[c];
+    }
+    if (live && r > j) {
+      double l = 0.0;
+#pragma unroll
+      for (int c = 0; c < PW; ++c) {
+        if (c == j) {
+          l = a[c] / prow[c];
+          a[c] = l;
+        } else if (c > j) {
+          a[c] = fma(-l, prow[c], a[c]);
+        }
+      }
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < PW; ++c)
+      if (c < w) P[r + (long long)c * m] = a[c];
+  }
+}
+
 // ------------------------------------------------------------------------------ swaps + TRSMs
 // blockIdx.x < ctiles : thread per column c outside the panel: row interchanges, and for c right of the
 //                       panel the unit-lower solve of the U row block.
@@ -661,6 +791,7 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
   const char* tenv = getenv("FW_TRACE");
   const bool trace2 = tenv && atoi(tenv) >= 2;
   static const int big_gemm_min = getenv("FW_BIG_GEMM_MIN") ? atoi(getenv("FW_BIG_GEMM_MIN")) : 384;
+  static const bool no_cluster_panel = getenv("FW_NO_CLUSTER_PANEL") != nullptr;
   for (int lev = Sy.n_levels - 1; lev >= 0; --lev) {
     const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
     const int* nodes = d.level_nodes.p + Sy.level_start[lev];
@@ -677,8 +808,17 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
     const int max_ns = Sy.level_max_ns[lev], max_m = Sy.level_max_m[lev];
     const int npan = (max_ns + PW - 1) / PW;
     for (int k = 0; k < npan; ++k) {
-      if (max_ns - k * PW > HWIN)
-        k_lu_panel_tall<S><<<nfront, TALL_THREADS, 0, s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
+      if (max_ns - k * PW > HWIN) {
+        bool done = false;
+        if constexpr (!scalar_traits<S>::is_complex) {
+          // few, tall f64 fronts (top of the tree): one 8-CTA cluster per front, the panel lives in registers
+          if (nfront <= 8 && max_ns - k * PW <= PCL * PCL_THREADS && !no_cluster_panel) {
+            k_lu_panel_cluster<<<nfront * PCL, PCL_THREADS, 0, s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
+            done = true;
+          }
+        }
+        if (!done) k_lu_panel_tall<S><<<nfront, TALL_THREADS, 0, s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
+      }
       k_lu_panel<S><<<nfront, HWIN, panel_smem, s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
       const int ctiles = (max_m + 127) / 128;
       const int rtiles = (max_m + 127) / 128;
