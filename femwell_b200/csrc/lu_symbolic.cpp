@@ -252,6 +252,7 @@ void lu_symbolic_build(LUSymbolic& S, int n, int nb, int ne, const int* edofs, c
   std::vector<std::vector<int>> bl(nn);
   for (int lev = S.n_levels - 1; lev >= 0; --lev) {
     const int l0 = S.level_start[lev], cnt = S.level_start[lev + 1] - l0;
+    double tl0 = Trace::now();
     parallel_chunks(cnt, 8, [&](int qa, int qb, int) {
       std::vector<int> tmp;
       for (int q = qa; q < qb; ++q) {
@@ -290,6 +291,7 @@ void lu_symbolic_build(LUSymbolic& S, int n, int nb, int ne, const int* edofs, c
         S.m[v] = nsv + (int)out.size();
       }
     });
+    if (trace && getenv("FW_TRACE_LEVELS")) fprintf(stderr, "[fw-trace]     blist level %d (%d nodes) %.3f ms\n", lev, cnt, Trace::now() - tl0);
   }
   mark("boundary lists");
   {

@@ -278,3 +278,31 @@ def test_oracle_cross_mesh_overlap_and_poynting_of_constant_fields():
     # energy density |ex|^2 + |ey|^2 (+ |ez| = 0)
     ed = fo.energy_current_density(mi.p, ti, di, 1, bi.X, bi.W, E_i)
     assert np.abs(ed - (abs(cEi[0]) ** 2 + abs(cEi[1]) ** 2)).max() < 1e-12
+
+
+# ----------------------------------------------------------------------------- .msh ingest
+@pytest.mark.parametrize("name", ["square_v41.msh", "square_v22.msh"])
+def test_read_msh_fixture(name):
+    from femwell_b200.msh import read_msh
+
+    m = read_msh(os.path.join(ROOT, "tests", "golden", name))
+    assert m.nvertices == 4 and m.nelements == 2  # the unused fifth node is pruned
+    assert np.array_equal(m.p, np.array([[0.0, 1.0, 1.0, 0.0], [0.0, 0.0, 1.0, 1.0]]))
+    assert np.array_equal(m.t, np.array([[0, 0], [1, 2], [2, 3]]))
+    assert {k: v.tolist() for k, v in m.subdomains.items()} == {"core": [0], "clad": [1]}
+    fac = {k: [tuple(m.facets[:, f]) for f in v] for k, v in m.boundaries.items()}
+    assert fac == {"bottom": [(0, 1)], "left": [(0, 3)]}
+
+
+def test_msh_round_trip_keeps_mesh_and_groups(tmp_path):
+    from femwell_b200.msh import read_msh, write_msh
+
+    m, _ = strip_problem(6, jitter=0.1)
+    m = m.with_boundaries({"left": lambda x: x[0] < x[0].min() + 1e-9, "top": lambda x: x[1] > x[1].max() - 1e-9})
+    path = str(tmp_path / "strip.msh")
+    write_msh(m, path)
+    r = read_msh(path)
+    assert np.array_equal(r.p, m.p) and np.array_equal(r.t, m.t)
+    assert np.array_equal(r.subdomains["core"], m.subdomains["core"])
+    for k in ("left", "top"):
+        assert np.array_equal(np.sort(r.boundaries[k]), np.sort(m.boundaries[k]))
