@@ -696,6 +696,8 @@ int fw_compute_modes(fw_handle* hh, const fw_modes_params* prm, double* lams, do
   }
   const double k0 = 2.0 * M_PI / prm->wavelength;
   assemble_waveguide(h, prm->eps_kind, prm->eps_is_complex != 0, prm->eps, k0, prm->mu_r, prm->radius);
+  // geometry-only operators of the H-field recovery: assembled now, while the host analysis of the LU is still running
+  assemble_aux(h);
   DevBuf<double> Xd, Hd;
   eigs_shift_invert(h, prm->eigs, (std::complex<double>*)lams, Xd, st);
   const int k = prm->eigs.k;

@@ -276,6 +276,17 @@ struct Trace {
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// function attributes (dynamic shared memory opt-in) are per device: true the first time a call site runs on the
+// current device
+inline bool first_use_on_device(bool (&done)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 constexpr int MAXNB = 14;  // local basis functions (N2 x P2)
 constexpr int MAXQ = 12;   // quadrature points
 

@@ -134,11 +134,10 @@ void lu_gemm_big_launch(FrontTab T, const int* nodes, int nfront, int kstep, S* 
   constexpr size_t smem = sizeof(S) * 2 * G2_KC * (TM + TM + 2);
   const int nt = (max_rem + TM - 1) / TM;
   if (nt <= 0) return;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  if (first_use_on_device(configured)) {
     FW_CHECK_CUDA(cudaFuncSetAttribute(k_lu_gemm_big<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FW_CHECK_CUDA(cudaFuncSetAttribute(k_lu_gemm_big<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   if (schur)
     k_lu_gemm_big<S, true><<<dim3(nfront, nt, nt), 256, smem, s>>>(T, nodes, kstep, F);

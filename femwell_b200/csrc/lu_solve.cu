@@ -818,11 +818,10 @@ struct InvChain<double, NRHS> {
   static void launch(bool fwd, int nfront, FrontTab T, const int* nodes, const double* F, LUDevice& d, double* work,
                      int64_t work_stride, double* xp, int na, cudaStream_t s) {
     constexpr int smem = INV_SMEM_BYTES + 2 * NRHS * PW * 8;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured)) {
       FW_CHECK_CUDA(cudaFuncSetAttribute(k_fwd_chain_inv<NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       FW_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_chain_inv<NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      configured = true;
     }
     if (fwd)
       k_fwd_chain_inv<NRHS><<<nfront * CL, CL_THREADS, smem, s>>>(T, nodes, F, d.dinv.p, d.rowperm.p, work, work_stride,
