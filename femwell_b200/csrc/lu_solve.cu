@@ -857,6 +857,9 @@ static void solve_typed(Handle& h, const S* b, S* x) {
   const bool no_inv = getenv("FW_NO_DINV") != nullptr;
   // levels of many small fronts: chain and off-diagonal update in one kernel (FW_FUSE_MAX_M=0 disables)
   static const int fuse_max_m = getenv("FW_FUSE_MAX_M") ? atoi(getenv("FW_FUSE_MAX_M")) : 512;
+  // forward fused kernel: two rows per thread (blockDim = m / 2) doubles the fronts in flight per SM -- the kernel is
+  // bound by the latency of its dependent steps, not by issue slots: leaf level 0.98 -> 0.70 ms (FW_FUSE_TDIV)
+  static const int fuse_tdiv = getenv("FW_FUSE_TDIV") ? std::max(1, atoi(getenv("FW_FUSE_TDIV"))) : 2;
   auto use_inv = [&](int max_ns) {
     return !scalar_traits<S>::is_complex && d.dinv_valid && !no_cluster && !no_inv && max_ns > CL_MIN_NS &&
            max_ns <= CL * CL_THREADS;
@@ -870,7 +873,7 @@ static void solve_typed(Handle& h, const S* b, S* x) {
     // measured (500k triangles): forward fusion pays only when the pivot block spans several panels
     const bool fuse = Sy.level_max_m[lev] <= fuse_max_m && nfront >= 296 && max_ns >= 64;
     if (fuse)
-      k_fwd_chain_fused<S, NRHS><<<nfront, chain_threads(Sy.level_max_m[lev]), 0, s>>>(T, nodes, F, d.rowperm.p, work,
+      k_fwd_chain_fused<S, NRHS><<<nfront, chain_threads(Sy.level_max_m[lev] / fuse_tdiv), 0, s>>>(T, nodes, F, d.rowperm.p, work,
                                                                                     Sy.work_entries, xp, na);
     else if (use_inv(max_ns))
       launch_inv_chain<S, NRHS>(true, nfront, T, nodes, F, d, work, Sy.work_entries, xp, na, s);
