@@ -13,6 +13,9 @@
 #include <thread>
 
 #include <climits>
+#include <mutex>
+#include <functional>
+#include <condition_variable>
 
 #include "lu.h"
 
@@ -28,6 +31,84 @@ int worker_count() {
   return n;
 }
 
+// Persistent workers: one analysis issues ~40 parallel loops (one per tree level and phase); creating and joining
+// 16 threads for each of them costs more than many of the loops themselves.
+class WorkerPool {
+ public:
+  static WorkerPool& instance() {
+    static WorkerPool p(worker_count() - 1);
+    return p;
+  }
+  // f(i) for i in [0, n); the caller takes part.  Returns false when the pool is busy (another analysis).
+  bool run(int n, const std::function<void(int)>& f) {
+    std::unique_lock<std::mutex> busy(busy_, std::try_to_lock);
+    if (!busy.owns_lock()) return false;
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = &f;
+      n_ = n;
+      next_ = 0;
+      pending_ = n;
+      ++generation_;
+    }
+    cv_start_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(m_);
+    cv_done_.wait(lk, [&] { return pending_ == 0; });
+    job_ = nullptr;
+    return true;
+  }
+  ~WorkerPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_start_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+
+ private:
+  explicit WorkerPool(int nthreads) {
+    for (int i = 0; i < nthreads; ++i) th_.emplace_back([this] { loop(); });
+  }
+  void work() {
+    for (;;) {
+      int i;
+      const std::function<void(int)>* f;
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (job_ == nullptr || next_ >= n_) return;
+        i = next_++;
+        f = job_;
+      }
+      (*f)(i);
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (--pending_ == 0) cv_done_.notify_all();
+      }
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_start_.wait(lk, [&] { return stop_ || generation_ != seen; });
+        if (stop_) return;
+        seen = generation_;
+      }
+      work();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_, busy_;
+  std::condition_variable cv_start_, cv_done_;
+  const std::function<void(int)>* job_ = nullptr;
+  int n_ = 0, next_ = 0, pending_ = 0;
+  uint64_t generation_ = 0;
+  bool stop_ = false;
+};
+
 // f(begin, end, thread_id) over [0, n) in contiguous chunks
 template <class F>
 void parallel_chunks(int n, int min_per_thread, F&& f) {
@@ -36,20 +117,24 @@ void parallel_chunks(int n, int min_per_thread, F&& f) {
     f(0, n, 0);
     return;
   }
-  std::vector<std::thread> th;
   std::atomic<bool> failed{false};
   std::string msg;
-  for (int t = 0; t < nt; ++t) {
-    int a = (int)((int64_t)n * t / nt), b = (int)((int64_t)n * (t + 1) / nt);
-    th.emplace_back([&, a, b, t] {
-      try {
-        f(a, b, t);
-      } catch (const std::exception& e) {
-        if (!failed.exchange(true)) msg = e.what();
-      }
-    });
+  std::mutex msg_m;
+  auto body = [&](int t) {
+    const int a = (int)((int64_t)n * t / nt), b = (int)((int64_t)n * (t + 1) / nt);
+    try {
+      f(a, b, t);
+    } catch (const std::exception& e) {
+      std::lock_guard<std::mutex> lk(msg_m);
+      if (!failed.exchange(true)) msg = e.what();
+    }
+  };
+  const std::function<void(int)> job = body;
+  if (!WorkerPool::instance().run(nt, job)) {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back([&, t] { body(t); });
+    for (auto& x : th) x.join();
   }
-  for (auto& x : th) x.join();
   if (failed) throw Error(FW_ERR_INTERNAL, msg);
 }
 }  // namespace
