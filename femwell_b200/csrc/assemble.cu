@@ -542,6 +542,19 @@ void assemble_waveguide(Handle& h, int eps_kind, bool eps_complex, const void* e
     assemble_ab_typed<double>(h, eps_kind, eps_host, k0, mu_r, radius);
 }
 
+// order 2 local layout P P P (N N P)x3 N N: the Nedelec pairs are the locals (3,4) (6,7) (9,10) (12,13)
+__global__ void k_mass_pairs(int ne, const int* __restrict__ edofs, int* __restrict__ pair) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int la[4] = {3, 6, 9, 12};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int a = edofs[(size_t)la[q] * ne + e], b = edofs[(size_t)(la[q] + 1) * ne + e];
+    pair[a] = b;  // every element sharing the edge writes the same values
+    pair[b] = a;
+  }
+}
+
 // geometry-only operators of calculate_hfield on the structural pattern (always f64)
 void assemble_aux(Handle& h) {
   FW_REQUIRE(h.sp.valid && h.has_symbolic, "space/symbolic missing");
@@ -581,6 +594,15 @@ void assemble_aux(Handle& h) {
   }
   // compact copy of the mass matrix (the cross blocks are structural zeros on the shared pattern)
   h.MassC.nnz = compact_csr_dev(h, pat, h.Mass, 2, h.MassC.indptr, h.MassC.indices, h.MassC.vals);
+  // 2 x 2 blocks of the block-Jacobi preconditioner of the H-field PCG: consecutive Nedelec functions of one entity
+  if (sp.nb == 14) {
+    h.MassC.pair.alloc((size_t)sp.n);
+    FW_CHECK_CUDA(cudaMemsetAsync(h.MassC.pair.p, 0xff, (size_t)sp.n * sizeof(int), s));
+    k_mass_pairs<<<cdiv(sp.ne, 256), 256, 0, s>>>(sp.ne, sp.edofs.p, h.MassC.pair.p);
+    h.tim.kernel_launches += 1;
+  } else {
+    h.MassC.pair.release();
+  }
   h.MassC.valid = true;
   h.tim.kernel_launches += 5;
 }

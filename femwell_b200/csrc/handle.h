@@ -63,6 +63,7 @@ struct Handle {
   struct CompactCsr {
     DevBuf<int> indptr, indices;
     DevBuf<double> vals;
+    DevBuf<int> pair;  // order 2: partner of every Nedelec dof (same edge / same triangle), -1 otherwise
     int64_t nnz = 0;
     bool valid = false;
   } MassC;

@@ -22,7 +22,7 @@ void hfield_dev(Handle& h, const cplx* E_dev, cplx beta, double omega, double mu
 void hfield_multi_dev(Handle& h, int k, const cplx* E_dev, const cplx* betas, double omega, double mu0, cplx* H_dev);
 void mass_solve_multi(Handle& h, int k, const cplx* B, cplx* X);
 void pcg_solve_multi(Handle& h, int n_rows, const int* indptr, const int* indices, const double* vals, int64_t nnz,
-                     int k, const cplx* B, cplx* X);
+                     int k, const cplx* B, cplx* X, const int* pair = nullptr);
 std::complex<double> overlap_cross_dev(Handle& h, const fw_space& sj, const cplx* Ei, const cplx* Hi, const double* Ej_host,
                                        const double* Hj_host, int mode, int n_sel, const int* elements_dev);
 void intensity_dev(Handle& h, const cplx* E, const cplx* Hf, double* out);
