@@ -252,7 +252,7 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
   sp.valid = true;
   h.generic.valid = false;
   h.has_symbolic = false;
-  h.A.valid = h.B.valid = h.Mass.valid = h.C0.valid = h.C1.valid = h.MassC.valid = false;
+  h.A.valid = h.B.valid = h.Mass.valid = h.C0.valid = h.C1.valid = h.MassC.valid = h.Bc.valid = false;
   h.lu.reset();
   h.tim = fw_timings{};
   h.tim.upload_ms = tu.stop();

@@ -67,6 +67,29 @@ static void op_apply_impl(Handle& h, const uint8_t* active, S alphaA, S alphaB, 
   h.tim.kernel_launches += 1;
 }
 
+// y = alpha * Bc x on the compact copy of B (rows/columns of inactive dofs masked; active == nullptr: none)
+template <class V, class S>
+__global__ void __launch_bounds__(256) k_spmv_bc(int n, const int* __restrict__ indptr, const int* __restrict__ indices,
+                                                 const V* __restrict__ B, S alpha, const uint8_t* __restrict__ active,
+                                                 const S* __restrict__ x, S* __restrict__ y) {
+  constexpr int TPR = 8;
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = (int)(gt / TPR), l = (int)(gt % TPR);
+  S acc = scalar_traits<S>::zero();
+  const bool live = row < n && (!active || active[row]);
+  if (live) {
+    const int a = indptr[row], b = indptr[row + 1];
+    for (int k = a + l; k < b; k += TPR) {
+      const int c = indices[k];
+      if (active && !active[c]) continue;
+      fma_(acc, cvt_<V, S>(B[k]), x[c]);
+    }
+  }
+#pragma unroll
+  for (int o = TPR / 2; o > 0; o >>= 1) acc = acc + shfl_xor_(acc, o);
+  if (l == 0 && row < n) y[row] = live ? alpha * acc : scalar_traits<S>::zero();
+}
+
 // ------------------------------------------------------------------------------ CGS2 kernels
 // partial[b*nvec + i] = sum over the rows of block b of conj(V[i][r]) * w[r]
 template <class T>
@@ -322,6 +345,7 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
 
   DevBuf<uint8_t> act;
   act.upload(active_host.data(), active_host.size(), s);
+  const bool any_inactive = std::find(active_host.begin(), active_host.end(), (uint8_t)0) != active_host.end();
   Work W;
   W.V.alloc((size_t)(m + 1) * n * wsc);
   W.w.alloc((size_t)n * wsc);
@@ -346,7 +370,13 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
   // y = OP x = (K - sigma M)^-1 M x, with `refine` steps of iterative refinement on the solve
   auto apply_op = [&](const T* x, T* y) {
     // t1 = M x = -(B x)
-    op_apply_impl<V, T>(h, act.p, zeroT, minus1, false, x, t1);
+    if (h.Bc.valid && !h.generic.valid) {
+      k_spmv_bc<V, T><<<cdiv((int64_t)n * 8, 256), 256, 0, s>>>(n, h.Bc.indptr.p, h.Bc.indices.p, (const V*)h.Bc.vals.p,
+                                                               minus1, any_inactive ? act.p : nullptr, x, t1);
+      h.tim.kernel_launches += 1;
+    } else {
+      op_apply_impl<V, T>(h, act.p, zeroT, minus1, false, x, t1);
+    }
     Timer ts(s);
     lu_solve_dev(h, t1, y, 1);
     for (int it = 0; it < refine; ++it) {

@@ -45,6 +45,7 @@ void setup_generic_csr(Handle& h, int n, const int* Kp, const int* Ki, const voi
                        const void* Mx, bool is_complex, const double* coords) {
   FW_REQUIRE(n > 0 && Kp && Ki && Kx && Mp && Mi && Mx, "bad CSR arguments");
   h.lu_prefetch.reset();  // joins a pending analysis of the previous space
+  h.Bc.valid = h.MassC.valid = false;
   const int w = is_complex ? 2 : 1;
   cudaStream_t s = h.stream;
   // ---- union pattern, A = -K, B = -M on it

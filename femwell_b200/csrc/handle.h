@@ -66,7 +66,7 @@ struct Handle {
     DevBuf<int> pair;  // order 2: partner of every Nedelec dof (same edge / same triangle), -1 otherwise
     int64_t nnz = 0;
     bool valid = false;
-  } MassC;
+  } MassC, Bc;  // Bc: bform without the zero slots of the shared pattern (M x of the Arnoldi operator)
   Connectivity generic;  // set by fw_eigs_csr instead of a space
   DevBuf<double> blocks;  // scratch: local element blocks (SoA [entry][Ne])
   // generic COO->CSR result

@@ -330,7 +330,7 @@ void symbolic_space(Handle& h) {
   tr.mark("symbolic: pattern");
   h.has_symbolic = true;
   h.pat.n_tt = -1;
-  h.A.valid = h.B.valid = h.Mass.valid = h.C0.valid = h.C1.valid = h.MassC.valid = false;
+  h.A.valid = h.B.valid = h.Mass.valid = h.C0.valid = h.C1.valid = h.MassC.valid = h.Bc.valid = false;
 }
 
 // ------------------------------------------------------------------------------ segmented reduce
