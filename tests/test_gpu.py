@@ -459,6 +459,41 @@ def test_cross_mesh_overlap_matches_oracle(ctx, order_i, order_j):
         calculate_overlap(bi, E_i, H_i, bk, E_j, H_j)
 
 
+def test_wavelength_sweep_reuses_symbolic_work_and_matches_cold_solves(ctx):
+    """Fixed-mesh sweep (vary_wavelength.py:83-95): CSR pattern and LU analysis are reused between the points;
+    every point must equal a cold solve of the same problem."""
+    from femwell_b200.maxwell.waveguide import compute_modes, get_context
+    from femwell_b200.sweep import group_index, wavelength_sweep
+
+    m, eps = strip_problem(14)
+    b0 = Basis(m, ElementTriP0(), intorder=4)
+    wls = np.linspace(1.5, 1.6, 4)
+    eps_of = lambda wl: eps * (1.0 + 0.02 * (wl - 1.55))
+    table = wavelength_sweep(b0, eps_of, wls, num_modes=2, order=2)
+    assert table.shape == (4, 2)
+    assert get_context().timings()["lu_symbolic_ms"] < 5.0  # last point: analysis reused
+    for i, wl in enumerate(wls):
+        get_context()._space_key = None  # cold: new space, new pattern, new analysis
+        cold = compute_modes(b0, eps_of(wl), wl, num_modes=2, order=2).n_effs
+        assert np.abs(table[i] - cold).max() < 1e-11
+    assert np.all(np.isfinite(group_index(wls, table[:, 0].real)))
+
+
+def test_sweep_two_gpus_nccl():
+    """One process per GPU, block partition of the sweep, one NCCL all_gather (skipped on a single-GPU box)."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "scripts", "sweep_nccl_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "SWEEP_NCCL_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_argument_validation(ctx):
     from femwell_b200.maxwell.waveguide import compute_modes
 
