@@ -499,15 +499,81 @@ __device__ __forceinline__ void bcast_to_cluster(double* xs_local, int buf, int 
   }
 }
 
+// ---- step signalling without a cluster barrier: the owner warp stores x_k into every CTA with st.async, which
+// completes transaction bytes on an mbarrier of the destination CTA; the consumers wait on their local mbarrier.
+// (A barrier.cluster with release/acquire semantics makes every thread wait for its outstanding prefetch loads:
+// 2.1 us per step; the mbarrier hand-off leaves the loads in flight.)  XRING slots, one cluster barrier every
+// XRING steps bounds how far the CTAs can drift apart, so a slot is never overwritten while it is still read.
+constexpr int XRING = 8;
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* b, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void st_async_remote(double* local_dst, unsigned long long* local_bar, unsigned cta, double v) {
+  unsigned ra, rb;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(smem_u32(local_dst)), "r"(cta));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(rb) : "r"(smem_u32(local_bar)), "r"(cta));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];\n" ::"r"(ra),
+               "l"(__double_as_longlong(v)), "r"(rb)
+               : "memory");
+}
+// one chain step: publish x_k (owner warp) and wait for it (everybody); returns the slot of the ring that holds x_k
+template <int NRHS>
+__device__ __forceinline__ const double* chain_step_exchange(int step, bool owner, int lane, int t, const double* Dw,
+                                                             double (&acc)[NRHS], double* xs, unsigned long long* mbar,
+                                                             int use_mbar) {
+  cg::cluster_group cl = cg::this_cluster();
+  if (!use_mbar) {
+    const int buf = step & 1;
+    if (owner) {
+      inv_block_matvec<NRHS>(Dw, lane, acc);
+      bcast_to_cluster<NRHS>(xs, buf, lane, acc);
+    }
+    cl.sync();
+    return xs + buf * NRHS * PW;
+  }
+  const int slot = step & (XRING - 1);
+  if (slot == 0 && step > 0) cl.sync();
+  if (t == 0) mbar_expect_tx(&mbar[slot], 8u * PW * NRHS);
+  if (owner) {
+    inv_block_matvec<NRHS>(Dw, lane, acc);
+#pragma unroll
+    for (int c = 0; c < CL; ++c)
+#pragma unroll
+      for (int r = 0; r < NRHS; ++r) st_async_remote(xs + (slot * NRHS + r) * PW + lane, &mbar[slot], (unsigned)c, acc[r]);
+  }
+  const unsigned par = (unsigned)(step / XRING) & 1u;
+  while (!mbar_try_wait(&mbar[slot], par)) {
+  }
+  return xs + slot * NRHS * PW;
+}
+
 template <int NRHS>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
     k_fwd_chain_inv(FrontTab T, const int* __restrict__ nodes, const double* __restrict__ F,
                     const double* __restrict__ dinv, const int* __restrict__ rowperm, double* work,
-                    int64_t work_stride, double* xp, int na) {
+                    int64_t work_stride, double* xp, int na, int use_mbar) {
   extern __shared__ __align__(16) double inv_smem[];
+  __shared__ __align__(8) unsigned long long mbar[XRING];
   double* Dsm = inv_smem;                                  // [warps][PW*PW]
-  double* xs = inv_smem + (CL_THREADS / 32) * PW * PW;     // [2][NRHS][PW]
+  double* xs = inv_smem + (CL_THREADS / 32) * PW * PW;     // [XRING][NRHS][PW]
   cg::cluster_group cl = cg::this_cluster();
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < XRING; ++b) mbar_init(&mbar[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
   const int node = nodes[blockIdx.x / CL];
   const int m = T.m[node], ns = T.ns[node], os = T.own_start[node];
   const double* Fn = F + T.front_off[node];
@@ -568,14 +634,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
   cp_async_wait_all();
   __syncwarp();
   for (int k = 0; k < npan; ++k) {
-    const int k0 = k * PW, buf = k & 1;
-    if (gw == k) {
-      inv_block_matvec<NRHS>(Dw, lane, acc);
-      bcast_to_cluster<NRHS>(xs, buf, lane, acc);
-    }
-    cl.sync();
+    const int k0 = k * PW;
+    const double* xk = chain_step_exchange<NRHS>(k, gw == k, lane, t, Dw, acc, xs, mbar, use_mbar);
     if (row0 >= k0 + PW && row0 < ns) {
-      panel_dot_sub<NRHS>(acc, ln, xs + buf * NRHS * PW);
+      panel_dot_sub<NRHS>(acc, ln, xk);
       if (row0 >= k0 + 2 * PW) {
 #pragma unroll
         for (int j = 0; j < PW; ++j) ln[j] = Fn[row0 + (long long)(k0 + PW + j) * m];
@@ -591,11 +653,18 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
 template <int NRHS>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
     k_bwd_chain_inv(FrontTab T, const int* __restrict__ nodes, const double* __restrict__ F,
-                    const double* __restrict__ dinv, double* work, int64_t work_stride, double* xp, int na) {
+                    const double* __restrict__ dinv, double* work, int64_t work_stride, double* xp, int na,
+                    int use_mbar) {
   extern __shared__ __align__(16) double inv_smem[];
+  __shared__ __align__(8) unsigned long long mbar[XRING];
   double* Dsm = inv_smem;
   double* xs = inv_smem + (CL_THREADS / 32) * PW * PW;
   cg::cluster_group cl = cg::this_cluster();
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < XRING; ++b) mbar_init(&mbar[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  cl.sync();  // the barriers of every CTA are initialised before anyone signals them
   const int node = nodes[blockIdx.x / CL];
   const int m = T.m[node], ns = T.ns[node], os = T.own_start[node];
   if (ns == 0) return;
@@ -631,14 +700,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
   cp_async_wait_all();
   __syncwarp();
   for (int k = npan - 1; k >= 0; --k) {
-    const int k0 = k * PW, buf = k & 1;
-    if (gw == k) {
-      inv_block_matvec<NRHS>(Dw, lane, acc);
-      bcast_to_cluster<NRHS>(xs, buf, lane, acc);
-    }
-    cl.sync();
+    const int k0 = k * PW;
+    const double* xk = chain_step_exchange<NRHS>(npan - 1 - k, gw == k, lane, t, Dw, acc, xs, mbar, use_mbar);
     if (row0 < k0) {
-      panel_dot_sub<NRHS>(acc, un, xs + buf * NRHS * PW);
+      panel_dot_sub<NRHS>(acc, un, xk);
       if (row0 < k0 - PW) {
 #pragma unroll
         for (int j = 0; j < PW; ++j) un[j] = Fn[row0 + (long long)(k0 - PW + j) * m];
@@ -817,7 +882,8 @@ template <int NRHS>
 struct InvChain<double, NRHS> {
   static void launch(bool fwd, int nfront, FrontTab T, const int* nodes, const double* F, LUDevice& d, double* work,
                      int64_t work_stride, double* xp, int na, cudaStream_t s) {
-    constexpr int smem = INV_SMEM_BYTES + 2 * NRHS * PW * 8;
+    constexpr int smem = INV_SMEM_BYTES + XRING * NRHS * PW * 8;
+    static const int use_mbar = getenv("FW_CHAIN_MBAR") ? atoi(getenv("FW_CHAIN_MBAR")) : 1;
     static bool configured[64] = {};
     if (first_use_on_device(configured)) {
       FW_CHECK_CUDA(cudaFuncSetAttribute(k_fwd_chain_inv<NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -825,9 +891,10 @@ struct InvChain<double, NRHS> {
     }
     if (fwd)
       k_fwd_chain_inv<NRHS><<<nfront * CL, CL_THREADS, smem, s>>>(T, nodes, F, d.dinv.p, d.rowperm.p, work, work_stride,
-                                                               xp, na);
+                                                               xp, na, use_mbar);
     else
-      k_bwd_chain_inv<NRHS><<<nfront * CL, CL_THREADS, smem, s>>>(T, nodes, F, d.dinv.p, work, work_stride, xp, na);
+      k_bwd_chain_inv<NRHS><<<nfront * CL, CL_THREADS, smem, s>>>(T, nodes, F, d.dinv.p, work, work_stride, xp, na,
+                                                               use_mbar);
   }
 };
 template <class S, int NRHS>
