@@ -440,7 +440,6 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
 //                earlier.
 // No global-memory access sits on the dependent path any more (the first version re-read w from L2 and ran a
 // 32-step shuffle substitution per panel: 4.8 us per step; see DESIGN.md for the measured effect).
-constexpr int INV_SMEM_BYTES = (CL_THREADS / 32) * PW * PW * 8;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -560,15 +559,18 @@ __device__ __forceinline__ const double* chain_step_exchange(int step, bool owne
   return xs + slot * NRHS * PW;
 }
 
-template <int NRHS>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
+// THREADS x CL rows per cluster; STAGES panels of factor entries are kept in flight per thread (registers): with one
+// stage the load issued at the end of step k is needed one step (~1 us) later and its L2 latency bounds the step;
+// 256 threads per CTA leave room for two or three stages.
+template <int NRHS, int THREADS, int STAGES>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS)
     k_fwd_chain_inv(FrontTab T, const int* __restrict__ nodes, const double* __restrict__ F,
                     const double* __restrict__ dinv, const int* __restrict__ rowperm, double* work,
                     int64_t work_stride, double* xp, int na, int use_mbar) {
   extern __shared__ __align__(16) double inv_smem[];
   __shared__ __align__(8) unsigned long long mbar[XRING];
-  double* Dsm = inv_smem;                                  // [warps][PW*PW]
-  double* xs = inv_smem + (CL_THREADS / 32) * PW * PW;     // [XRING][NRHS][PW]
+  double* Dsm = inv_smem;                               // [warps][PW*PW]
+  double* xs = inv_smem + (THREADS / 32) * PW * PW;     // [XRING][NRHS][PW]
   cg::cluster_group cl = cg::this_cluster();
   if (threadIdx.x == 0) {
     for (int b = 0; b < XRING; ++b) mbar_init(&mbar[b], 1);
@@ -581,8 +583,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
 #pragma unroll
   for (int r = 0; r < NRHS; ++r) w[r] = work + (size_t)r * work_stride + T.work_off[node];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const int nth = CL_THREADS * CL;
-  const int gt = (int)cl.block_rank() * CL_THREADS + t;
+  const int nth = THREADS * CL;
+  const int gt = (int)cl.block_rank() * THREADS + t;
   // panels are dealt round-robin to the CTAs of the cluster: the rows still active at any step are spread
   // evenly over the 8 SMs (the chain is bound by the L2 -> SM fill bandwidth of the SMs that hold rows)
   const int gw = wid * CL + (int)cl.block_rank();  // the panel owned by this warp
@@ -598,10 +600,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
   // L2 now (one bulk prefetch per column, issued by the thread that owns the row of the same index), so that
   // the one-step-ahead register prefetch below is served by L2 instead of HBM.
   if (row0 < ns) prefetch_l2_bulk(Fn + (long long)row0 * m + row0, (long long)(ns - row0) * 8);
-  double ln[PW];
-  if (row0 >= PW && row0 < ns) {
+  double ln[STAGES][PW];
 #pragma unroll
-    for (int j = 0; j < PW; ++j) ln[j] = Fn[row0 + (long long)j * m];
+  for (int st = 0; st < STAGES; ++st) {
+    if (st < npan && row0 >= (st + 1) * PW && row0 < ns) {
+#pragma unroll
+      for (int j = 0; j < PW; ++j) ln[st][j] = Fn[row0 + (long long)(st * PW + j) * m];
+    }
   }
   // assemble w: own rhs entries + contributions of the children (same as the generic chain)
   for (int i = gt; i < m; i += nth)
@@ -633,14 +638,19 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
   for (int r = 0; r < NRHS; ++r) acc[r] = row0 < ns ? xp[(size_t)r * na + os + rowperm[os + row0]] : 0.0;
   cp_async_wait_all();
   __syncwarp();
-  for (int k = 0; k < npan; ++k) {
-    const int k0 = k * PW;
-    const double* xk = chain_step_exchange<NRHS>(k, gw == k, lane, t, Dw, acc, xs, mbar, use_mbar);
-    if (row0 >= k0 + PW && row0 < ns) {
-      panel_dot_sub<NRHS>(acc, ln, xk);
-      if (row0 >= k0 + 2 * PW) {
+  for (int kb = 0; kb < npan; kb += STAGES) {
 #pragma unroll
-        for (int j = 0; j < PW; ++j) ln[j] = Fn[row0 + (long long)(k0 + PW + j) * m];
+    for (int st = 0; st < STAGES; ++st) {
+      const int k = kb + st;
+      if (k < npan) {
+        const double* xk = chain_step_exchange<NRHS>(k, gw == k, lane, t, Dw, acc, xs, mbar, use_mbar);
+        if (row0 >= (k + 1) * PW && row0 < ns) panel_dot_sub<NRHS>(acc, ln[st], xk);
+        // this stage is free again: entries of panel k + STAGES (a row below a panel means the panel is full)
+        const int kn = k + STAGES;
+        if (kn < npan && row0 >= (kn + 1) * PW && row0 < ns) {
+#pragma unroll
+          for (int j = 0; j < PW; ++j) ln[st][j] = Fn[row0 + (long long)(kn * PW + j) * m];
+        }
       }
     }
   }
@@ -650,15 +660,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
   }
 }
 
-template <int NRHS>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
+template <int NRHS, int THREADS, int STAGES>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS)
     k_bwd_chain_inv(FrontTab T, const int* __restrict__ nodes, const double* __restrict__ F,
                     const double* __restrict__ dinv, double* work, int64_t work_stride, double* xp, int na,
                     int use_mbar) {
   extern __shared__ __align__(16) double inv_smem[];
   __shared__ __align__(8) unsigned long long mbar[XRING];
   double* Dsm = inv_smem;
-  double* xs = inv_smem + (CL_THREADS / 32) * PW * PW;
+  double* xs = inv_smem + (THREADS / 32) * PW * PW;
   cg::cluster_group cl = cg::this_cluster();
   if (threadIdx.x == 0) {
     for (int b = 0; b < XRING; ++b) mbar_init(&mbar[b], 1);
@@ -673,7 +683,6 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
 #pragma unroll
   for (int r = 0; r < NRHS; ++r) w[r] = work + (size_t)r * work_stride + T.work_off[node];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const int gt = (int)cl.block_rank() * CL_THREADS + t;
   const int gw = wid * CL + (int)cl.block_rank();  // round-robin panel ownership (see k_fwd_chain_inv)
   const int row0 = gw * PW + lane;
   const int npan = (ns + PW - 1) / PW;
@@ -685,13 +694,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
   }
   // upper triangle of U11 into L2 (see k_fwd_chain_inv)
   if (row0 < ns) prefetch_l2_bulk(Fn + (long long)row0 * m, (long long)(row0 + 1) * 8);
-  double un[PW];
-  {
-    // entries of the last (possibly ragged) panel for the rows above it
-    const int k0 = (npan - 1) * PW, wd = ns - k0;
-    if (row0 < k0) {
+  // stage st holds the entries of panel npan - 1 - (step) for the steps = st (mod STAGES); the last panel may be ragged
+  double un[STAGES][PW];
 #pragma unroll
-      for (int j = 0; j < PW; ++j) un[j] = j < wd ? Fn[row0 + (long long)(k0 + j) * m] : 0.0;
+  for (int st = 0; st < STAGES; ++st) {
+    const int kp = npan - 1 - st;
+    if (kp >= 0 && row0 < kp * PW) {
+      const int wd = min(PW, ns - kp * PW);
+#pragma unroll
+      for (int j = 0; j < PW; ++j) un[st][j] = j < wd ? Fn[row0 + (long long)(kp * PW + j) * m] : 0.0;
     }
   }
   double acc[NRHS];
@@ -699,14 +710,19 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
   for (int r = 0; r < NRHS; ++r) acc[r] = row0 < ns ? w[r][row0] : 0.0;
   cp_async_wait_all();
   __syncwarp();
-  for (int k = npan - 1; k >= 0; --k) {
-    const int k0 = k * PW;
-    const double* xk = chain_step_exchange<NRHS>(npan - 1 - k, gw == k, lane, t, Dw, acc, xs, mbar, use_mbar);
-    if (row0 < k0) {
-      panel_dot_sub<NRHS>(acc, un, xk);
-      if (row0 < k0 - PW) {
+  for (int sb = 0; sb < npan; sb += STAGES) {
 #pragma unroll
-        for (int j = 0; j < PW; ++j) un[j] = Fn[row0 + (long long)(k0 - PW + j) * m];
+    for (int st = 0; st < STAGES; ++st) {
+      const int step = sb + st;
+      if (step < npan) {
+        const int k = npan - 1 - step;
+        const double* xk = chain_step_exchange<NRHS>(step, gw == k, lane, t, Dw, acc, xs, mbar, use_mbar);
+        if (row0 < k * PW) panel_dot_sub<NRHS>(acc, un[st], xk);
+        const int kn = k - STAGES;  // always a full panel
+        if (kn >= 0 && row0 < kn * PW) {
+#pragma unroll
+          for (int j = 0; j < PW; ++j) un[st][j] = Fn[row0 + (long long)(kn * PW + j) * m];
+        }
       }
     }
   }
@@ -876,31 +892,47 @@ static int chain_threads(int max_ns) {
 
 template <class S, int NRHS>
 struct InvChain {
-  static void launch(bool, int, FrontTab, const int*, const S*, LUDevice&, S*, int64_t, S*, int, cudaStream_t) {}
+  static void launch(bool, int, int, FrontTab, const int*, const S*, LUDevice&, S*, int64_t, S*, int, cudaStream_t) {}
 };
 template <int NRHS>
 struct InvChain<double, NRHS> {
-  static void launch(bool fwd, int nfront, FrontTab T, const int* nodes, const double* F, LUDevice& d, double* work,
-                     int64_t work_stride, double* xp, int na, cudaStream_t s) {
-    constexpr int smem = INV_SMEM_BYTES + XRING * NRHS * PW * 8;
-    static const int use_mbar = getenv("FW_CHAIN_MBAR") ? atoi(getenv("FW_CHAIN_MBAR")) : 1;
+  template <int THREADS, int STAGES>
+  static void run(bool fwd, int nfront, FrontTab T, const int* nodes, const double* F, LUDevice& d, double* work,
+                  int64_t work_stride, double* xp, int na, cudaStream_t s, int use_mbar) {
+    constexpr int smem = (THREADS / 32) * PW * PW * 8 + XRING * NRHS * PW * 8;
     static bool configured[64] = {};
     if (first_use_on_device(configured)) {
-      FW_CHECK_CUDA(cudaFuncSetAttribute(k_fwd_chain_inv<NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      FW_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_chain_inv<NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      FW_CHECK_CUDA(cudaFuncSetAttribute(k_fwd_chain_inv<NRHS, THREADS, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      FW_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_chain_inv<NRHS, THREADS, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     if (fwd)
-      k_fwd_chain_inv<NRHS><<<nfront * CL, CL_THREADS, smem, s>>>(T, nodes, F, d.dinv.p, d.rowperm.p, work, work_stride,
-                                                               xp, na, use_mbar);
+      k_fwd_chain_inv<NRHS, THREADS, STAGES><<<nfront * CL, THREADS, smem, s>>>(T, nodes, F, d.dinv.p, d.rowperm.p, work,
+                                                                              work_stride, xp, na, use_mbar);
     else
-      k_bwd_chain_inv<NRHS><<<nfront * CL, CL_THREADS, smem, s>>>(T, nodes, F, d.dinv.p, work, work_stride, xp, na,
-                                                               use_mbar);
+      k_bwd_chain_inv<NRHS, THREADS, STAGES><<<nfront * CL, THREADS, smem, s>>>(T, nodes, F, d.dinv.p, work, work_stride,
+                                                                              xp, na, use_mbar);
+  }
+  static void launch(bool fwd, int nfront, int max_ns, FrontTab T, const int* nodes, const double* F, LUDevice& d,
+                     double* work, int64_t work_stride, double* xp, int na, cudaStream_t s) {
+    static const int use_mbar = getenv("FW_CHAIN_MBAR") ? atoi(getenv("FW_CHAIN_MBAR")) : 1;
+    // measured on the 2001-row root front (forward chain): 512 threads / 1 stage 0.125 ms, 256 / 2 stages 0.102 ms,
+    // 256 / 3 stages 0.125 ms (255 registers)
+    static const int stages = getenv("FW_CHAIN_STAGES") ? atoi(getenv("FW_CHAIN_STAGES")) : 2;
+    // pivot blocks of up to 8 x 256 rows: one row per thread with 256-thread CTAs and a deeper register pipeline
+    if (max_ns <= CL * 256 && stages >= 3 && NRHS == 1)
+      run<256, 3>(fwd, nfront, T, nodes, F, d, work, work_stride, xp, na, s, use_mbar);
+    else if (max_ns <= CL * 256 && stages == 2)
+      run<256, 2>(fwd, nfront, T, nodes, F, d, work, work_stride, xp, na, s, use_mbar);
+    else
+      run<CL_THREADS, 1>(fwd, nfront, T, nodes, F, d, work, work_stride, xp, na, s, use_mbar);
   }
 };
 template <class S, int NRHS>
-static void launch_inv_chain(bool fwd, int nfront, FrontTab T, const int* nodes, const S* F, LUDevice& d, S* work,
-                             int64_t work_stride, S* xp, int na, cudaStream_t s) {
-  InvChain<S, NRHS>::launch(fwd, nfront, T, nodes, F, d, work, work_stride, xp, na, s);
+static void launch_inv_chain(bool fwd, int nfront, int max_ns, FrontTab T, const int* nodes, const S* F, LUDevice& d,
+                             S* work, int64_t work_stride, S* xp, int na, cudaStream_t s) {
+  InvChain<S, NRHS>::launch(fwd, nfront, max_ns, T, nodes, F, d, work, work_stride, xp, na, s);
 }
 
 template <class S, int NRHS>
@@ -943,7 +975,7 @@ static void solve_typed(Handle& h, const S* b, S* x) {
       k_fwd_chain_fused<S, NRHS><<<nfront, chain_threads(Sy.level_max_m[lev] / fuse_tdiv), 0, s>>>(T, nodes, F, d.rowperm.p, work,
                                                                                     Sy.work_entries, xp, na);
     else if (use_inv(max_ns))
-      launch_inv_chain<S, NRHS>(true, nfront, T, nodes, F, d, work, Sy.work_entries, xp, na, s);
+      launch_inv_chain<S, NRHS>(true, nfront, max_ns, T, nodes, F, d, work, Sy.work_entries, xp, na, s);
     else if (max_ns > CL_MIN_NS && !no_cluster)
       k_fwd_chain_cluster<S, NRHS><<<nfront * CL, CL_THREADS, 0, s>>>(T, nodes, F, d.rowperm.p, work,
                                                                       Sy.work_entries, xp, na);
@@ -998,7 +1030,7 @@ static void solve_typed(Handle& h, const S* b, S* x) {
       k_bwd_chain_fused<S, NRHS><<<nfront, chain_threads(std::max(max_ns, 64)), 0, s>>>(T, nodes, F, work, Sy.work_entries,
                                                                                      xp, na);
     else if (use_inv(max_ns))
-      launch_inv_chain<S, NRHS>(false, nfront, T, nodes, F, d, work, Sy.work_entries, xp, na, s);
+      launch_inv_chain<S, NRHS>(false, nfront, max_ns, T, nodes, F, d, work, Sy.work_entries, xp, na, s);
     else if (max_ns > CL_MIN_NS && !no_cluster)
       k_bwd_chain_cluster<S, NRHS><<<nfront * CL, CL_THREADS, 0, s>>>(T, nodes, F, work, Sy.work_entries, xp, na);
     else
