@@ -792,6 +792,11 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
   const bool trace2 = tenv && atoi(tenv) >= 2;
   static const int big_gemm_min = getenv("FW_BIG_GEMM_MIN") ? atoi(getenv("FW_BIG_GEMM_MIN")) : 384;
   static const bool no_cluster_panel = getenv("FW_NO_CLUSTER_PANEL") != nullptr;
+  // per-panel rank-32 updates: the 64x64 tile kernel (3+ CTAs per SM) beats the 128x128 one (244 registers, one CTA
+  // per SM, only two K-chunks to pipeline): 69.9 vs 76.5 ms over the nine top levels; the big kernel keeps the Schur
+  // updates (K = ns)
+  static const int big_gemm_min_panel =
+      getenv("FW_BIG_GEMM_MIN_PANEL") ? atoi(getenv("FW_BIG_GEMM_MIN_PANEL")) : (1 << 30);
   for (int lev = Sy.n_levels - 1; lev >= 0; --lev) {
     const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
     const int* nodes = d.level_nodes.p + Sy.level_start[lev];
@@ -825,7 +830,7 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
       k_lu_swap_trsm<S><<<dim3(nfront, ctiles + rtiles), 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles);
       const int rem = max_m - (k * PW);  // upper bound of the trailing size
       const int nt = (rem + 63) / 64;
-      if (rem >= big_gemm_min)
+      if (rem >= big_gemm_min_panel)
         lu_gemm_big_launch<S>(T, nodes, nfront, k, F, rem, false, s);
       else if (nt > 0)
         k_lu_gemm<S, false><<<dim3(nfront, nt, nt), 256, 0, s>>>(T, nodes, k, F);
