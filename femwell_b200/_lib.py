@@ -76,7 +76,7 @@ class FemwellB200Error(RuntimeError):
 
 # every symbol include/femwell_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "fw_last_error", "fw_version", "fw_create", "fw_destroy", "fw_synchronize", "fw_set_option", "fw_set_space",
+    "fw_last_error", "fw_version", "fw_create", "fw_destroy", "fw_synchronize", "fw_set_option", "fw_set_space", "fw_analysis_hint",
     "fw_symbolic", "fw_assemble_waveguide", "fw_matrix_nnz", "fw_matrix_export", "fw_coo_to_csr",
     "fw_coo_to_csr_export", "fw_matrix_spmv", "fw_eigs", "fw_eigs_csr", "fw_lu_factor_shifted", "fw_lu_solve",
     "fw_postprocess_modes", "fw_hfield", "fw_functional", "fw_intensity", "fw_poynting", "fw_overlap_cross", "fw_energy_current_density", "fw_compute_modes", "fw_get_timings",

@@ -56,10 +56,16 @@ class Context:
         (s.p, s.t, s.element_dofs, s.kind, s.vec, s.sc, s.X, s.W) = [a.ctypes.data for a in keep]
         return s, keep, tb
 
-    def set_space(self, basis: Basis):
-        """Upload mesh + FE space (a1).  ``basis`` must carry the mixed N x P element."""
+    def set_space(self, basis: Basis, solve_hint=None):
+        """Upload mesh + FE space (a1).  ``basis`` must carry the mixed N x P element.
+        ``solve_hint = (dirichlet_dofs or None, leaf_elements)`` announces the eigen-solve that follows, so that the host
+        analysis of its sparse LU already runs while the mesh is uploaded."""
         s, keep, tb = self._space_struct(basis)
         m = basis.mesh
+        if solve_hint is not None:
+            d, leaf = solve_hint
+            d = None if d is None else L.as_i32(d)
+            L.check(self.lib.fw_analysis_hint(self._h, 0 if d is None else d.size, L.ptr(d), int(leaf or 0)))
         L.check(self.lib.fw_set_space(self._h, C.byref(s)))
         self.basis = basis
         self.n = basis.N

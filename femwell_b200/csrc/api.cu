@@ -240,6 +240,19 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
     FW_REQUIRE(!(b & 1), "t out of range");
     FW_REQUIRE(!(b & 2), "element_dofs out of range");
   }
+  h.lu.reset();
+  if (h.hint_valid) {
+    // the caller announced the solve that follows (fw_analysis_hint): the host analysis of its sparse LU starts now and
+    // overlaps the uploads below and everything up to the factorisation
+    h.hint_valid = false;
+    std::vector<uint8_t> active((size_t)sp.n, 1);
+    for (int d : h.hint_dirichlet) {
+      FW_REQUIRE(d >= 0 && d < sp.n, "dirichlet dof out of range");
+      active[d] = 0;
+    }
+    h.generic.valid = false;
+    lu_analyse_prefetch(h, active, h.hint_leaf);
+  }
   sp.p.alloc(sp.h_p.size());
   sp.t.alloc(sp.h_t.size());
   sp.edofs.alloc(sp.h_edofs.size());
@@ -256,6 +269,16 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
   h.lu.reset();
   h.tim = fw_timings{};
   h.tim.upload_ms = tu.stop();
+  FW_API_END
+}
+
+int fw_analysis_hint(fw_handle* hh, int32_t n_dirichlet, const int32_t* dirichlet, int32_t leaf_elements) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && (n_dirichlet == 0 || dirichlet), "NULL argument");
+  Handle& h = hh->h;
+  h.hint_dirichlet.assign(dirichlet, dirichlet + (n_dirichlet > 0 ? n_dirichlet : 0));
+  h.hint_leaf = leaf_elements;
+  h.hint_valid = true;
   FW_API_END
 }
 

@@ -76,6 +76,10 @@ struct Handle {
   DevBuf<uint32_t> scan_tmp, scan_tmp2;
   std::unique_ptr<LU> lu;
   std::unique_ptr<LUPrefetch> lu_prefetch;
+  // fw_analysis_hint: Dirichlet set / leaf size of the solve that will follow the next fw_set_space (one shot)
+  std::vector<int> hint_dirichlet;
+  int hint_leaf = 0;
+  bool hint_valid = false;
   // big LU buffers live here so that they survive a new space / analysis (no 25 GB cudaFree + cudaMalloc per solve)
   struct LUArena {
     DevBuf<double> factors, work, xperm, scratch, dinv;

@@ -77,10 +77,13 @@ static bool lu_reusable(const Handle& h, const std::vector<uint8_t>& active, int
 }
 
 void lu_analyse_prefetch(Handle& h, const std::vector<uint8_t>& active, int leaf_elements) {
+  // an analysis with the same keys may already be running (started by fw_set_space from fw_analysis_hint)
+  if (h.lu_prefetch && h.lu_prefetch->lu && h.lu_prefetch->lu->leaf_key == leaf_elements &&
+      h.lu_prefetch->lu->active_key == active)
+    return;
   h.lu_prefetch.reset();
   if (lu_reusable(h, active, leaf_elements)) return;
   if (getenv("FW_NO_PREFETCH")) return;
-  FW_REQUIRE(h.sp.valid || h.generic.valid, "space missing");
   h.lu_prefetch.reset(new LUPrefetch());
   LUPrefetch* pf = h.lu_prefetch.get();
   pf->lu.reset(new LU());

@@ -259,7 +259,7 @@ def compute_modes(
     ctx = get_context(device)
     reuse = ctx.same_space(basis) and ctx.nnz_structural is not None
     if not reuse:
-        ctx.set_space(basis)
+        ctx.set_space(basis, solve_hint=(dirichlet, opts.get("leaf_elements", 0)))
     lams, E, H, powers, stats = ctx.compute_modes(
         eps_kind, epsilon_r, wavelength, num_modes, sigma, mu_r=float(mu_r), radius=float(radius),
         dirichlet=dirichlet, reuse_symbolic=reuse, **opts)

@@ -80,6 +80,10 @@ typedef struct {
   const double* W;          /* [nqp]     quadrature weights                          */
 } fw_space;
 int fw_set_space(fw_handle* h, const fw_space* s);
+/* Optional, before fw_set_space: announces the Dirichlet set (condense, waveguide.py:610-619) and the leaf size of
+ * the solve that will follow, so that the host analysis of its sparse LU starts inside fw_set_space and overlaps
+ * the uploads.  One shot; a solve with other parameters simply redoes the analysis. */
+int fw_analysis_hint(fw_handle* h, int32_t n_dirichlet, const int32_t* dirichlet, int32_t leaf_elements);
 
 /* ---- a5 (structural half): sort-by-key of the (row, col) pairs of all local blocks;
  *      replaces scikit-fem COOData -> scipy coo_matrix.tocsr() index work              */
