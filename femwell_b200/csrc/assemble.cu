@@ -21,6 +21,8 @@
 // Stores are SoA, out[(i*NB+j)*Ne + e]: every store instruction of a warp is one contiguous 256 B (f64) /
 // 512 B (c128) segment.  The kernel sits at the FP64 ridge: the HBM-store floor and the FP64-pipe floor are
 // both ~0.16 ms at 500k triangles (profiles/).
+#include <algorithm>
+
 #include "handle.h"
 
 namespace fw {
@@ -559,6 +561,104 @@ __global__ void k_mass_pairs(int ne, const int* __restrict__ edofs, int* __restr
   }
 }
 
+// ---- split of the compact mass matrix into its Nedelec and Lagrange diagonal blocks
+__global__ void k_flag_z_u32(const uint8_t* __restrict__ is_z, int n, uint32_t* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = is_z[i] ? 1u : 0u;
+}
+// rank[d] = index of dof d inside its own block; idxN / idxP = the inverse maps
+__global__ void k_block_index(const uint8_t* __restrict__ is_z, const uint32_t* __restrict__ zscan, int n,
+                              int* __restrict__ rank, int* __restrict__ idxN, int* __restrict__ idxP) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n) return;
+  const int rp = (int)zscan[d];
+  if (is_z[d]) {
+    rank[d] = rp;
+    idxP[rp] = d;
+  } else {
+    rank[d] = d - rp;
+    idxN[d - rp] = d;
+  }
+}
+__global__ void k_block_rowlen(const int* __restrict__ idx, int nsub, const int* __restrict__ indptr,
+                               uint32_t* __restrict__ len) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nsub) len[i] = (uint32_t)(indptr[idx[i] + 1] - indptr[idx[i]]);
+  if (i == nsub) len[i] = 0;
+}
+__global__ void k_block_fill(const int* __restrict__ idx, int nsub, const int* __restrict__ indptr,
+                             const int* __restrict__ indices, const double* __restrict__ vals,
+                             const int* __restrict__ rank, const uint8_t* __restrict__ is_z,
+                             const int* __restrict__ sub_indptr, int* __restrict__ sub_indices,
+                             double* __restrict__ sub_vals, const int* __restrict__ pair, int* __restrict__ sub_pair,
+                             int* __restrict__ cross) {
+  constexpr int TPR = 8;
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(gt / TPR), l = (int)(gt % TPR);
+  if (i >= nsub) return;
+  const int d = idx[i];
+  const int a = indptr[d], b = indptr[d + 1], o = sub_indptr[i];
+  for (int e = a + l; e < b; e += TPR) {
+    const int c = indices[e];
+    if (is_z[c] != is_z[d]) atomicExch(cross, 1);  // cannot happen for a block-diagonal mass matrix
+    sub_indices[o + (e - a)] = rank[c];
+    sub_vals[o + (e - a)] = vals[e];
+  }
+  if (l == 0 && sub_pair) sub_pair[i] = (pair && pair[d] >= 0) ? rank[pair[d]] : -1;
+}
+
+static void build_mass_blocks(Handle& h) {
+  const Space& sp = h.sp;
+  cudaStream_t s = h.stream;
+  const int n = sp.n;
+  h.mass_split = false;
+  if (getenv("FW_NO_MASS_SPLIT")) return;
+  DevBuf<uint32_t> zs;
+  DevBuf<int> rank, cross;
+  zs.alloc((size_t)n + 1), rank.alloc((size_t)n), cross.alloc(1);
+  cross.zero(s);
+  k_flag_z_u32<<<cdiv(n, 256), 256, 0, s>>>(sp.is_z.p, n, zs.p);
+  uint32_t last_flag = 0, last_scan = 0;
+  FW_CHECK_CUDA(cudaMemcpyAsync(&last_flag, zs.p + (n - 1), 4, cudaMemcpyDeviceToHost, s));
+  exclusive_scan_u32(zs.p, zs.p, n, h.scan_tmp, s);
+  FW_CHECK_CUDA(cudaMemcpyAsync(&last_scan, zs.p + (n - 1), 4, cudaMemcpyDeviceToHost, s));
+  FW_CHECK_CUDA(cudaStreamSynchronize(s));
+  const int nP = (int)(last_scan + last_flag), nN = n - nP;
+  if (nP == 0 || nN == 0) return;
+  h.MassN.idx.alloc((size_t)nN), h.MassP.idx.alloc((size_t)nP);
+  k_block_index<<<cdiv(n, 256), 256, 0, s>>>(sp.is_z.p, zs.p, n, rank.p, h.MassN.idx.p, h.MassP.idx.p);
+  const int* pair = h.MassC.pair.n ? h.MassC.pair.p : nullptr;
+  for (int blk = 0; blk < 2; ++blk) {
+    Handle::MassBlock& B = blk ? h.MassP : h.MassN;
+    B.n = blk ? nP : nN;
+    DevBuf<uint32_t> len;
+    len.alloc((size_t)B.n + 1);
+    k_block_rowlen<<<cdiv(B.n + 1, 256), 256, 0, s>>>(B.idx.p, B.n, h.MassC.indptr.p, len.p);
+    exclusive_scan_u32(len.p, len.p, (int64_t)B.n + 1, h.scan_tmp, s);
+    uint32_t tot = 0;
+    FW_CHECK_CUDA(cudaMemcpyAsync(&tot, len.p + B.n, 4, cudaMemcpyDeviceToHost, s));
+    FW_CHECK_CUDA(cudaStreamSynchronize(s));
+    B.nnz = tot;
+    B.indptr.alloc((size_t)B.n + 1);
+    FW_CHECK_CUDA(cudaMemcpyAsync(B.indptr.p, len.p, ((size_t)B.n + 1) * 4, cudaMemcpyDeviceToDevice, s));
+    B.indices.alloc((size_t)std::max<int64_t>(1, B.nnz)), B.vals.alloc((size_t)std::max<int64_t>(1, B.nnz));
+    const bool with_pair = !blk && pair;
+    if (with_pair)
+      B.pair.alloc((size_t)B.n);
+    else
+      B.pair.release();
+    k_block_fill<<<cdiv((int64_t)B.n * 8, 256), 256, 0, s>>>(B.idx.p, B.n, h.MassC.indptr.p, h.MassC.indices.p,
+                                                            h.MassC.vals.p, rank.p, sp.is_z.p, B.indptr.p, B.indices.p,
+                                                            B.vals.p, pair, with_pair ? B.pair.p : nullptr, cross.p);
+  }
+  int hcross = 0;
+  cross.download(&hcross, 1, s);
+  FW_CHECK_CUDA(cudaStreamSynchronize(s));
+  FW_CHECK_CUDA(cudaGetLastError());
+  h.mass_split = hcross == 0;
+  h.tim.kernel_launches += 12;
+}
+
 // geometry-only operators of calculate_hfield on the structural pattern (always f64)
 void assemble_aux(Handle& h) {
   FW_REQUIRE(h.sp.valid && h.has_symbolic, "space/symbolic missing");
@@ -607,6 +707,7 @@ void assemble_aux(Handle& h) {
   } else {
     h.MassC.pair.release();
   }
+  build_mass_blocks(h);
   h.MassC.valid = true;
   h.tim.kernel_launches += 5;
 }

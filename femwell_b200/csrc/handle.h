@@ -67,6 +67,15 @@ struct Handle {
     int64_t nnz = 0;
     bool valid = false;
   } MassC, Bc;  // Bc: bform without the zero slots of the shared pattern (M x of the Arnoldi operator)
+  // the mass matrix is block diagonal (Nedelec | Lagrange): the two blocks are solved as separate PCG systems -- the
+  // Lagrange block converges in ~1/3 of the iterations of the Nedelec block
+  struct MassBlock {
+    DevBuf<int> idx, indptr, indices, pair;  // idx: block dof -> dof of the space
+    DevBuf<double> vals;
+    int n = 0;
+    int64_t nnz = 0;
+  } MassN, MassP;
+  bool mass_split = false;
   Connectivity generic;  // set by fw_eigs_csr instead of a space
   DevBuf<double> blocks;  // scratch: local element blocks (SoA [entry][Ne])
   // generic COO->CSR result

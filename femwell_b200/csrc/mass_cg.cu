@@ -231,15 +231,17 @@ __global__ void __launch_bounds__(256) k_cg_direction(int n, double2* __restrict
 
 // [k][n] <-> interleaved [n][K]
 template <int K>
-__global__ void k_cg_interleave(int n, const cplx* __restrict__ in, cplx* __restrict__ out, bool to_interleaved) {
+__global__ void k_cg_interleave(int n, const cplx* __restrict__ in, cplx* __restrict__ out, bool to_interleaved,
+                                const int* __restrict__ idx, int n_full) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const int64_t d = idx ? idx[i] : i;
 #pragma unroll
   for (int r = 0; r < K; ++r) {
     if (to_interleaved)
-      out[(size_t)i * K + r] = in[(size_t)r * n + i];
+      out[(size_t)i * K + r] = in[(size_t)r * n_full + d];
     else
-      out[(size_t)r * n + i] = in[(size_t)i * K + r];
+      out[(size_t)r * n_full + d] = in[(size_t)i * K + r];
   }
 }
 
@@ -248,6 +250,8 @@ struct CsrView {
   const double* vals;
   int64_t nnz;
   const int* pair;  // optional: partner dof of the 2 x 2 blocks of the block-Jacobi preconditioner (-1: none)
+  const int* idx;   // optional: row i of this system is dof idx[i] of the right-hand side / solution arrays
+  int n_full;       // leading dimension of those arrays
 };
 
 template <int K>
@@ -276,7 +280,7 @@ static void mass_solve_k(Handle& h, int n, const CsrView& M, const cplx* B, cplx
   k_cg_diag<<<g256, 256, 0, s>>>(n, M.indptr, M.indices, M.vals, idiag.p);
   k_cg_block_weights<<<g256, 256, 0, s>>>(n, M.indptr, M.indices, M.vals, idiag.p, M.pair, wself.p, wpart.p);
   FW_CHECK_CUDA(cudaMemsetAsync(xv, 0, vec * sizeof(double), s));
-  k_cg_interleave<K><<<g256, 256, 0, s>>>(n, B, rv, true);
+  k_cg_interleave<K><<<g256, 256, 0, s>>>(n, B, rv, true, M.idx, M.n_full);
   k_cg_step<K, true><<<nblk, 256, 0, s>>>(n, (double2*)xv, (const double2*)rv, nullptr, (const double2*)pv,
                                           (const double2*)qv, (double2*)zv, wself.p, wpart.p, M.pair, nullptr, nullptr,
                                           part_rr, part_rz, nblk);
@@ -310,7 +314,7 @@ static void mass_solve_k(Handle& h, int n, const CsrView& M, const cplx* B, cplx
     }
   }
   tr.mark("    mass PCG: iterations");
-  k_cg_interleave<K><<<g256, 256, 0, s>>>(n, xv, X, false);
+  k_cg_interleave<K><<<g256, 256, 0, s>>>(n, xv, X, false, M.idx, M.n_full);
   ++launches;
   FW_CHECK_CUDA(cudaGetLastError());
   h.tim.kernel_launches += launches;
@@ -320,17 +324,31 @@ static void mass_solve_k(Handle& h, int n, const CsrView& M, const cplx* B, cplx
 }
 
 // M X = B for a real SPD CSR matrix and k <= CG_MAXK complex right-hand sides ([k][n] each); X overwritten.
+static void pcg_solve_view(Handle& h, int n_rows, const CsrView& V, int k, const cplx* B, cplx* X);
+
 void mass_solve_multi(Handle& h, int k, const cplx* B, cplx* X) {
   FW_REQUIRE(h.Mass.valid && h.MassC.valid, "mass matrix missing");
+  if (h.mass_split) {
+    // Nedelec and Lagrange blocks as two independent systems (every dof belongs to exactly one of them)
+    for (const Handle::MassBlock* b : {&h.MassN, &h.MassP}) {
+      const CsrView V{b->indptr.p, b->indices.p, b->vals.p, b->nnz, b->pair.n ? b->pair.p : nullptr, b->idx.p, h.sp.n};
+      pcg_solve_view(h, b->n, V, k, B, X);
+    }
+    return;
+  }
   pcg_solve_multi(h, h.sp.n, h.MassC.indptr.p, h.MassC.indices.p, h.MassC.vals.p, h.MassC.nnz, k, B, X,
                   h.MassC.pair.n ? h.MassC.pair.p : nullptr);
 }
 
 void pcg_solve_multi(Handle& h, int n_rows, const int* indptr, const int* indices, const double* vals, int64_t nnz,
                      int k, const cplx* B, cplx* X, const int* pair) {
+  const CsrView V{indptr, indices, vals, nnz, pair, nullptr, n_rows};
+  pcg_solve_view(h, n_rows, V, k, B, X);
+}
+
+static void pcg_solve_view(Handle& h, int n_rows, const CsrView& V, int k, const cplx* B, cplx* X) {
   FW_REQUIRE(k >= 1 && k <= CG_MAXK, "pcg_solve_multi: 1 <= k <= 8");
-  const size_t n = (size_t)n_rows;
-  const CsrView V{indptr, indices, vals, nnz, pair};
+  const size_t n = (size_t)V.n_full;  // stride between the systems in B and X
   // systems are solved in groups of 4 / 2 / 1 (compile-time interleave factor)
   int done = 0;
   while (done < k) {
