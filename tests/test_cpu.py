@@ -306,3 +306,45 @@ def test_msh_round_trip_keeps_mesh_and_groups(tmp_path):
     assert np.array_equal(r.subdomains["core"], m.subdomains["core"])
     for k in ("left", "top"):
         assert np.array_equal(np.sort(r.boundaries[k]), np.sort(m.boundaries[k]))
+
+
+def test_read_msh_entity_with_two_physical_groups(tmp_path):
+    """gmsh 4.1: an entity may carry several physical tags; every one of them becomes a sub-domain."""
+    from femwell_b200.msh import read_msh
+
+    src = open(os.path.join(ROOT, "tests", "golden", "square_v41.msh")).read()
+    src = src.replace('4\n1 20 "bottom"', '5\n2 12 "everything"\n1 20 "bottom"')
+    src = src.replace("1 0 0 0 1 1 0 1 10 3 1 2 3", "1 0 0 0 1 1 0 2 10 12 3 1 2 3")
+    src = src.replace("2 0 0 0 1 1 0 1 11 3 3 4 1", "2 0 0 0 1 1 0 2 11 12 3 3 4 1")
+    path = tmp_path / "two_groups.msh"
+    path.write_text(src)
+    m = read_msh(str(path))
+    assert m.subdomains["everything"].tolist() == [0, 1]
+    assert m.subdomains["core"].tolist() == [0] and m.subdomains["clad"].tolist() == [1]
+
+
+def test_basis_dof_counts_of_projection_spaces():
+    from femwell_b200.element import ElementDG, ElementTriP1, ElementTriP2, ElementVector
+
+    m, _ = strip_problem(4)
+    b = Basis(m, ElementTriP0(), intorder=4)
+    ne = m.nelements
+    assert b.N == ne
+    assert b.with_element(ElementDG(ElementTriP1())).N == 3 * ne
+    assert b.with_element(ElementDG(ElementTriP2())).N == 6 * ne
+    assert b.with_element(ElementVector(ElementDG(ElementTriP2()), 3)).N == 18 * ne
+    assert b.with_element(ElementVector(ElementTriP0(), 3)).N == 3 * ne
+
+
+def test_overlap_dispatch_same_basis_vs_cross_mesh():
+    """calculate_overlap takes the one-mesh Functional only for the same mesh, element and quadrature
+    (waveguide.py:729-731); anything else goes to the cross-mesh branch."""
+    from femwell_b200.maxwell.waveguide import _same_quadrature_space
+
+    m1, _ = strip_problem(4)
+    m2, _ = strip_problem(4)
+    b1 = Basis(m1, ElementTriP0(), intorder=4).with_element(mode_element(2))
+    assert _same_quadrature_space(b1, b1.with_element(mode_element(2)))
+    assert not _same_quadrature_space(b1, Basis(m2, ElementTriP0(), intorder=4).with_element(mode_element(2)))
+    assert not _same_quadrature_space(b1, Basis(m1, ElementTriP0(), intorder=2).with_element(mode_element(2)))
+    assert not _same_quadrature_space(b1, b1.with_element(mode_element(1)))
