@@ -62,6 +62,8 @@ class FwTimings(C.Structure):
         ("lu_symbolic_ms", c_f64), ("lu_factor_ms", c_f64), ("arnoldi_ms", c_f64), ("postprocess_ms", c_f64),
         ("total_ms", c_f64), ("download_ms", c_f64), ("element_kernel_launches", c_i64),
         ("kernel_launches", c_i64), ("nnz_structural", c_i64),
+        ("lu_solve_entries", c_i64), ("lu_factor_flops", c_f64), ("pcg_iterations", c_i64),
+        ("pcg_rel_residual", c_f64), ("hfield_ms", c_f64),
     ]
 
     def as_dict(self):
@@ -74,12 +76,40 @@ class FemwellB200Error(RuntimeError):
         self.code = code
 
 
+try:  # the reference's callers catch scipy's class (scipy/sparse/linalg/_eigen/arpack/arpack.py:303-329)
+    from scipy.sparse.linalg import ArpackNoConvergence as _ArpackNoConvergence
+except Exception:  # pragma: no cover - scipy is a hard dependency of the reference
+    _ArpackNoConvergence = RuntimeError
+
+
+class B200NoConvergence(FemwellB200Error, _ArpackNoConvergence):
+    """FW_ERR_NOCONV.  Compatible with ``scipy.sparse.linalg.ArpackNoConvergence``: ``eigenvalues`` and
+    ``eigenvectors`` hold the pairs that did converge (shapes ``(nconv,)`` and ``(N, nconv)``)."""
+
+    def __init__(self, code, msg, eigenvalues=None, eigenvectors=None):
+        RuntimeError.__init__(self, f"ARPACK error -1: {msg}" if not msg.startswith("ARPACK") else msg)
+        self.code = code
+        self.eigenvalues = np.zeros(0, dtype=np.complex128) if eigenvalues is None else eigenvalues
+        self.eigenvectors = np.zeros((0, 0), dtype=np.complex128) if eigenvectors is None else eigenvectors
+
+
+class B200SingularError(FemwellB200Error):
+    """FW_ERR_SINGULAR: a ``RuntimeError`` with the message of scipy's ``splu`` (SuperLU) for this case."""
+
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "Factor is exactly singular")
+        self.code = code
+
+
+ERR_NOCONV, ERR_SINGULAR = -3, -4
+
+
 # every symbol include/femwell_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "fw_last_error", "fw_version", "fw_create", "fw_destroy", "fw_synchronize", "fw_set_option", "fw_set_space", "fw_analysis_hint",
+    "fw_last_error", "fw_version", "fw_create", "fw_destroy", "fw_synchronize", "fw_set_option", "fw_set_space", "fw_set_element_subset", "fw_analysis_hint",
     "fw_symbolic", "fw_assemble_waveguide", "fw_matrix_nnz", "fw_matrix_export", "fw_coo_to_csr",
-    "fw_coo_to_csr_export", "fw_matrix_spmv", "fw_eigs", "fw_eigs_csr", "fw_lu_factor_shifted", "fw_lu_solve",
-    "fw_postprocess_modes", "fw_hfield", "fw_functional", "fw_intensity", "fw_poynting", "fw_overlap_cross", "fw_energy_current_density", "fw_compute_modes", "fw_get_timings",
+    "fw_coo_to_csr_export", "fw_matrix_spmv", "fw_bench_spmv", "fw_eigs", "fw_eigs_csr", "fw_lu_factor_shifted", "fw_lu_solve",
+    "fw_postprocess_modes", "fw_hfield", "fw_functional", "fw_error_estimator", "fw_intensity", "fw_poynting", "fw_overlap_cross", "fw_energy_current_density", "fw_compute_modes", "fw_get_timings",
     "fw_host_dense_eig", "fw_debug_lu_symbolic", "fw_debug_lu_symbolic_get", "fw_debug_lu_get",
 ]
 
@@ -106,9 +136,18 @@ def load():
     return _lib
 
 
-def check(code):
-    if code != 0:
-        raise FemwellB200Error(code, load().fw_last_error().decode())
+def check(code, partial=None):
+    """Raise for a non-zero status.  ``partial() -> (eigenvalues, eigenvectors)`` supplies the converged pairs that
+    a FW_ERR_NOCONV call has already written to the caller's buffers."""
+    if code == 0:
+        return
+    msg = load().fw_last_error().decode()
+    if code == ERR_NOCONV:
+        lam, vec = partial() if partial is not None else (None, None)
+        raise B200NoConvergence(code, msg, lam, vec)
+    if code == ERR_SINGULAR:
+        raise B200SingularError(code, msg)
+    raise FemwellB200Error(code, msg)
 
 
 def ptr(a):

@@ -52,6 +52,11 @@ class Basis:
             self.X, self.W = triangle_quadrature(2 * elem.maxdeg if intorder is None else intorder)
         self.tind = None if elements is None else mesh.normalize_elements(elements)
         self._dofs = None
+        # optional reference tables of a foreign local basis (scikit-fem's ``elem.lbasis``, femwell_b200.bridge);
+        # None: the built-in hierarchical basis of femwell_b200.element
+        self._tables = None
+        self._n_dofs = None
+        self._fw_device = None  # GPU the basis was solved on (set by compute_modes; follows derived bases)
 
     # -- scikit-fem compatible helpers ------------------------------------------------
     @property
@@ -62,6 +67,7 @@ class Basis:
         """Same mesh, quadrature and element subset, other element."""
         b = Basis(self.mesh, elem, quadrature=(self.X, self.W))
         b.tind = self.tind
+        b._fw_device = self._fw_device
         return b
 
     def with_elements(self, elements) -> "Basis":
@@ -69,7 +75,38 @@ class Basis:
         b.tind = self.mesh.normalize_elements(elements)
         if self._dofs is not None:
             b._dofs = self._dofs
+        b._tables, b._n_dofs, b._fw_device = self._tables, self._n_dofs, self._fw_device
         return b
+
+    def with_tables(self, kind, vec, sc, element_dofs=None, n_dofs=None) -> "Basis":
+        """The same mode basis with a foreign local basis: reference tables ``(kind, vec, sc)`` at this basis'
+        quadrature points (layout of femwell_b200.element.ElementTables) and, optionally, the owner's own
+        ``element_dofs`` / dof count.  All kernels are table driven, so dof vectors then refer to that basis."""
+        from .element import ElementTables, local_layout
+
+        if not self.is_mode_basis:
+            raise ValueError("with_tables needs the mixed Nedelec x Lagrange basis")
+        lk, sub = local_layout(self.elem.order)
+        kind = np.ascontiguousarray(kind, dtype=np.int32)
+        if not np.array_equal(kind, lk):
+            raise ValueError("local dof layout must be entity-major: vertex, facet, interior (SURVEY.md A.3)")
+        b = Basis(self.mesh, self.elem, quadrature=(self.X, self.W))
+        b.tind = self.tind
+        b._fw_device = self._fw_device
+        b._tables = ElementTables(self.elem.order, kind.size, self.X.shape[1], kind,
+                                  np.ascontiguousarray(vec, dtype=np.float64), np.ascontiguousarray(sc, dtype=np.float64),
+                                  self.X, self.W, sub)
+        if element_dofs is not None:
+            b._dofs = np.ascontiguousarray(element_dofs, dtype=np.int32)
+            b._n_dofs = int(n_dofs) if n_dofs is not None else int(b._dofs.max()) + 1
+        return b
+
+    @property
+    def tables_id(self):
+        """hashable identity of the reference tables (None: built-in)"""
+        if self._tables is None:
+            return None
+        return (self._tables.vec.tobytes(), self._tables.sc.tobytes())
 
     def __eq__(self, other):
         return (
@@ -95,6 +132,8 @@ class Basis:
     @property
     def N(self) -> int:
         m = self.mesh
+        if self._n_dofs is not None:
+            return self._n_dofs
         if self.is_mode_basis:
             if self.elem.order == 1:
                 return m.nvertices + m.nfacets
@@ -170,7 +209,28 @@ class Basis:
 
     # -- convenience (host, numpy) ---------------------------------------------------------
     def tables(self):
+        if self._tables is not None:
+            return self._tables
         return element_tables(self.elem.order, self.X, self.W)
+
+    def facet_tables(self):
+        """Gauss-Legendre rule on [0, 1] of degree 2 * maxdeg (scikit-fem's default for an InteriorFacetBasis of this
+        element, waveguide.py:475) and the reference vectors of every local basis function at its points on the three
+        local edges (0,1) (1,2) (0,2): ``(s [nqf], w [nqf], vec [nb, 3, 2, nqf])``."""
+        if self._tables is not None and getattr(self, "_facet_vec", None) is None:
+            raise NotImplementedError("a foreign local basis needs its own facet tables (Basis._facet_vec)")
+        npts = int(np.ceil((2 * self.elem.maxdeg + 1) / 2))
+        x, w = np.polynomial.legendre.leggauss(npts)
+        s, w = 0.5 * (x + 1.0), 0.5 * w
+        if self._tables is not None:
+            return s, w, np.ascontiguousarray(self._facet_vec, dtype=np.float64)
+        ends = [((0.0, 0.0), (1.0, 0.0)), ((1.0, 0.0), (0.0, 1.0)), ((0.0, 0.0), (0.0, 1.0))]
+        nb = self.tables().nbfun
+        vec = np.zeros((nb, 3, 2, npts))
+        for k, (a, b) in enumerate(ends):
+            Xk = np.stack([a[0] + s * (b[0] - a[0]), a[1] + s * (b[1] - a[1])])
+            vec[:, k] = element_tables(self.elem.order, Xk, w).vec
+        return np.ascontiguousarray(s), np.ascontiguousarray(w), np.ascontiguousarray(vec)
 
     def interpolate(self, x: np.ndarray):
         """Host-side evaluation at the quadrature points (not on the hot path).

@@ -26,6 +26,7 @@ class Context:
         self.device = device
         self.basis: Optional[Basis] = None
         self._space_key = None
+        self._subset_key = None
         self.n = 0
         self.nnz_structural = None
 
@@ -70,11 +71,47 @@ class Context:
         self.basis = basis
         self.n = basis.N
         self.nnz_structural = None
-        self._space_key = (id(m), basis.elem.order, tb.X.tobytes(), tb.W.tobytes())
+        self._space_key = self._key_of(basis)
+        self._subset_key = None
+        self.set_element_subset(basis.tind)
+
+    @staticmethod
+    def _key_of(basis: Basis):
+        tb = basis.tables()
+        return (id(basis.mesh), basis.elem.order, tb.X.tobytes(), tb.W.tobytes(), basis.tables_id)
+
+    def set_element_subset(self, tind):
+        """Restrict the forms to the elements of the basis (scikit-fem ``CellBasis.tind``, waveguide.py:574);
+        ``None`` or all elements: no restriction."""
+        ne = self.basis.mesh.nelements
+        if tind is not None:
+            tind = L.as_i32(np.unique(np.asarray(tind)))
+            if tind.size == ne:
+                tind = None
+        key = None if tind is None else tind.tobytes()
+        if key == self._subset_key:
+            return
+        L.check(self.lib.fw_set_element_subset(self._h, -1 if tind is None else tind.size, L.ptr(tind)))
+        self._subset_key = key
+
+    def set_option(self, option: int, value: int):
+        L.check(self.lib.fw_set_option(self._h, int(option), int(value)))
+
+    def bench_spmv(self, which: int = MAT_A, x_is_complex: bool = False, reps: int = 20) -> float:
+        """ms per device-resident y = M x (measurement only)."""
+        ms = C.c_double()
+        L.check(self.lib.fw_bench_spmv(self._h, which, int(x_is_complex), reps, C.byref(ms)))
+        return ms.value
+
+    def matrix_nnz(self, which: int, eliminate_zeros: bool = True) -> int:
+        L.check(self.lib.fw_set_option(self._h, 0, int(eliminate_zeros)))
+        nnz, cx = C.c_int64(), C.c_int32()
+        L.check(self.lib.fw_matrix_nnz(self._h, which, C.byref(nnz), C.byref(cx)))
+        return nnz.value
 
     def same_space(self, basis: Basis) -> bool:
-        tb_x, tb_w = basis.X, basis.W
-        return self._space_key == (id(basis.mesh), basis.elem.order, tb_x.tobytes(), tb_w.tobytes())
+        """Same mesh, order, quadrature and reference tables (the element subset is handled separately)."""
+        return self._space_key is not None and self._space_key == self._key_of(basis)
 
     def symbolic(self) -> int:
         nnz = C.c_int64()
@@ -164,7 +201,8 @@ class Context:
         lams = np.empty(k, dtype=np.complex128)
         X = np.empty((k, self.n), dtype=np.complex128)
         st = L.FwEigsStats()
-        L.check(self.lib.fw_eigs(self._h, C.byref(p), L.ptr(lams), L.ptr(X), C.byref(st)))
+        L.check(self.lib.fw_eigs(self._h, C.byref(p), L.ptr(lams), L.ptr(X), C.byref(st)),
+                partial=lambda: (lams[:st.nconv].copy(), X[:st.nconv].T.copy()))
         return lams, X, st.as_dict()
 
     def eigs_csr(self, K, M, k, sigma, coords=None, v0=None, ncv=0, tol=0.0, maxiter=0, refine=0, leaf_elements=0):
@@ -186,7 +224,8 @@ class Context:
         X = np.empty((k, n), dtype=np.complex128)
         st = L.FwEigsStats()
         L.check(self.lib.fw_eigs_csr(self._h, n, L.ptr(kp), L.ptr(ki), L.ptr(kd), L.ptr(mp), L.ptr(mi), L.ptr(md),
-                                     int(cx), L.ptr(co), C.byref(p), L.ptr(lams), L.ptr(X), C.byref(st)))
+                                     int(cx), L.ptr(co), C.byref(p), L.ptr(lams), L.ptr(X), C.byref(st)),
+                partial=lambda: (lams[:st.nconv].copy(), X[:st.nconv].T.copy()))
         return lams, X, st.as_dict()
 
     # ---------------------------------------------------------------- post-processing
@@ -238,6 +277,21 @@ class Context:
         L.check(self.lib.fw_energy_current_density(self._h, L.ptr(xs), L.ptr(out)))
         return out
 
+    def error_estimator(self, E, eps_kind, epsilon_r):
+        """eta_E [Ne] of Mode.eval_error_estimator (waveguide.py:473-502) for the current space."""
+        b = self.basis
+        m = b.mesh
+        E = L.as_c128(E)
+        cx = np.iscomplexobj(epsilon_r)
+        eps = L.as_c128(epsilon_r) if cx else L.as_f64(epsilon_r)
+        s, w, vec = b.facet_tables()
+        t2f, f2t = L.as_i32(m.t2f), L.as_i32(m.f2t)
+        out = np.empty(m.nelements, dtype=np.float64)
+        L.check(self.lib.fw_error_estimator(self._h, L.ptr(E), int(eps_kind), int(cx), L.ptr(eps), m.nfacets,
+                                            L.ptr(t2f), L.ptr(f2t), s.size, L.ptr(s), L.ptr(w), L.ptr(vec),
+                                            L.ptr(out)))
+        return out
+
     def functional(self, kind, fields, aux=None, aux_kind=0, elements=None, option=0):
         fs = [None if f is None else L.as_c128(f) for f in fields] + [None] * (4 - len(fields))
         a = None
@@ -268,7 +322,8 @@ class Context:
         powers = np.empty(k, dtype=np.complex128)
         st = L.FwEigsStats()
         L.check(self.lib.fw_compute_modes(self._h, C.byref(p), L.ptr(lams), L.ptr(E), L.ptr(H), L.ptr(powers),
-                                          C.byref(st)))
+                                          C.byref(st)),
+                partial=lambda: (lams[:st.nconv].copy(), E[:st.nconv].T.copy()))
         return lams, E, H, powers, st.as_dict()
 
     def timings(self) -> dict:

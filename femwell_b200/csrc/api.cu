@@ -174,14 +174,25 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
   current_pool() = &h.pool;
+  Space& sp = h.sp;
+  h.lu_prefetch.reset();  // joins a pending analysis before the host arrays change
+  // whatever happens below, the handle no longer holds the previous space: a failed call must leave it in the
+  // "no space" state (host sizes, device buffers and the CSR pattern would otherwise disagree), and a one-shot
+  // analysis hint must not leak to an unrelated mesh
+  const bool hinted = h.hint_valid;
+  h.hint_valid = false;
+  sp.valid = false;
+  sp.has_emask = false;
+  h.generic.valid = false;
+  h.has_symbolic = false;
+  h.A.valid = h.B.valid = h.Mass.valid = h.C0.valid = h.C1.valid = h.MassC.valid = h.Bc.valid = false;
+  h.lu.reset();
   FW_REQUIRE(s->order == 1 || s->order == 2, "Only order 1 and 2 implemented by now.");
   const int nb = s->order == 1 ? 6 : 14;
   FW_REQUIRE(s->nbfun == nb, "nbfun does not match order");
   FW_REQUIRE(s->nqp >= 1 && s->nqp <= MAXQ, "nqp out of range (1..12)");
   FW_REQUIRE(s->n_vertices > 0 && s->n_elements > 0 && s->n_dofs > 0, "empty mesh");
   FW_REQUIRE(s->p && s->t && s->element_dofs && s->kind && s->vec && s->sc && s->X && s->W, "NULL array");
-  Space& sp = h.sp;
-  h.lu_prefetch.reset();  // joins a pending analysis before the host arrays change
   Timer tu(h.stream);
   sp.order = s->order;
   sp.nv = s->n_vertices;
@@ -240,11 +251,9 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
     FW_REQUIRE(!(b & 1), "t out of range");
     FW_REQUIRE(!(b & 2), "element_dofs out of range");
   }
-  h.lu.reset();
-  if (h.hint_valid) {
+  if (hinted) {
     // the caller announced the solve that follows (fw_analysis_hint): the host analysis of its sparse LU starts now and
     // overlaps the uploads below and everything up to the factorisation
-    h.hint_valid = false;
     std::vector<uint8_t> active((size_t)sp.n, 1);
     for (int d : h.hint_dirichlet) {
       FW_REQUIRE(d >= 0 && d < sp.n, "dirichlet dof out of range");
@@ -272,6 +281,32 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
   FW_API_END
 }
 
+int fw_set_element_subset(fw_handle* hh, int32_t n_sel, const int32_t* elements) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh, "handle is NULL");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
+  Space& sp = h.sp;
+  FW_REQUIRE(sp.valid, "fw_set_space must be called first");
+  // the assembled operators no longer match the basis
+  h.A.valid = h.B.valid = h.Mass.valid = h.C0.valid = h.C1.valid = h.MassC.valid = h.Bc.valid = false;
+  if (n_sel < 0 || !elements) {
+    sp.has_emask = false;
+    sp.emask.release();
+    return FW_OK;
+  }
+  std::vector<uint8_t> m((size_t)sp.ne, 0);
+  for (int i = 0; i < n_sel; ++i) {
+    FW_REQUIRE(elements[i] >= 0 && elements[i] < sp.ne, "element index out of range");
+    m[elements[i]] = 1;
+  }
+  sp.emask.upload(m.data(), m.size(), h.stream);
+  FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
+  sp.has_emask = true;
+  FW_API_END
+}
+
 int fw_analysis_hint(fw_handle* hh, int32_t n_dirichlet, const int32_t* dirichlet, int32_t leaf_elements) {
   FW_API_BEGIN
   FW_REQUIRE(hh && (n_dirichlet == 0 || dirichlet), "NULL argument");
@@ -289,6 +324,11 @@ int fw_set_option(fw_handle* hh, int32_t option, int32_t value) {
     case FW_OPT_ELIMINATE_ZEROS:
       hh->h.eliminate_zeros = value != 0;
       break;
+    case FW_OPT_PCG_TOL_EXP:
+      FW_REQUIRE(value >= 1 && value <= 15, "PCG tolerance exponent out of range (1..15)");
+      hh->h.pcg_tol = std::pow(10.0, -(double)value);
+      break;
+
     default:
       throw Error(FW_ERR_INVALID, "unknown option");
   }
@@ -407,6 +447,41 @@ int fw_matrix_spmv(fw_handle* hh, int32_t which, int32_t x_is_complex, const voi
   FW_API_END
 }
 
+int fw_bench_spmv(fw_handle* hh, int32_t which, int32_t x_is_complex, int32_t reps, double* ms_per_apply) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && ms_per_apply && reps >= 1, "bad argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
+  if (which >= FW_MAT_MASS) assemble_aux(h);
+  Values& v = pick(h, which);
+  FW_REQUIRE(v.valid, "matrix has not been assembled");
+  const int n = h.sp.n;
+  cudaStream_t s = h.stream;
+  const bool cx = v.is_complex || x_is_complex;
+  DevBuf<double> dx, dy;
+  dx.alloc((size_t)n * (cx ? 2 : 1));
+  dy.alloc((size_t)n * (cx ? 2 : 1));
+  std::vector<double> x0((size_t)n * (cx ? 2 : 1));
+  for (size_t i = 0; i < x0.size(); ++i) x0[i] = 1.0 / (1.0 + (double)(i % 97));
+  dx.upload(x0.data(), x0.size(), s);
+  auto once = [&] {
+    if (!cx)
+      spmv<double, double>(n, h.pat.indptr.p, h.pat.indices.p, v.v.p, dx.p, dy.p, s);
+    else if (!v.is_complex)
+      spmv<double, cplx>(n, h.pat.indptr.p, h.pat.indices.p, v.v.p, (const cplx*)dx.p, (cplx*)dy.p, s);
+    else
+      spmv<cplx, cplx>(n, h.pat.indptr.p, h.pat.indices.p, (const cplx*)v.v.p, (const cplx*)dx.p, (cplx*)dy.p, s);
+  };
+  for (int i = 0; i < 3; ++i) once();
+  FW_CHECK_CUDA(cudaStreamSynchronize(s));
+  Timer t(s);
+  for (int i = 0; i < reps; ++i) once();
+  *ms_per_apply = t.stop() / reps;
+  FW_CHECK_CUDA(cudaGetLastError());
+  FW_API_END
+}
+
 int fw_eigs(fw_handle* hh, const fw_eigs_params* prm, double* lams, double* X, fw_eigs_stats* st) {
   FW_API_BEGIN
   FW_REQUIRE(hh && prm && lams && X, "NULL argument");
@@ -414,9 +489,11 @@ int fw_eigs(fw_handle* hh, const fw_eigs_params* prm, double* lams, double* X, f
   FW_CHECK_CUDA(cudaSetDevice(h.device));
   current_pool() = &h.pool;
   DevBuf<double> Xd;
-  eigs_shift_invert(h, *prm, (std::complex<double>*)lams, Xd, st);
+  std::string why;
+  const bool ok = eigs_shift_invert(h, *prm, (std::complex<double>*)lams, Xd, st, &why);
   Xd.download(X, (size_t)prm->k * h.sp.n * 2, h.stream);
   FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
+  if (!ok) throw Error(FW_ERR_NOCONV, why);  // the converged pairs (st->nconv) have been handed over
   FW_API_END
 }
 
@@ -435,9 +512,11 @@ int fw_eigs_csr(fw_handle* hh, int32_t n, const int32_t* K_indptr, const int32_t
     h.tim.upload_ms = t.stop();
   }
   DevBuf<double> Xd;
-  eigs_shift_invert(h, *prm, (std::complex<double>*)lams, Xd, st);
+  std::string why;
+  const bool ok = eigs_shift_invert(h, *prm, (std::complex<double>*)lams, Xd, st, &why);
   Xd.download(X, (size_t)prm->k * n * 2, h.stream);
   FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
+  if (!ok) throw Error(FW_ERR_NOCONV, why);
   FW_API_END
 }
 
@@ -641,6 +720,35 @@ int fw_energy_current_density(fw_handle* hh, const double* xs, double* out) {
   FW_API_END
 }
 
+int fw_error_estimator(fw_handle* hh, const double* E, int32_t eps_kind, int32_t eps_is_complex, const void* eps,
+                       int32_t n_facets, const int32_t* t2f, const int32_t* f2t, int32_t nqf, const double* sq,
+                       const double* wq, const double* facet_vec, double* out) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && E && eps && t2f && f2t && sq && wq && facet_vec && out, "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
+  const Space& sp = h.sp;
+  FW_REQUIRE(sp.valid, "space missing");
+  FW_REQUIRE(n_facets > 0, "no facets");
+  for (size_t i = 0; i < (size_t)3 * sp.ne; ++i) FW_REQUIRE(t2f[i] >= 0 && t2f[i] < n_facets, "t2f out of range");
+  for (size_t i = 0; i < (size_t)2 * n_facets; ++i) FW_REQUIRE(f2t[i] >= -1 && f2t[i] < sp.ne, "f2t out of range");
+  cudaStream_t s = h.stream;
+  DevBuf<double> dE, deps, dout;
+  DevBuf<int> dt2f, df2t;
+  dE.upload(E, (size_t)sp.n * 2, s);
+  const size_t neps = (eps_kind == FW_EPS_P0 ? (size_t)sp.ne : (size_t)3 * sp.ne) * (eps_is_complex ? 2 : 1);
+  deps.upload((const double*)eps, neps, s);
+  dt2f.upload(t2f, (size_t)3 * sp.ne, s);
+  df2t.upload(f2t, (size_t)2 * n_facets, s);
+  dout.alloc((size_t)sp.ne);
+  error_estimator_dev(h, (const cplx*)dE.p, eps_kind, eps_is_complex != 0, deps.p, n_facets, dt2f.p, df2t.p, nqf, sq, wq,
+                      facet_vec, dout.p);
+  dout.download(out, (size_t)sp.ne, s);
+  FW_CHECK_CUDA(cudaStreamSynchronize(s));
+  FW_API_END
+}
+
 int fw_functional(fw_handle* hh, int32_t kind, const double* f0, const double* f1, const double* f2,
                   const double* f3, int32_t aux_kind, int32_t aux_is_complex, const void* aux, int32_t n_sel,
                   const int32_t* elements, int32_t option, double* out) {
@@ -722,9 +830,17 @@ int fw_compute_modes(fw_handle* hh, const fw_modes_params* prm, double* lams, do
   // geometry-only operators of the H-field recovery: assembled now, while the host analysis of the LU is still running
   assemble_aux(h);
   DevBuf<double> Xd, Hd;
-  eigs_shift_invert(h, prm->eigs, (std::complex<double>*)lams, Xd, st);
+  std::string why;
+  const bool ok = eigs_shift_invert(h, prm->eigs, (std::complex<double>*)lams, Xd, st, &why);
   const int k = prm->eigs.k;
   const size_t cnt = (size_t)k * h.sp.n * 2;
+  if (!ok) {
+    // no convergence: the raw (not un-scaled, unit 2-norm) converged eigenvectors go to E[0:nconv], like the
+    // eigenvectors attribute of scipy's ArpackNoConvergence
+    Xd.download(E, cnt, s);
+    FW_CHECK_CUDA(cudaStreamSynchronize(s));
+    throw Error(FW_ERR_NOCONV, why);
+  }
   Hd.alloc(cnt);
   {
     Timer t(s);

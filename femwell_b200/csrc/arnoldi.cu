@@ -611,33 +611,53 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
     fprintf(stderr, "[fw-trace] arnoldi host wall: op %.1f ms  cgs2 %.1f ms  ritz %.1f ms  restart %.1f ms\n", tw_op,
             tw_cgs, tw_ritz, tw_restart);
 
-  // ---- extract the k wanted Ritz pairs
+  // ---- extract the k wanted Ritz pairs.  Without convergence only the converged ones among them are returned
+  // (first st->nconv entries of lams / rows of X): scipy's ArpackNoConvergence carries exactly those
+  // (arpack.py:303-329); the caller turns st->nconv < k into FW_ERR_NOCONV after the stats are complete.
   const int me = m_eff;
   const int kk = std::min(k, me);
-  if (nconv < kk || kk < k) {
-    if (st) {
-      st->nconv = nconv;
-      st->iterations = iterations;
-      st->restarts = restarts;
-      st->n_op = n_op;
-    }
-    throw Error(FW_ERR_NOCONV, "ARPACK-style error: no convergence (" + std::to_string(nconv) + "/" +
-                                   std::to_string(k) + " eigenvalues converged after " + std::to_string(restarts) +
-                                   " restarts)");
-  }
-  std::vector<cplx> Yh((size_t)me * k);
-  double maxres = 0;
-  for (int i = 0; i < k; ++i) {
+  const bool noconv = nconv < kk || kk < k;
+  std::vector<int> sel;
+  for (int i = 0; i < kk; ++i) {
     const int o = order[i];
-    lams[i] = sigma + 1.0 / theta[o];
-    maxres = std::max(maxres, resid[o] / std::abs(theta[o]));
-    for (int l = 0; l < me; ++l) Yh[(size_t)i * me + l] = cplx{Y[(size_t)o * me + l].real(), Y[(size_t)o * me + l].imag()};
+    if (!noconv || resid[o] <= tol * std::max(3.666852862501036e-11, std::abs(theta[o]))) sel.push_back(o);
   }
-  W.Yd.upload((const double*)Yh.data(), Yh.size() * 2, s);
+  const int kout = (int)sel.size();
+  for (int i = 0; i < k; ++i) lams[i] = cd(0.0, 0.0);
   X_dev.alloc((size_t)k * n * 2);
-  k_ritz_vectors<T><<<cdiv(n, 128), 128, 0, s>>>(Vb, ld, n, me, k, (const cplx*)W.Yd.p, (cplx*)X_dev.p);
-  h.tim.kernel_launches += 1;
-  for (int i = 0; i < k; ++i) {
+  if (kout < k) X_dev.zero(s, (size_t)k * n * 2);
+  std::vector<cplx> Yh((size_t)me * std::max(1, kout));
+  double maxres = 0;
+  for (int i = 0; i < kout; ++i) {
+    const int o = sel[i];
+    // (ARPACK's real driver returns exactly real values for real Ritz values, scipy arpack.py:898-915; the complex QR
+    // used on the projected matrix here leaves an imaginary part of a few ulp)
+    const bool real_ritz = !scalar_traits<T>::is_complex && std::abs(theta[o].imag()) <= 1e-12 * std::abs(theta[o]);
+    lams[i] = sigma + 1.0 / (real_ritz ? cd(theta[o].real(), 0.0) : theta[o]);
+    maxres = std::max(maxres, resid[o] / std::abs(theta[o]));
+    // real arithmetic and a real Ritz value: the eigenvector of the real projected matrix is real up to a phase.
+    // Remove the phase, so that the returned eigenvector is exactly real (the H-field recovery then solves real
+    // mass systems, mass_cg.cu)
+    cd ph(1.0, 0.0);
+    const bool make_real = real_ritz;
+    if (make_real) {
+      int big = 0;
+      for (int l = 1; l < me; ++l)
+        if (std::abs(Y[(size_t)o * me + l]) > std::abs(Y[(size_t)o * me + big])) big = l;
+      const cd yb = Y[(size_t)o * me + big];
+      if (std::abs(yb) > 0) ph = std::conj(yb) / std::abs(yb);
+    }
+    for (int l = 0; l < me; ++l) {
+      const cd y = Y[(size_t)o * me + l] * ph;
+      Yh[(size_t)i * me + l] = cplx{y.real(), make_real ? 0.0 : y.imag()};
+    }
+  }
+  if (kout > 0) {
+    W.Yd.upload((const double*)Yh.data(), (size_t)me * kout * 2, s);
+    k_ritz_vectors<T><<<cdiv(n, 128), 128, 0, s>>>(Vb, ld, n, me, kout, (const cplx*)W.Yd.p, (cplx*)X_dev.p);
+    h.tim.kernel_launches += 1;
+  }
+  for (int i = 0; i < kout; ++i) {
     cplx* xi = (cplx*)X_dev.p + (int64_t)i * n;
     double nv = dev_norm<cplx>(h, xi, n, W);
     if (nv > 0) k_scale_copy<cplx><<<cdiv(n, 256), 256, 0, s>>>(xi, xi, n, 1.0 / nv);
@@ -648,18 +668,19 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
     rbuf.alloc((size_t)2 * n);
     cplx* rv = (cplx*)rbuf.p;
     maxres = 0;
-    for (int i = 0; i < k; ++i) {
+    for (int i = 0; i < kout; ++i) {
       const cplx* xi = (const cplx*)X_dev.p + (int64_t)i * n;
       op_apply_impl<V, cplx>(h, act.p, cplx{-1.0, 0.0}, cplx{0.0, 0.0}, true, xi, rv);
       const double kx = dev_norm<cplx>(h, rv, n, W);
       op_apply_impl<V, cplx>(h, act.p, cplx{-1.0, 0.0}, cplx{lams[i].real(), lams[i].imag()}, true, xi, rv);
       const double rr = dev_norm<cplx>(h, rv, n, W);
-      maxres = std::max(maxres, kx > 0 ? rr / kx : rr);
+      const double rel = kx > 0 ? rr / kx : rr;
+      if (!(rel <= maxres)) maxres = rel;  // a NaN sticks
     }
   }
   FW_CHECK_CUDA(cudaStreamSynchronize(s));
   if (st) {
-    st->nconv = nconv;
+    st->nconv = noconv ? kout : nconv;
     st->iterations = iterations;
     st->restarts = restarts;
     st->n_op = n_op;
@@ -668,7 +689,8 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
   }
 }
 
-void eigs_shift_invert(Handle& h, const fw_eigs_params& prm, cd* lams, DevBuf<double>& X_dev, fw_eigs_stats* st) {
+bool eigs_shift_invert(Handle& h, const fw_eigs_params& prm, cd* lams, DevBuf<double>& X_dev, fw_eigs_stats* st,
+                       std::string* why) {
   FW_REQUIRE((h.sp.valid || h.generic.valid) && h.has_symbolic && h.A.valid && h.B.valid, "assemble A and B first");
   FW_REQUIRE(prm.k >= 1, "k must be >= 1");
   const int n = h.sp.n;
@@ -703,13 +725,18 @@ void eigs_shift_invert(Handle& h, const fw_eigs_params& prm, cd* lams, DevBuf<do
     st->lu_fronts = h.lu->sym.n_nodes;
     st->lu_factor_entries = h.lu->sym.factor_entries;
   }
-  // refine == 0: no iterative refinement unless the returned pairs miss 1e-10 (then one retry with one
-  // refinement step per solve); refine > 0: that many steps; refine < 0: never
+  h.tim.lu_solve_entries = h.lu->sym.solve_entries;
+  h.tim.lu_factor_flops = h.lu->sym.factor_flops * (cplx_arith ? 4.0 : 1.0);  // one complex FMA = 4 real ones
+  // refine == 0: no iterative refinement unless the returned pairs miss 1e-10 (then retried with one, then two
+  // refinement steps per solve); refine > 0: that many steps; refine < 0: never.  Pairs that still miss
+  // RESID_FAIL after the last attempt are an error, not a result.
+  constexpr double RESID_RETRY = 1e-10, RESID_FAIL = 1e-8;
   fw_eigs_stats tmp{}, acc{};
   int refine = prm.refine > 0 ? prm.refine : 0;
+  bool converged = true;
   {
     Timer t(s);
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int attempt = 0; attempt < 3; ++attempt) {
       tmp = fw_eigs_stats{};
       if (!cplx_arith)
         eigs_typed<double, double>(h, prm, refine, active, sigma, lams, X_dev, &tmp);
@@ -721,8 +748,15 @@ void eigs_shift_invert(Handle& h, const fw_eigs_params& prm, cd* lams, DevBuf<do
       acc.restarts += tmp.restarts;
       acc.n_op += tmp.n_op;
       acc.t_solve_ms_total += tmp.t_solve_ms_total;
-      if (prm.refine != 0 || tmp.max_residual <= 1e-10) break;
-      refine = 1;
+      if (tmp.nconv < prm.k) {
+        converged = false;
+        if (why)
+          *why = "ARPACK-style error: no convergence (" + std::to_string(tmp.nconv) + "/" + std::to_string(prm.k) +
+                 " eigenvalues converged after " + std::to_string(tmp.restarts) + " restarts)";
+        break;
+      }
+      if (prm.refine != 0 || tmp.max_residual <= RESID_RETRY) break;
+      refine = attempt + 1;
     }
     double ms = t.stop();
     h.tim.arnoldi_ms = ms;
@@ -736,6 +770,15 @@ void eigs_shift_invert(Handle& h, const fw_eigs_params& prm, cd* lams, DevBuf<do
     st->t_solve_ms_total = acc.t_solve_ms_total;
     st->max_residual = tmp.max_residual;
   }
+  if (converged && !(tmp.max_residual <= RESID_FAIL)) {
+    char buf[256];
+    snprintf(buf, sizeof buf,
+             "eigenpairs of the shift-invert Arnoldi miss the residual bound: ||K x - lam M x|| / ||K x|| = %.3e "
+             "(limit %.0e, %d pivots perturbed) -- choose another n_guess / sigma",
+             tmp.max_residual, RESID_FAIL, h.lu->perturbed);
+    throw Error(FW_ERR_NOCONV, buf);
+  }
+  return converged;
 }
 
 }  // namespace fw

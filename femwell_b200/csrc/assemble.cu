@@ -450,6 +450,26 @@ static void dispatch_eps(Handle& h, int eps_kind, const S* eps_dev, double k0, d
   }
 }
 
+// Element subset of the basis (scikit-fem CellBasis(elements=...), kept by with_element, waveguide.py:574): the forms
+// are assembled over the selected elements only.  The local blocks of the others are zeroed before the reduce, so
+// their contributions vanish from the values and -- being exact zeros -- from the exported pattern.
+template <class S>
+__global__ void __launch_bounds__(256) k_zero_masked_blocks(int ne, int nplanes, const uint8_t* __restrict__ emask,
+                                                            S* __restrict__ blocks) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne || emask[e]) return;
+  for (int pl = blockIdx.y; pl < nplanes; pl += gridDim.y) blocks[(size_t)pl * ne + e] = scalar_traits<S>::zero();
+}
+template <class S>
+static void apply_element_mask(Handle& h, S* blocks, int nplanes) {
+  const Space& sp = h.sp;
+  if (!sp.has_emask) return;
+  k_zero_masked_blocks<S><<<dim3(cdiv(sp.ne, 256), std::min(nplanes, 64)), 256, 0, h.stream>>>(sp.ne, nplanes, sp.emask.p,
+                                                                                             blocks);
+  FW_CHECK_CUDA(cudaGetLastError());
+  h.tim.kernel_launches += 1;
+}
+
 static void make_b_lut(const Space& sp, std::vector<int>& lut) {
   lut.assign((size_t)sp.nb * sp.nb, -1);
   std::vector<int> rank(sp.nb, -1);
@@ -509,6 +529,8 @@ static void assemble_ab_typed(Handle& h, int eps_kind, const void* eps_host, dou
     // generic path: aform Nedelec rows + Lagrange rows, bform Nedelec rows
     h.tim.kernel_launches += h.tim.element_kernel_launches;
   }
+  apply_element_mask<S>(h, bA, sp.nb * sp.nb);
+  apply_element_mask<S>(h, bB, sp.nt * sp.nt);
   // segmented reduce onto the structural pattern
   std::vector<int> lut;
   make_b_lut(sp, lut);
@@ -687,6 +709,7 @@ void assemble_aux(Handle& h) {
       else
         dispatch_nq<14, double, FW_EPS_P0, FORM_C1>(h, nullptr, 1.0, 1.0, 0.0, b);
     }
+    apply_element_mask<double>(h, b, sp.nb * sp.nb);
     Values& v = *vals[f];
     v.is_complex = false;
     v.v.alloc((size_t)pat.nnz);

@@ -38,6 +38,8 @@ struct Space {
   DevBuf<double> p;
   DevBuf<int> t, edofs;
   DevBuf<uint8_t> is_z;  // [n] 1 for Lagrange (E_z) dofs
+  DevBuf<uint8_t> emask; // [ne] 1 for the elements of the basis (CellBasis.tind); empty: all elements
+  bool has_emask = false;
   bool valid = false;
 };
 
@@ -58,6 +60,7 @@ struct Handle {
   Pattern pat;
   bool has_symbolic = false;
   bool eliminate_zeros = true;  // export semantics of scipy's coo.eliminate_zeros()
+  double pcg_tol = 1e-10;       // relative residual of the H-field mass solves (FW_OPT_PCG_TOL_EXP)
   Values A, B, Mass, C0, C1;
   // mass matrix without the structurally-zero cross blocks (own compact CSR; used by the PCG of the H field)
   struct CompactCsr {

@@ -21,6 +21,8 @@ struct LUSymbolic {
   int n_nodes = 0, n_levels = 0;
   int64_t factor_entries = 0;  // sum m^2
   int64_t work_entries = 0;    // sum m
+  int64_t solve_entries = 0;   // sum m^2 - (m - ns)^2: entries of L and U read by one forward + backward substitution
+  double factor_flops = 0;     // sum over fronts of the partial-LU flops (ns pivots of an m x m front)
   int max_m = 0, max_ns = 0;
   std::vector<int> perm;      // [n_active] new -> old dof
   std::vector<int> iperm;     // [n] old -> new (or -1)

@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(HWIN) k_lu_panel(FrontTab T, const int* __rest
         // static pivot perturbation (tiny / exactly singular pivot); corrected by iterative refinement
         a[j * LD + bi] = scalar_traits<S>::from(thr, 0.0);
         atomicAdd(&counters[0], 1);
+        if (bv == 0.0) atomicAdd(&counters[1], 1);  // whole column exactly zero: SuperLU's "Factor is exactly singular"
       }
     }
     __syncthreads();
@@ -361,6 +362,7 @@ __global__ void __launch_bounds__(TALL_THREADS) k_lu_panel_tall(FrontTab T, cons
       if (!(bv >= thr)) {
         P[bi + (long long)j * m] = scalar_traits<S>::from(thr, 0.0);
         atomicAdd(&counters[0], 1);
+        if (bv == 0.0) atomicAdd(&counters[1], 1);
       }
     }
     __syncthreads();
@@ -459,6 +461,7 @@ __global__ void __cluster_dims__(PCL, 1, 1) __launch_bounds__(PCL_THREADS)
     if (rank == 0 && t == 0) {
       piv[T.own_start[node] + k0 + j] = k0 + pr;
       if (tiny) atomicAdd(&counters[0], 1);
+      if (bv == 0.0) atomicAdd(&counters[1], 1);
     }
     // ---- broadcast the pivot row and row j (their owners stage the registers in shared memory, the owner's
     //      warp copies the 32 values into every CTA)
@@ -875,6 +878,10 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
   d.counters.download(cnt, 4, s);
   FW_CHECK_CUDA(cudaStreamSynchronize(s));
   lu.perturbed = cnt[0];
+  if (cnt[1] > 0) {
+    lu.factored = false;
+    throw Error(FW_ERR_SINGULAR, "Factor is exactly singular");  // the message of scipy's splu (SuperLU) for this case
+  }
   lu.factored = true;
   h.tim.kernel_launches += launches;
 }

@@ -432,6 +432,11 @@ void lu_symbolic_build(LUSymbolic& S, int n, int nb, int ne, const int* edofs, c
       S.level_max_nb[d] = std::max(S.level_max_nb[d], S.m[v] - S.ns[v]);
       S.max_m = std::max(S.max_m, S.m[v]);
       S.max_ns = std::max(S.max_ns, S.ns[v]);
+      const double m = S.m[v], ns = S.ns[v], nbd = m - ns;
+      S.solve_entries += (int64_t)S.m[v] * S.m[v] - (int64_t)(S.m[v] - S.ns[v]) * (S.m[v] - S.ns[v]);
+      // sum_{j<ns} [ (m-j-1) divisions + 2 (m-j-1)^2 ] = 2/3 (m^3 - nbd^3) - ... ; written as the exact sum of squares
+      auto sq = [](double x) { return x * (x + 1) * (2 * x + 1) / 6; };  // sum_{i<=x} i^2
+      S.factor_flops += 2.0 * (sq(m - 1) - sq(nbd - 1 < 0 ? 0 : nbd - 1)) + 0.5 * (m - 1 + nbd) * ns;
     }
   S.factor_entries = fo;
   S.work_entries = wo;

@@ -289,11 +289,31 @@ static void mass_solve_k(Handle& h, int n, const CsrView& M, const cplx* B, cplx
   double bnorm2[CG_MAXK], rr[CG_MAXK];
   FW_CHECK_CUDA(cudaMemcpyAsync(bnorm2, d_rr, sizeof(double) * K, cudaMemcpyDeviceToHost, s));
   FW_CHECK_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < K; ++i)
+    if (!std::isfinite(bnorm2[i])) throw Error(FW_ERR_INVALID, "mass PCG (H field): non-finite right-hand side");
   tr.mark("    mass PCG: init");
   int64_t launches = 6;
   int cur = 0, it = 0;
   const int check_every = 4;
-  for (; it < 600; ++it) {
+  const int max_it = 600;
+  // ||r|| <= tol ||b||.  The reference's H carries complex64 rounding (1e-7, waveguide.py:658,666) and the north star
+  // asks 1e-6 on overlaps; the default 1e-10 keeps H four digits beyond that (FW_OPT_PCG_TOL_EXP).
+  const double tol2 = h.pcg_tol * h.pcg_tol;
+  bool converged = false;
+  double worst = 0.0;
+  auto check = [&]() {
+    FW_CHECK_CUDA(cudaMemcpyAsync(rr, d_rr, sizeof(double) * K, cudaMemcpyDeviceToHost, s));
+    FW_CHECK_CUDA(cudaStreamSynchronize(s));
+    bool done = true;
+    worst = 0.0;
+    for (int i = 0; i < K; ++i) {
+      if (!(rr[i] <= tol2 * bnorm2[i])) done = false;
+      const double rel = bnorm2[i] > 0 ? std::sqrt(rr[i] / bnorm2[i]) : (rr[i] > 0 ? INFINITY : 0.0);
+      if (!(rel <= worst)) worst = rel;  // NaN propagates
+    }
+    return done;
+  };
+  for (; it < max_it; ++it) {
     k_spmv_multi<K><<<nblk_mv, 256, 0, s>>>(n, M.indptr, M.indices, M.vals, (const double*)pv, (double*)qv, part_pq,
                                             nblk_mv);
     k_cg_reduce<<<K, 256, 0, s>>>(part_pq, nblk_mv, d_pq);
@@ -304,23 +324,26 @@ static void mass_solve_k(Handle& h, int n, const CsrView& M, const cplx* B, cplx
     k_cg_direction<K><<<cdiv((int64_t)n * K, 256), 256, 0, s>>>(n, (double2*)pv, (const double2*)zv, d_rz[cur ^ 1], d_rz[cur]);
     cur ^= 1;
     launches += 5;
-    if ((it + 1) % check_every == 0) {
-      FW_CHECK_CUDA(cudaMemcpyAsync(rr, d_rr, sizeof(double) * K, cudaMemcpyDeviceToHost, s));
-      FW_CHECK_CUDA(cudaStreamSynchronize(s));
-      bool done = true;
-      for (int i = 0; i < K; ++i)
-        if (!(rr[i] <= 1e-26 * bnorm2[i])) done = false;  // ||r|| <= 1e-13 ||b|| (the reference's H carries complex64 rounding, 1e-7)
-      if (done) break;
+    if ((it + 1) % check_every == 0 && check()) {
+      converged = true;
+      ++it;
+      break;
     }
   }
+  if (!converged) converged = check();  // the loop may end between two checks (or without any iteration)
   tr.mark("    mass PCG: iterations");
+  h.tim.pcg_iterations = std::max<int64_t>(h.tim.pcg_iterations, it);
+  if (!(worst <= h.tim.pcg_rel_residual)) h.tim.pcg_rel_residual = worst;
+  if (!converged)
+    throw Error(FW_ERR_NOCONV, "mass PCG (H field) did not converge: ||r||/||b|| = " + std::to_string(worst) + " after " +
+                                   std::to_string(it) + " iterations (tolerance " + std::to_string(h.pcg_tol) + ")");
   k_cg_interleave<K><<<g256, 256, 0, s>>>(n, xv, X, false, M.idx, M.n_full);
   ++launches;
   FW_CHECK_CUDA(cudaGetLastError());
   h.tim.kernel_launches += launches;
   if (getenv("FW_TRACE"))
-    fprintf(stderr, "[fw-trace]   mass PCG: %d rhs, %d iterations, %lld kernel launches, mass nnz %lld\n", K, it + 1,
-            (long long)launches, (long long)M.nnz);
+    fprintf(stderr, "[fw-trace]   mass PCG: %d rhs, %d iterations, rel. residual %.2e, %lld kernel launches, mass nnz %lld\n",
+            K, it, worst, (long long)launches, (long long)M.nnz);
 }
 
 // M X = B for a real SPD CSR matrix and k <= CG_MAXK complex right-hand sides ([k][n] each); X overwritten.
@@ -346,8 +369,111 @@ void pcg_solve_multi(Handle& h, int n_rows, const int* indptr, const int* indice
   pcg_solve_view(h, n_rows, V, k, B, X);
 }
 
+// ---- real packing.  With a real permittivity the modes come out of the real-arithmetic Arnoldi as real vectors, so
+// every right-hand side C(beta) e restricted to one block of the mass matrix is purely real (Lagrange rows) or purely
+// imaginary (Nedelec rows).  Two such real systems are then solved as ONE complex system M (x_a + i x_b) = b_a + i b_b
+// (the matrix is real): half the vector traffic of the PCG.  The structure is detected on the device, never assumed.
+struct CompSel {
+  int comp[CG_MAXK];  // 0: the real part carries the data, 1: the imaginary part
+};
+// out[2r] = max |Re b_r|, out[2r+1] = max |Im b_r| over the rows of the block (non-negative doubles order like their
+// bit patterns)
+__global__ void __launch_bounds__(256) k_cg_component_max(int n, int k, const cplx* __restrict__ B,
+                                                          const int* __restrict__ idx, int n_full,
+                                                          unsigned long long* __restrict__ out) {
+  for (int r = 0; r < k; ++r) {
+    double mre = 0.0, mim = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const cplx v = B[(size_t)r * n_full + (idx ? idx[i] : i)];
+      const double a = fabs(v.re), b = fabs(v.im);
+      mre = a > mre || a != a ? a : mre;  // a NaN sticks (and counts as "non-zero")
+      mim = b > mim || b != b ? b : mim;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double a = __shfl_xor_sync(0xffffffffu, mre, o), b = __shfl_xor_sync(0xffffffffu, mim, o);
+      mre = a > mre || a != a ? a : mre;
+      mim = b > mim || b != b ? b : mim;
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMax(&out[2 * r], (unsigned long long)__double_as_longlong(mre));
+      atomicMax(&out[2 * r + 1], (unsigned long long)__double_as_longlong(mim));
+    }
+  }
+}
+// Bp[j][d] = (b'_{2j}[d], b'_{2j+1}[d]) with b'_r the data-carrying component of b_r (0 beyond k)
+__global__ void __launch_bounds__(256) k_cg_pack_real(int n, int k, const cplx* __restrict__ B,
+                                                      const int* __restrict__ idx, int n_full, CompSel sel,
+                                                      cplx* __restrict__ Bp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t d = idx ? idx[i] : i;
+  for (int j = 0; 2 * j < k; ++j) {
+    const cplx a = B[(size_t)(2 * j) * n_full + d];
+    cplx o{sel.comp[2 * j] ? a.im : a.re, 0.0};
+    if (2 * j + 1 < k) {
+      const cplx b = B[(size_t)(2 * j + 1) * n_full + d];
+      o.im = sel.comp[2 * j + 1] ? b.im : b.re;
+    }
+    Bp[(size_t)j * n_full + d] = o;
+  }
+}
+__global__ void __launch_bounds__(256) k_cg_unpack_real(int n, int k, const cplx* __restrict__ Xp,
+                                                        const int* __restrict__ idx, int n_full, CompSel sel,
+                                                        cplx* __restrict__ X) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t d = idx ? idx[i] : i;
+  for (int r = 0; r < k; ++r) {
+    const cplx v = Xp[(size_t)(r >> 1) * n_full + d];
+    const double x = (r & 1) ? v.im : v.re;
+    X[(size_t)r * n_full + d] = sel.comp[r] ? cplx{0.0, x} : cplx{x, 0.0};
+  }
+}
+
+static void pcg_solve_groups(Handle& h, int n_rows, const CsrView& V, int k, const cplx* B, cplx* X);
+
 static void pcg_solve_view(Handle& h, int n_rows, const CsrView& V, int k, const cplx* B, cplx* X) {
   FW_REQUIRE(k >= 1 && k <= CG_MAXK, "pcg_solve_multi: 1 <= k <= 8");
+  static const bool no_pack = getenv("FW_PCG_NO_PACK") != nullptr;
+  if (k >= 2 && !no_pack) {
+    cudaStream_t s = h.stream;
+    DevBuf<double> cm;
+    cm.alloc(2 * CG_MAXK);
+    cm.zero(s);
+    k_cg_component_max<<<296, 256, 0, s>>>(n_rows, k, B, V.idx, V.n_full, (unsigned long long*)cm.p);
+    double mx[2 * CG_MAXK];
+    cm.download(mx, 2 * CG_MAXK, s);
+    FW_CHECK_CUDA(cudaStreamSynchronize(s));
+    h.tim.kernel_launches += 1;
+    CompSel sel{};
+    bool packable = true;
+    for (int r = 0; r < k; ++r) {
+      if (mx[2 * r + 1] == 0.0)
+        sel.comp[r] = 0;
+      else if (mx[2 * r] == 0.0)
+        sel.comp[r] = 1;
+      else
+        packable = false;  // genuinely complex (or non-finite) right-hand side
+    }
+    if (packable) {
+      const int k2 = (k + 1) / 2;
+      DevBuf<double> bp, xp;
+      bp.alloc((size_t)2 * V.n_full * k2);
+      xp.alloc((size_t)2 * V.n_full * k2);
+      const int g = cdiv(n_rows, 256);
+      k_cg_pack_real<<<g, 256, 0, s>>>(n_rows, k, B, V.idx, V.n_full, sel, (cplx*)bp.p);
+      pcg_solve_groups(h, n_rows, V, k2, (const cplx*)bp.p, (cplx*)xp.p);
+      k_cg_unpack_real<<<g, 256, 0, s>>>(n_rows, k, (const cplx*)xp.p, V.idx, V.n_full, sel, X);
+      FW_CHECK_CUDA(cudaGetLastError());
+      h.tim.kernel_launches += 2;
+      return;
+    }
+  }
+  pcg_solve_groups(h, n_rows, V, k, B, X);
+}
+
+static void pcg_solve_groups(Handle& h, int n_rows, const CsrView& V, int k, const cplx* B, cplx* X) {
   const size_t n = (size_t)V.n_full;  // stride between the systems in B and X
   // systems are solved in groups of 4 / 2 / 1 (compile-time interleave factor)
   int done = 0;

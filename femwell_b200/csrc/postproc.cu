@@ -208,6 +208,9 @@ static void mass_solve(Handle& h, const cplx* b, cplx* x) {
 // all k modes at once: rhs_i = C0 e_i + i beta_i C1 e_i, one block PCG for the k mass solves
 void hfield_multi_dev(Handle& h, int k, const cplx* E_dev, const cplx* betas, double omega, double mu0, cplx* H_dev) {
   Trace tr(h.stream);
+  Timer th(h.stream);
+  h.tim.pcg_iterations = 0;
+  h.tim.pcg_rel_residual = 0.0;
   assemble_aux(h);
   tr.mark("  hfield: aux operators");
   const int n = h.sp.n;
@@ -234,6 +237,7 @@ void hfield_multi_dev(Handle& h, int k, const cplx* E_dev, const cplx* betas, do
   k_cscale<<<cdiv((int64_t)n * k, 256), 256, 0, s>>>(H_dev, n * k, f);
   FW_CHECK_CUDA(cudaGetLastError());
   h.tim.kernel_launches += 1;
+  h.tim.hfield_ms = th.stop();
 }
 
 void hfield_dev(Handle& h, const cplx* E_dev, cplx beta, double omega, double mu0, cplx* H_dev) {

@@ -9,8 +9,10 @@ namespace fw {
 bool dense_eig(int n, const std::complex<double>* a, std::complex<double>* w, std::complex<double>* v);
 
 // device result: lams (host) and X_dev [k][n] c128 on the device (unit 2-norm Ritz vectors)
-void eigs_shift_invert(Handle& h, const fw_eigs_params& prm, std::complex<double>* lams, DevBuf<double>& X_dev,
-                       fw_eigs_stats* st);
+// returns false when fewer than k pairs converged: st->nconv pairs are then in lams[0:nconv] / X_dev[0:nconv] and
+// *why holds the message (the API turns this into FW_ERR_NOCONV after handing the partial result to the caller)
+bool eigs_shift_invert(Handle& h, const fw_eigs_params& prm, std::complex<double>* lams, DevBuf<double>& X_dev,
+                       fw_eigs_stats* st, std::string* why = nullptr);
 
 // y = (alphaA*A + alphaB*B) x with Dirichlet rows/cols masked (identity rows give 0 here)
 template <class V, class S>
@@ -28,6 +30,9 @@ std::complex<double> overlap_cross_dev(Handle& h, const fw_space& sj, const cplx
 void intensity_dev(Handle& h, const cplx* E, const cplx* Hf, double* out);
 void poynting_dev(Handle& h, const cplx* E, const cplx* Hf, cplx* out);
 void energy_density_dev(Handle& h, const cplx* E, cplx* out);
+void error_estimator_dev(Handle& h, const cplx* E, int eps_kind, bool eps_complex, const void* eps_dev, int nf,
+                         const int* t2f_dev, const int* f2t_dev, int nqf, const double* s, const double* w,
+                         const double* vec, double* eta_dev);
 void setup_generic_csr(Handle& h, int n, const int* Kp, const int* Ki, const void* Kx, const int* Mp, const int* Mi,
                        const void* Mx, bool is_complex, const double* coords);
 void functional_dev(Handle& h, int kind, const cplx* f0, const cplx* f1, const cplx* f2, const cplx* f3, int aux_kind,

@@ -48,11 +48,18 @@ def get_context(device: Optional[int] = None) -> Context:
     return _contexts[device]
 
 
-def _bind(basis: Basis, device=None) -> Context:
+def _bind(basis: Basis, device=None, subset=False) -> Context:
+    """Handle that holds ``basis``: the device the basis was solved on (``solver_options={"device": ...}``) unless
+    ``device`` is given.  ``subset``: also restrict the forms to ``basis.tind`` (only the bilinear forms need it;
+    the functionals take their element selection per call)."""
+    if device is None:
+        device = getattr(basis, "_fw_device", None)
     ctx = get_context(device)
     if not ctx.same_space(basis) or ctx.nnz_structural is None:
         ctx.set_space(basis)
         ctx.symbolic()
+    elif subset:
+        ctx.set_element_subset(basis.tind)
     return ctx
 
 
@@ -182,6 +189,13 @@ class Mode:
         basis2 = self.basis.with_element(ElementDG(ElementTriP1()))
         return basis2, _bind(self.basis).intensity(self.E, self.H)
 
+    def eval_error_estimator(self):
+        """Interior-facet jump estimator (waveguide.py:473-502): per element, half the sum over its facets of
+        ``int_f h (|[grad E_z] . n|^2 + |[eps E_t] . n|^2) ds``; feeds ``adaptive_theta`` / ``mesh.refined``
+        (docs/photonics/examples/refinement.py:58-80)."""
+        return _bind(self.basis).error_estimator(self.E, eps_kind_of(self.basis_epsilon_r.elem),
+                                                 np.asarray(self.epsilon_r))
+
     def calculate_pertubated_neff(self, delta_epsilon):
         return self.n_eff + self.calculate_coupling_coefficient(self, delta_epsilon) * epsilon_0 * speed_of_light * 0.5
 
@@ -234,14 +248,25 @@ def compute_modes(
     """Computes the modes of a waveguide (reference signature, waveguide.py:528-540).
 
     ``solver`` must be ``"b200"``; ``solver_options`` (dict, optional): ``v0``, ``ncv``, ``tol``,
-    ``maxiter``, ``refine``, ``leaf_elements``, ``reuse_symbolic``, ``device``.
+    ``maxiter``, ``refine``, ``leaf_elements``, ``reuse_symbolic`` (default True: keep the CSR pattern and the LU
+    analysis while the mesh stays), ``device``, ``pcg_tol_exp`` (H-field mass solves to 10^-value, default 10),
+    ``mode_tables`` (``dict(kind=, vec=, sc=, element_dofs=, n_dofs=)``: a foreign local basis, see
+    ``Basis.with_tables`` / ``femwell_b200.bridge``).
+
+    Errors mirror the reference: unknown ``solver`` -> ``ValueError`` (waveguide.py:563), ``order`` not in (1, 2)
+    -> ``AssertionError`` (:572), no convergence -> a ``scipy.sparse.linalg.ArpackNoConvergence`` subclass carrying
+    the converged pairs, singular shifted pencil -> ``RuntimeError("Factor is exactly singular")`` (scipy ``splu``).
     """
     if solver != "b200":
-        raise ValueError("`solver` must be `b200` in femwell_b200 (use femwell itself for `scipy`/`slepc`)")
+        raise ValueError("`solver` must either be `scipy` or `slepc` (femwell's CPU paths, not carried by "
+                         "femwell_b200) or `b200`")
     opts = dict(solver_options or {})
     k0 = 2 * np.pi / wavelength
     element = _mode_element(order)
     basis = basis_epsilon_r.with_element(element)
+    mode_tables = opts.pop("mode_tables", None)
+    if mode_tables is not None:
+        basis = basis.with_tables(**mode_tables)
     basis_epsilon_r = basis.with_element(basis_epsilon_r.elem)  # adjust quadrature (waveguide.py:575)
     epsilon_r = np.asarray(epsilon_r)
     eps_kind = eps_kind_of(basis_epsilon_r.elem)
@@ -251,15 +276,21 @@ def compute_modes(
     else:
         sigma = k0**2 * np.max(epsilon_r) * 1.1
 
-    dirichlet = None
-    if metallic_boundaries:
+    dirichlet = opts.pop("dirichlet_dofs", None)  # precomputed by the scikit-fem bridge (its own get_dofs)
+    if metallic_boundaries and dirichlet is None:
         dirichlet = basis.get_dofs(None if metallic_boundaries is True else metallic_boundaries)
 
     device = opts.pop("device", None)
     ctx = get_context(device)
-    reuse = ctx.same_space(basis) and ctx.nnz_structural is not None
+    basis._fw_device = ctx.device  # the Mode post-processing binds to the same GPU
+    reuse = bool(opts.pop("reuse_symbolic", True)) and ctx.same_space(basis) and ctx.nnz_structural is not None
     if not reuse:
         ctx.set_space(basis, solve_hint=(dirichlet, opts.get("leaf_elements", 0)))
+    else:
+        ctx.set_element_subset(basis.tind)
+    pcg_tol_exp = opts.pop("pcg_tol_exp", None)
+    if pcg_tol_exp is not None:
+        ctx.set_option(1, int(pcg_tol_exp))
     lams, E, H, powers, stats = ctx.compute_modes(
         eps_kind, epsilon_r, wavelength, num_modes, sigma, mu_r=float(mu_r), radius=float(radius),
         dirichlet=dirichlet, reuse_symbolic=reuse, **opts)
@@ -284,7 +315,7 @@ def compute_modes(
 
 def calculate_hfield(basis, xs, beta, omega):
     """waveguide.py:657-677"""
-    return _bind(basis).hfield(xs, beta, omega, mu_0)
+    return _bind(basis, subset=True).hfield(xs, beta, omega, mu_0)
 
 
 def calculate_energy_current_density(basis, xs):
@@ -294,10 +325,24 @@ def calculate_energy_current_density(basis, xs):
     return basis.with_element(ElementTriP0()), _bind(basis).energy_current_density(xs)
 
 
+def _same_mesh(mi, mj):
+    return mi is mj or (mi.p.shape == mj.p.shape and mi.t.shape == mj.t.shape and np.array_equal(mi.t, mj.t)
+                        and np.array_equal(mi.p, mj.p))
+
+
 def _same_quadrature_space(basis_i, basis_j):
-    """the reference's same-basis test (waveguide.py:729-731): equal bases, or equal quadrature on one mesh"""
-    return basis_i.mesh is basis_j.mesh and basis_i.elem == basis_j.elem and np.array_equal(basis_i.X, basis_j.X) \
-        and np.array_equal(basis_i.W, basis_j.W)
+    """The reference's same-basis test (waveguide.py:727-729): ``basis_i == basis_j`` or equal quadrature rules.
+    DEVIATION (documented in INTEGRATION.md): the reference takes the same-basis branch for ANY two bases with equal
+    rules and then pairs the two meshes element by element -- a numpy broadcast error for different element counts,
+    a meaningless number otherwise.  Here equal rules on different meshes go to the cross-mesh branch."""
+    if basis_i is basis_j:
+        return True
+    if basis_i.elem != basis_j.elem or basis_i.tables_id != basis_j.tables_id:
+        return False
+    if basis_i.X.shape != basis_j.X.shape or not (np.isclose(basis_i.X, basis_j.X).all()
+                                                   and np.isclose(basis_i.W, basis_j.W).all()):
+        return False
+    return _same_mesh(basis_i.mesh, basis_j.mesh)
 
 
 def calculate_overlap(basis_i, E_i, H_i, basis_j, E_j, H_j):

@@ -63,6 +63,24 @@ class MeshTri:
     def nfacets(self) -> int:
         return self.facets.shape[1]
 
+    @property
+    def f2t(self) -> np.ndarray:
+        """int32 (2, Nf): the two elements of every facet, ``-1`` on the boundary (scikit-fem ``mesh.f2t``); side 0
+        is the element with the lower index."""
+        if getattr(self, "_f2t", None) is None:
+            ne = self.nelements
+            f = self.t2f.ravel()
+            e = np.tile(np.arange(ne, dtype=np.int64), 3)
+            order = np.lexsort((e, f))
+            fs, es = f[order], e[order]
+            first = np.ones(fs.size, dtype=bool)
+            first[1:] = fs[1:] != fs[:-1]
+            out = np.full((2, self.nfacets), -1, dtype=np.int32)
+            out[0, fs[first]] = es[first]
+            out[1, fs[~first]] = es[~first]
+            self._f2t = out
+        return self._f2t
+
     def boundary_facets(self) -> np.ndarray:
         """Facets belonging to exactly one element."""
         return np.nonzero(self._facet_count == 1)[0].astype(np.int32)
@@ -231,5 +249,55 @@ def waveguide_mesh(
         "slab": np.nonzero(slab)[0].astype(np.int32),
         "box": np.nonzero(box)[0].astype(np.int32),
         "clad": np.nonzero(clad)[0].astype(np.int32),
+    }
+    return m
+
+
+def geometric_axis(a: float, b: float, h0: float, ratio: float, fine_end: str) -> np.ndarray:
+    """Grid from ``a`` to ``b`` whose spacing is ``h0`` at the ``fine_end`` ("a" or "b") and grows
+    geometrically by ``ratio`` per cell towards the other end (rescaled to hit both ends exactly)."""
+    length = b - a
+    hs = []
+    h = h0
+    while sum(hs) + h < length:
+        hs.append(h)
+        h *= ratio
+    hs = np.asarray(hs if hs else [length], dtype=np.float64)
+    hs *= length / hs.sum()
+    pts = np.concatenate([[0.0], np.cumsum(hs)])
+    pts[-1] = length
+    return a + pts if fine_end == "a" else b - pts[::-1]
+
+
+def rib_benchmark_mesh(slab_thickness: float, h0: float = 0.075, ratio: float = 1.2, core_width: float = 3.0,
+                       core_thickness: float = 1.0, slab_width: float = 18.0, box_thickness: float = 10.0,
+                       clad_thickness: float = 3.0, jitter: float = 0.0) -> MeshTri:
+    """Rib waveguide of the reference's second mode-solver benchmark (docs/benchmarks/mode_solver.py:52-104,
+    after Hadley 2002): core ``core_width x core_thickness`` on a slab of ``slab_thickness`` spanning the whole
+    width, box below, cladding above.  The reference meshes it with gmsh (resolution 0.1 in the core growing to
+    0.3); here: a tensor grid with spacing ``h0`` over the core, growing geometrically by ``ratio`` away from it,
+    grid lines on every material interface.  Sub-domains ``core`` (core + slab), ``box``, ``clad``."""
+    hw, sw = core_width / 2, slab_width / 2
+    xs = np.concatenate([
+        geometric_axis(-sw, -hw, h0, ratio, "b")[:-1],
+        np.linspace(-hw, hw, int(round(core_width / h0)) + 1)[:-1],
+        geometric_axis(hw, sw, h0, ratio, "a"),
+    ])
+    ybr = sorted({0.0, core_thickness} | ({slab_thickness} if slab_thickness > 0 else set()))
+    ys = [geometric_axis(-box_thickness, 0.0, h0, ratio, "b")[:-1]]
+    for a, b in zip(ybr[:-1], ybr[1:]):
+        ys.append(np.linspace(a, b, max(1, int(round((b - a) / h0))) + 1)[:-1])
+    ys.append(geometric_axis(core_thickness, clad_thickness, h0, ratio, "a"))
+    ys = np.concatenate(ys)
+    m = MeshTri.structured(xs, ys, jitter=jitter, frozen_x=[-hw, hw], frozen_y=ybr)
+    c = m.centroids()
+    core = (np.abs(c[0]) < hw) & (c[1] > 0) & (c[1] < core_thickness)
+    if slab_thickness > 0:
+        core |= (c[1] > 0) & (c[1] < slab_thickness)
+    box = c[1] < 0
+    m.subdomains = {
+        "core": np.nonzero(core)[0].astype(np.int32),
+        "box": np.nonzero(box)[0].astype(np.int32),
+        "clad": np.nonzero(~(core | box))[0].astype(np.int32),
     }
     return m

@@ -63,7 +63,12 @@ int fw_synchronize(fw_handle* h);
 /* FW_OPT_ELIMINATE_ZEROS (default 1): matrix export drops local contributions that are exactly 0.0
  * like scikit-fem's COOData (coo_matrix.eliminate_zeros()); 0 exports the structural
  * pattern (every (test dof, trial dof) pair of every element).                                   */
-enum { FW_OPT_ELIMINATE_ZEROS = 0 };
+enum {
+  FW_OPT_ELIMINATE_ZEROS = 0,
+  /* relative residual 10^-value of the H-field mass solves (block PCG replacing the spsolve of waveguide.py:671);
+   * default 10: the reference's H carries complex64 rounding (1e-7, :658,:666)                                  */
+  FW_OPT_PCG_TOL_EXP = 1
+};
 int fw_set_option(fw_handle* h, int32_t option, int32_t value);
 
 /* ---- a1: mesh + FE space (waveguide.py:567-575; scikit-fem CellBasis) ------------ */
@@ -80,6 +85,11 @@ typedef struct {
   const double* W;          /* [nqp]     quadrature weights                          */
 } fw_space;
 int fw_set_space(fw_handle* h, const fw_space* s);
+/* Element subset of the basis (scikit-fem CellBasis(elements=...); basis_epsilon_r.with_element keeps it,
+ * waveguide.py:574): the forms are assembled over `elements` only.  Call after fw_set_space; n_sel < 0 or NULL
+ * restores "all elements" (the state after fw_set_space).  Dofs no selected element touches get empty rows, as in
+ * the reference (whose factorisation then fails: FW_ERR_SINGULAR here).                                     */
+int fw_set_element_subset(fw_handle* h, int32_t n_sel, const int32_t* elements);
 /* Optional, before fw_set_space: announces the Dirichlet set (condense, waveguide.py:610-619) and the leaf size of
  * the solve that will follow, so that the host analysis of its sparse LU starts inside fw_set_space and overlaps
  * the uploads.  One shot; a solve with other parameters simply redoes the analysis. */
@@ -109,6 +119,11 @@ int fw_coo_to_csr_export(fw_handle* h, int32_t* indptr, int32_t* indices, void* 
 
 /* ---- K4: CSR SpMV y = M x on the assembled operators (x,y host, length n_dofs)       */
 int fw_matrix_spmv(fw_handle* h, int32_t which, int32_t x_is_complex, const void* x, void* y);
+
+/* Device-resident timing of K4 (measurement only): `reps` applications y = M x of an assembled operator on an
+ * internal vector, CUDA events on the handle's stream; *ms_per_apply = average.  x_is_complex selects the
+ * f64 or c128 vector kernel.                                                                              */
+int fw_bench_spmv(fw_handle* h, int32_t which, int32_t x_is_complex, int32_t reps, double* ms_per_apply);
 
 /* ---- a6-a9: shift-invert Arnoldi on (-A) x = lam (-B) x  (waveguide.py:605-625,
  *      scipy eigs mode 3).  dirichlet: dofs condensed out (waveguide.py:610-619).
@@ -186,6 +201,17 @@ int fw_poynting(fw_handle* h, const double* E, const double* H, double* out);
  * |e_x|^2 + |e_y|^2 + |e_z|.  xs: complex128 [n_dofs]; out: complex128 [n_elements]. */
 int fw_energy_current_density(fw_handle* h, const double* xs, double* out);
 
+/* Mode.eval_error_estimator (femwell/maxwell/waveguide.py:473-502): eta[e] = 1/2 sum_{f in e} int_f h (|[grad E_z].n|^2 +
+ * |[eps E_t].n|^2) ds over the interior facets (h = |f|), the indicator of the adaptive refinement loop of
+ * docs/photonics/examples/refinement.py:58-105.  E: complex128 [n_dofs]; eps as in fw_assemble_waveguide (FW_EPS_P0 or
+ * FW_EPS_DG_P1); t2f int32 [3, Ne] facet of local edge (0,1) (1,2) (0,2); f2t int32 [2, n_facets] the two elements
+ * of a facet (-1: boundary); s, w [nqf] Gauss-Legendre rule on [0, 1] (the reference: degree 2 * maxdeg);
+ * facet_vec float64 [nbfun, 3, 2, nqf]: reference vector of every local basis function (Nedelec value / Lagrange
+ * gradient) at the points of the three local edges.  out: float64 [Ne].                                          */
+int fw_error_estimator(fw_handle* h, const double* E, int32_t eps_kind, int32_t eps_is_complex, const void* eps,
+                       int32_t n_facets, const int32_t* t2f, const int32_t* f2t, int32_t nqf, const double* s,
+                       const double* w, const double* facet_vec, double* out);
+
 /* ---- whole path with HOST buffers (the call the Python shim makes for compute_modes) */
 typedef struct {
   double wavelength, mu_r, radius;
@@ -202,6 +228,14 @@ typedef struct {
   double upload_ms, symbolic_ms, element_kernel_ms, reduce_ms, lu_symbolic_ms, lu_factor_ms,
       arnoldi_ms, postprocess_ms, total_ms, download_ms;
   int64_t element_kernel_launches, kernel_launches, nnz_structural;
+  /* roofline inputs of the sparse LU (from the analysis tables): entries of L and U that one pair of triangular
+   * solves reads (sum over fronts of m^2 - (m - ns)^2) and the flops of one numeric factorisation              */
+  int64_t lu_solve_entries;
+  double lu_factor_flops;
+  /* H-field mass solves (block PCG): iterations of the slowest system and its final ||r|| / ||b||             */
+  int64_t pcg_iterations;
+  double pcg_rel_residual;
+  double hfield_ms;      /* calculate_hfield part of postprocess_ms                                             */
 } fw_timings;
 int fw_get_timings(fw_handle* h, fw_timings* t);
 

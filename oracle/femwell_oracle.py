@@ -81,9 +81,59 @@ class LocalBasis:
     grad: Optional[np.ndarray] = None  # (2, Ne, nq)
 
 
+def physical_basis_from_tables(tables, p, t, X):
+    """The same interface for a FOREIGN local basis given by reference tables ``(kind, vec, sc)`` at the points X
+    (scikit-fem ``elem.lbasis``): covariant Piola map for the H(curl) functions
+    (phi = A^-T phi_hat, curl phi = curl_hat / det A) and the gradient map for the H1 functions."""
+    kind, vec, sc = tables
+    p = np.asarray(p, dtype=np.float64)
+    t = np.asarray(t)
+    ne, nq = t.shape[1], X.shape[1]
+    v = [p[:, t[a]] for a in range(3)]
+    e1, e2 = v[1] - v[0], v[2] - v[0]
+    det = e1[0] * e2[1] - e1[1] * e2[0]
+    # A = [e1 e2]; A^-T = 1/det [[e2y, -e1y], [-e2x, e1x]]
+    def piola(vh):  # (2, nq) -> (2, Ne, nq)
+        return np.stack([(e2[1][:, None] * vh[0][None, :] - e1[1][:, None] * vh[1][None, :]) / det[:, None],
+                         (-e2[0][:, None] * vh[0][None, :] + e1[0][:, None] * vh[1][None, :]) / det[:, None]])
+
+    out = []
+    for l in range(len(kind)):
+        if kind[l] == 0:
+            out.append(LocalBasis(0, t=piola(vec[l]), curl=sc[l][None, :] / det[:, None]))
+        else:
+            out.append(LocalBasis(1, z=np.broadcast_to(sc[l], (ne, nq)).copy(), grad=piola(vec[l])))
+    ones = np.ones(nq)
+    xq = v[0][:, :, None] + e1[:, :, None] * X[0][None, None, :] + e2[:, :, None] * X[1][None, None, :]
+    dx = np.abs(det)[:, None] * ones[None, :]
+    return out, xq, dx
+
+
+# a foreign local basis for all assembly / interpolation routines below (tests only; None: Appendix-D basis)
+_TABLES = None
+
+
+class foreign_tables:
+    """``with foreign_tables((kind, vec, sc)): ...`` -- every routine of this module then evaluates the local
+    basis from the given reference tables instead of the built-in Appendix-D formulas."""
+
+    def __init__(self, tables):
+        self.tables = tables
+
+    def __enter__(self):
+        global _TABLES
+        self.prev, _TABLES = _TABLES, self.tables
+
+    def __exit__(self, *exc):
+        global _TABLES
+        _TABLES = self.prev
+
+
 def physical_basis(order, p, t, X):
     """All local basis functions (composite entity-major order) at all points.
     Basis of SURVEY.md Appendix D written with physical gradients of the barycentrics."""
+    if _TABLES is not None:
+        return physical_basis_from_tables(_TABLES, p, t, X)
     p = np.asarray(p, dtype=np.float64)
     t = np.asarray(t)
     ne, nq = t.shape[1], X.shape[1]
@@ -471,6 +521,56 @@ def energy_current_density(p, t, dofs, order, X, W, xs):
     a = np.sum(dxw * (np.abs(ex) ** 2 + np.abs(ey) ** 2 + np.abs(ez)), axis=1).astype(complex)
     b = np.sum(dxw, axis=1)
     return a / b
+
+
+def eval_error_estimator(p, t, dofs, order, E, eps_kind, epsilon_r):
+    """Mode.eval_error_estimator (waveguide.py:473-502) restated: two InteriorFacetBasis objects (sides 0 / 1) on the
+    Gauss-Legendre rule of degree 2 * maxdeg, ``w.h`` = facet length, ``edge_jump.elemental`` per interior facet,
+    ``eta_E = sum(0.5 * tmp[t2f], axis=0)``.  Evaluated element by element with the physical basis at the facet
+    points (no reference tables)."""
+    t = np.asarray(t, dtype=np.int64)
+    ne = t.shape[1]
+    facets, t2f = topology(p, t)
+    nf = facets.shape[1]
+    npts = int(np.ceil((2 * order + 1) / 2))
+    xg, wg = np.polynomial.legendre.leggauss(npts)
+    sg, wg = 0.5 * (xg + 1), 0.5 * wg
+    a, b = p[:, facets[0]], p[:, facets[1]]
+    length = np.hypot(*(b - a))
+    nrm = np.stack([(b - a)[1], -(b - a)[0]]) / length  # (2, nf)
+    # traces of (grad E_z . n, eps E_t . n) from both neighbours: lists per facet
+    gz = [[None] * nf, [None] * nf]
+    dn = [[None] * nf, [None] * nf]
+    seen = np.zeros(nf, dtype=int)
+    ends = [((0.0, 0.0), (1.0, 0.0)), ((1.0, 0.0), (0.0, 1.0)), ((0.0, 0.0), (0.0, 1.0))]
+    e3 = None if eps_kind == 0 else np.asarray(epsilon_r).reshape(ne, 3)
+    for k in range(3):
+        (xa, ya), (xb, yb) = ends[k]
+        Xk = np.stack([xa + sg * (xb - xa), ya + sg * (yb - ya)])
+        fns, _, _ = physical_basis(order, p, t, Xk)
+        et, _ = interpolate_mode(fns, dofs, E)  # (2, Ne, nq)
+        gzv = np.zeros((2, ne, npts), dtype=complex)
+        for l, fn in enumerate(fns):
+            if fn.kind == 1:
+                gzv += fn.grad * E[dofs[l]][None, :, None]
+        if eps_kind == 0:
+            ev = np.asarray(epsilon_r)[:, None] * np.ones(npts)[None, :]
+        else:
+            lam = np.stack([1 - Xk[0] - Xk[1], Xk[0], Xk[1]])
+            ev = e3 @ lam
+        for e in range(ne):
+            f = t2f[k, e]
+            side = seen[f]
+            seen[f] += 1
+            n = nrm[:, f]
+            gz[side][f] = gzv[0, e] * n[0] + gzv[1, e] * n[1]
+            dn[side][f] = (et[0, e] * n[0] + et[1, e] * n[1]) * ev[e]
+    tmp = np.zeros(nf)
+    for f in range(nf):
+        if seen[f] == 2:
+            val = np.abs(gz[0][f] - gz[1][f]) ** 2 + np.abs(dn[0][f] - dn[1][f]) ** 2
+            tmp[f] = np.sum(wg * length[f] * length[f] * val)
+    return np.sum(0.5 * tmp[t2f], axis=0)
 
 
 # ----------------------------------------------------------------------------- driver

@@ -581,3 +581,383 @@ def test_solver_eigen_b200_generic_stencil(ctx):
     ref = spla.eigs(K, M=M, k=4, sigma=0.05, return_eigenvectors=False)
     for lam in lams:
         assert np.min(abs(ref - lam)) < 1e-10 * abs(lam)
+
+
+# ============================================================================= round 2: BASELINE configs and branches
+def _z_rescale(b, E, lam, k0):
+    """E (un-scaled E_z) back to the solved variable E_3 = i beta E_z (waveguide.py:627 inverted)"""
+    x = np.array(E, dtype=complex)
+    x[b.split_indices()[1]] *= 1j * np.sqrt(lam / k0**4)
+    return x
+
+
+def _compare_modes_with_oracle(modes, r, m, b, wavelength, order, check_h=True, dirichlet=None):
+    """n_eff 1e-9, eigen-residual against the oracle's pencil, normalised overlap with the oracle's mode 1e-6,
+    H against the oracle's calculate_hfield 1e-9, unit power."""
+    from femwell_b200.maxwell.waveguide import speed_of_light
+
+    k0 = 2 * np.pi / wavelength
+    ed = b.element_dofs.astype(np.int64)
+    args = (m.p, m.t.astype(np.int64), ed, order, b.X, b.W)
+    idx = _match(np.array([md.k**2 for md in modes]), r.lams)
+    keep = np.ones(b.N, dtype=bool)
+    if dirichlet is not None:
+        keep[dirichlet] = False
+    for i, md in enumerate(modes):
+        j = idx[i]
+        assert abs(md.n_eff - r.n_effs[j]) < 1e-9 * abs(r.n_effs[j]), (md.n_eff, r.n_effs[j])
+        x = _z_rescale(b, md.E, md.k**2, k0)
+        res = np.linalg.norm((-(r.A @ x) + md.k**2 * (r.B @ x))[keep]) / np.linalg.norm((r.A @ x)[keep])
+        assert res < 1e-10, res
+        if dirichlet is not None:
+            assert np.all(md.E[dirichlet] == 0)
+        if check_h:
+            H_ref = fo.calculate_hfield(*args, md.E, md.k, md.k0 * speed_of_light, b.N)
+            assert np.linalg.norm(md.H - H_ref) < 1e-9 * np.linalg.norm(H_ref)
+            assert abs(md.calculate_power() - 1) < 1e-9
+            xr = _z_rescale(b, r.E[:, j], r.lams[j], k0)
+            res_ref = np.linalg.norm((-(r.A @ xr) + r.lams[j] * (r.B @ xr))[keep]) / np.linalg.norm((r.A @ xr)[keep])
+            if res_ref < 1e-9:  # ARPACK's last vectors may be polluted by null(M), DESIGN.md section 2
+                ov = fo.calculate_overlap(*args, md.E, md.H, r.E[:, j], r.H[:, j])
+                assert abs(abs(ov) - 1) < 1e-6, ov
+
+
+def test_config1_strip_5k_triangles_matches_oracle(ctx):
+    """BASELINE config 1 exactly: Si strip 500x220 nm in SiO2, lambda 1.55, 2*50^2 = 5000 triangles, order 2,
+    num_modes 2, intorder 4 (the reference's CPU-runnable case)."""
+    from femwell_b200.maxwell.waveguide import compute_modes
+
+    m, eps = strip_problem(50)
+    assert m.nelements == 5000
+    b0 = Basis(m, ElementTriP0(), intorder=4)
+    modes = compute_modes(b0, eps, 1.55, num_modes=2, order=2)
+    b = modes[0].basis
+    v0 = np.random.default_rng(0).uniform(-1, 1, b.N)
+    r = fo.compute_modes(m.p, m.t, 0, eps, 1.55, b.X, b.W, num_modes=2, order=2, v0=v0)
+    _compare_modes_with_oracle(modes, r, m, b, 1.55, 2)
+    assert modes[0].n_eff.real > modes[1].n_eff.real > 1.444  # guided, fundamental first
+    assert modes[0].te_fraction > 0.9
+
+
+def test_bend_with_pml_fields_match_oracle(ctx):
+    """config-3 style (bent_waveguide.py:73-119): DG-P1 complex eps with a PML ramp, radius 5, n_guess -- H field,
+    power normalisation and overlap with the oracle's mode, not only n_eff."""
+    from femwell_b200.maxwell.waveguide import compute_modes
+    from femwell_b200.mesh import waveguide_mesh
+
+    m = waveguide_mesh(14, slab_h=0.11, bbox=(-1.25, 4.25, -1.0, 1.22), extra_x=[2.25])
+    b0 = Basis(m, ElementDG(ElementTriP1()), intorder=4)
+    base = np.full(m.nelements, 1.0)
+    for name, nn in {"core": 3.48, "slab": 3.48, "box": 1.48, "clad": 1.0}.items():
+        base[m.subdomains[name]] = nn**2
+    eps = np.repeat(base, 3).astype(complex)
+    xv = m.p[0, m.t].T.reshape(-1)
+    eps += -10j * np.maximum(0, xv - 2.25) ** 2
+    straight = compute_modes(b0, eps, 1.55, num_modes=1, order=2)
+    bent = compute_modes(b0, eps, 1.55, num_modes=2, order=2, radius=5.0, n_guess=straight[0].n_eff)
+    b = bent[0].basis
+    v0 = np.random.default_rng(0).uniform(-1, 1, b.N)
+    r = fo.compute_modes(m.p, m.t, 1, eps, 1.55, b.X, b.W, num_modes=2, order=2, radius=5.0,
+                         n_guess=straight[0].n_eff, v0=v0)
+    _compare_modes_with_oracle(bent, r, m, b, 1.55, 2)
+    assert bent[0].n_eff.imag != 0 and bent[0].H.imag.any()
+    # lossy problem: the power is complex before normalisation, exactly 1 after (waveguide.py:636-638)
+    assert abs(bent[0].calculate_overlap(bent[0]) - 1) < 1e-9
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_anisotropic_epsilon_through_compute_modes(ctx, cplx):
+    """ElementVector(ElementTriP0(), 3): eps_t = diag(eps_0, eps_1), eps_z = eps_2 (waveguide.py:579-586,
+    waveguide_anisotropic.py:81-84) through the whole solve, not only the assembly."""
+    from femwell_b200.maxwell.waveguide import compute_modes
+
+    m, _ = strip_problem(16)
+    b0 = Basis(m, ElementVector(ElementTriP0(), 3), intorder=4)
+    eps = _make_eps(m, 2, cplx, seed=5)
+    assert eps.size == 3 * m.nelements
+    modes = compute_modes(b0, eps, 1.55, num_modes=2, order=2)
+    b = modes[0].basis
+    v0 = np.random.default_rng(0).uniform(-1, 1, b.N)
+    r = fo.compute_modes(m.p, m.t, 2, eps, 1.55, b.X, b.W, num_modes=2, order=2, v0=v0)
+    _compare_modes_with_oracle(modes, r, m, b, 1.55, 2)
+    # the isotropic solve of the same structure differs: the anisotropy really entered
+    iso = compute_modes(Basis(m, ElementTriP0(), intorder=4), eps.reshape(-1, 3)[:, 0].copy(), 1.55, num_modes=1,
+                        order=2)
+    assert abs(iso[0].n_eff - modes[0].n_eff) > 1e-4
+
+
+@pytest.mark.parametrize("case,order", [(0, 1), (2, 1), (1, 2)])
+def test_metallic_boundaries_order_1_and_2(ctx, case, order):
+    """condense on named boundaries (waveguide.py:610-619) at both orders; fields and H, not only n_eff."""
+    from femwell_b200.maxwell.waveguide import compute_modes
+
+    m, eps, bnd, fsel, ref = rectangle_problem(24, case)
+    b0 = Basis(m, ElementTriP0(), intorder=4)
+    modes = compute_modes(b0, eps, 1.5, num_modes=2, order=order, metallic_boundaries=bnd)
+    b = modes[0].basis
+    D = b.get_dofs(bnd)
+    v0 = np.random.default_rng(0).uniform(-1, 1, b.N)
+    r = fo.compute_modes(m.p, m.t, 0, eps, 1.5, b.X, b.W, num_modes=2, order=order, dirichlet_facets=fsel, v0=v0)
+    assert np.array_equal(np.sort(D), fo.boundary_dofs(order, m.nvertices, m.facets.astype(np.int64), fsel))
+    _compare_modes_with_oracle(modes, r, m, b, 1.5, order, dirichlet=D)
+    tol = 5e-5 if order == 2 else 5e-4  # n = 24: discretisation error vs the literature value (O(h^2) at order 1)
+    assert abs(modes[0].n_eff.real - ref) < tol
+
+
+def test_config2_at_scale_residual_and_leaf_size_independence(ctx):
+    """BASELINE config 2 at full size (500k triangles, order 2, 4 modes): the assembled pencil is exported and the
+    eigen-residual of every returned mode is evaluated ON THE HOST (scipy SpMV), the power normalisation is
+    re-checked, and n_eff must not depend on the nested-dissection leaf size (a different elimination order)."""
+    import sys
+
+    from femwell_b200.maxwell.waveguide import compute_modes, get_context
+
+    sys.path.insert(0, ROOT)
+    from bench import make_problem
+
+    m, eps = make_problem(500)
+    assert m.nelements == 500000
+    b0 = Basis(m, ElementTriP0(), intorder=4)
+    modes = compute_modes(b0, eps, 1.55, num_modes=4, order=2)
+    b = modes[0].basis
+    assert b.N == 3504001
+    c = get_context()
+    A, B = c.matrix(0), c.matrix(1)
+    assert A.shape == (b.N, b.N) and A.nnz > 79_000_000 and B.nnz > 28_000_000
+    k0 = 2 * np.pi / 1.55
+    for md in modes:
+        x = _z_rescale(b, md.E, md.k**2, k0)
+        Ax = A @ x
+        res = np.linalg.norm(-Ax + md.k**2 * (B @ x)) / np.linalg.norm(Ax)
+        assert res < 1e-10, res
+        assert abs(md.calculate_power() - 1) < 1e-9
+    assert modes.stats["max_residual"] < 1e-10 and modes.stats["nconv"] == 4
+    assert modes.stats["timings"]["pcg_rel_residual"] <= 1e-10
+    n1 = modes.n_effs
+    del A, B
+    other = compute_modes(b0, eps, 1.55, num_modes=4, order=2, solver_options={"leaf_elements": 32})
+    assert other.stats["lu_fronts"] != modes.stats["lu_fronts"]
+    assert np.abs(other.n_effs - n1).max() < 1e-10 * abs(n1).max()
+    # mode-field overlaps between the two solves (normalised, phase free): the same modes
+    for a, bb in zip(modes, other):
+        assert abs(abs(a.calculate_overlap(bb)) - 1) < 1e-6
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_rib_known_answers(ctx, case):
+    """The eight rib values of docs/benchmarks/mode_solver.py:52-68 at the reference's 5e-6 (:160), and the oracle's
+    value on the same mesh (tests/golden/rib_neff.json, pinned by the CPU suite) at 1e-9."""
+    import sys
+
+    from femwell_b200.maxwell.waveguide import compute_modes
+
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_rib import PAPER, SLABS, rib_problem
+
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "rib_neff.json")))
+    m, eps = rib_problem(SLABS[case])
+    modes = compute_modes(Basis(m, ElementTriP0()), eps, 1.15, num_modes=1, order=2)  # default 3-point rule
+    assert abs(modes[0].n_eff.real - PAPER[case]) < 5e-6
+    assert abs(modes[0].n_eff.real - g["oracle"][case]) < 1e-9 * g["oracle"][case]
+
+
+def test_rib_known_answer_on_a_fine_mesh(ctx):
+    """the same benchmark on a ~100k-triangle mesh the CPU oracle would not finish in test time"""
+    import sys
+
+    from femwell_b200.maxwell.waveguide import compute_modes
+
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_rib import PAPER, rib_problem
+
+    m, eps = rib_problem(0.4, h0=0.02, ratio=1.1)
+    assert m.nelements > 80000
+    modes = compute_modes(Basis(m, ElementTriP0()), eps, 1.15, num_modes=1, order=2)
+    assert abs(modes[0].n_eff.real - PAPER[4]) < 5e-6
+
+
+# ----------------------------------------------------------------------------- boundary: foreign basis, subsets, errors
+@pytest.mark.parametrize("order", [1, 2])
+def test_bridge_with_foreign_local_basis(ctx, order):
+    """compute_modes_from_skfem(tables="skfem") with duck-typed scikit-fem objects whose ``lbasis`` is a deliberately
+    different local basis of the same space: matrix entries equal the oracle driven by the same tables, n_eff is
+    invariant, and the dof vectors are those of the foreign basis (x_builtin = T^T x_foreign entity by entity)."""
+    from types import SimpleNamespace
+
+    from test_cpu import FakeSkfemElement, foreign_tables_of
+
+    from femwell_b200 import bridge
+    from femwell_b200.maxwell.waveguide import compute_modes
+
+    m, eps = strip_problem(12)
+    X, W = triangle_quadrature(4)
+    kind, vec, sc, T = foreign_tables_of(order, X, W)
+    own = Basis(m, ElementTriP0(), intorder=4).with_element(mode_element(order))
+
+    class ElementTriP0_:  # scikit-fem's class name decides the epsilon kind
+        pass
+
+    ElementTriP0_.__name__ = "ElementTriP0"
+    sk_mesh = SimpleNamespace(p=m.p, t=m.t, subdomains=dict(m.subdomains), boundaries=dict(m.boundaries))
+    sk_eps_basis = SimpleNamespace(mesh=sk_mesh, elem=ElementTriP0_(), X=X, W=W, tind=None)
+    sk_mode_basis = SimpleNamespace(elem=FakeSkfemElement(kind, vec, sc), element_dofs=own.element_dofs, N=own.N)
+    RefMode = lambda **kw: SimpleNamespace(**kw)
+    RefModes = lambda modes: list(modes)
+    got = bridge.compute_modes_from_skfem(sk_eps_basis, eps, 1.55, num_modes=2, order=order, Mode=RefMode, Modes=RefModes,
+                                          mode_basis=sk_mode_basis)
+    assert got[0].basis is sk_mode_basis and got[0].basis_epsilon_r is sk_eps_basis
+    ref = compute_modes(Basis(m, ElementTriP0(), intorder=4), eps, 1.55, num_modes=2, order=order)
+    # (a) matrices of the foreign basis vs the oracle driven by the same tables
+    from femwell_b200.maxwell.waveguide import get_context
+
+    bt = own.with_tables(kind, vec, sc, element_dofs=own.element_dofs, n_dofs=own.N)
+    c = get_context()
+    c.set_space(bt)
+    c.symbolic()
+    k0 = 2 * np.pi / 1.55
+    c.assemble(0, eps, k0)
+    A, B = c.matrix(0), c.matrix(1)
+    with fo.foreign_tables((kind, vec, sc)):
+        A_ref, B_ref = _oracle_AB(m, own, 0, eps, k0)
+    assert csr_rel_diff(A, A_ref)[0] < 1e-12 and csr_rel_diff(B, B_ref)[0] < 1e-12
+    # (b) n_eff invariant, (c) dof vectors related by the change of basis
+    ed = own.element_dofs
+    for md_f, md_b in zip(got, ref):
+        assert abs(md_f.k - md_b.k) < 1e-9 * abs(md_b.k)
+        # element-wise: local coefficients x_builtin = T^T x_foreign (up to the common phase of the eigenvector)
+        xf, xb = md_f.E[ed], md_b.E[ed]  # (nb, Ne)
+        xb_from_f = T.T @ xf
+        ph = np.vdot(xb_from_f.ravel(), xb.ravel())
+        ph /= abs(ph)
+        assert np.abs(xb_from_f * ph - xb).max() < 1e-7 * np.abs(xb).max()
+        hb_from_f = T.T @ md_f.H[ed]
+        assert np.abs(hb_from_f * ph - md_b.H[ed]).max() < 1e-7 * np.abs(md_b.H[ed]).max()
+
+
+def test_element_subset_of_the_basis_is_honoured(ctx):
+    """basis_epsilon_r.with_element keeps ``tind`` (waveguide.py:574): the forms are assembled over the subset only.
+    The reference's pencil then has empty rows for every dof outside the subset and scipy's splu raises
+    RuntimeError("Factor is exactly singular"); so does the GPU factorisation."""
+    from femwell_b200.maxwell.waveguide import compute_modes, get_context
+
+    m, eps = strip_problem(10)
+    sel = np.nonzero(m.centroids()[0] < 0.4)[0].astype(np.int32)
+    b0 = Basis(m, ElementTriP0(), intorder=4, elements=sel)
+    b = b0.with_element(mode_element(2))
+    assert np.array_equal(b.tind, sel)
+    c = get_context()
+    c.set_space(b)
+    c.symbolic()
+    k0 = 2 * np.pi / 1.55
+    c.assemble(0, eps, k0)
+    A, B = c.matrix(0), c.matrix(1)
+    ed = b.element_dofs.astype(np.int64)
+    eq = fo.interpolate_eps(0, eps[sel], sel.size, b.X)
+    A_ref, B_ref = fo.assemble_waveguide(m.p, m.t.astype(np.int64), ed, 2, b.X, b.W, eq, k0, n=b.N, subset=sel)
+    assert csr_rel_diff(A, A_ref)[0] < 1e-12 and csr_rel_diff(B, B_ref)[0] < 1e-12
+    assert _pattern_diff_is_roundoff(A, A_ref)[0]
+    untouched = np.setdiff1d(np.arange(b.N), np.unique(ed[:, sel]))
+    assert untouched.size > 0 and A[untouched].nnz == 0
+    with pytest.raises(RuntimeError, match="Factor is exactly singular"):
+        compute_modes(b0, eps, 1.55, num_modes=1, order=2)
+    # the whole mesh given as an explicit element list is the ordinary solve
+    full = compute_modes(Basis(m, ElementTriP0(), intorder=4, elements=np.arange(m.nelements)), eps, 1.55, order=2)
+    plain = compute_modes(Basis(m, ElementTriP0(), intorder=4), eps, 1.55, order=2)
+    assert abs(full[0].n_eff - plain[0].n_eff) < 1e-12
+
+
+def test_no_convergence_raises_arpack_compatible_error_with_partial_pairs(ctx):
+    """scipy raises ArpackNoConvergence carrying the converged pairs (arpack.py:303-329)."""
+    from scipy.sparse.linalg import ArpackNoConvergence
+
+    from femwell_b200.maxwell.waveguide import compute_modes
+
+    m, eps = strip_problem(16)
+    b0 = Basis(m, ElementTriP0(), intorder=4)
+    with pytest.raises(ArpackNoConvergence) as ei:
+        compute_modes(b0, eps, 1.55, num_modes=6, order=2, solver_options={"ncv": 8, "maxiter": 1, "tol": 1e-15})
+    e = ei.value
+    assert isinstance(e, RuntimeError) and e.code == -3
+    n = Basis(m, mode_element(2)).N
+    nconv = e.eigenvalues.shape[0]
+    assert 0 <= nconv < 6 and e.eigenvectors.shape == (n, nconv)
+    if nconv:
+        good = compute_modes(b0, eps, 1.55, num_modes=6, order=2)
+        lam = np.array([md.k**2 for md in good])
+        for z in e.eigenvalues:
+            assert np.min(abs(lam - z)) < 1e-8 * abs(z)
+    # the handle stays usable
+    assert compute_modes(b0, eps, 1.55, num_modes=1, order=2)[0].n_eff.real > 1.444
+
+
+def test_hfield_rejects_non_finite_input_and_reports_pcg_stats(ctx):
+    """The mass PCG must not return an unconverged H silently."""
+    from femwell_b200._lib import FemwellB200Error
+    from femwell_b200.maxwell.waveguide import calculate_hfield, compute_modes, get_context, speed_of_light
+
+    m, eps = strip_problem(12)
+    b0 = Basis(m, ElementTriP0(), intorder=4)
+    modes = compute_modes(b0, eps, 1.55, num_modes=2, order=2)
+    t = modes.stats["timings"]
+    assert 0 < t["pcg_iterations"] < 600 and t["pcg_rel_residual"] <= 1e-10
+    md = modes[0]
+    bad = md.E.copy()
+    bad[7] = np.nan
+    with pytest.raises(FemwellB200Error):
+        calculate_hfield(md.basis, bad, md.k, md.k0 * speed_of_light)
+    # tighter and looser tolerances both land on the oracle's H within their own accuracy
+    H13 = compute_modes(b0, eps, 1.55, num_modes=2, order=2, solver_options={"pcg_tol_exp": 13})[0].H
+    H6 = compute_modes(b0, eps, 1.55, num_modes=2, order=2, solver_options={"pcg_tol_exp": 6})[0].H
+    get_context().set_option(1, 10)
+    ph = np.vdot(H13, md.H)
+    ph /= abs(ph)
+    assert np.linalg.norm(H13 * ph - md.H) < 1e-8 * np.linalg.norm(md.H)
+    ph6 = np.vdot(H13, H6)
+    ph6 /= abs(ph6)
+    assert 1e-13 < np.linalg.norm(H13 * ph6 - H6) / np.linalg.norm(H6) < 1e-4
+
+
+def test_real_problem_returns_real_transverse_field(ctx):
+    """real eps: ARPACK's real driver returns real eigenvectors for real eigenvalues; after the E_z un-scaling E_t is
+    real and E_z imaginary up to one global phase, and the packed real PCG (two real systems per complex slot) must
+    reproduce the general complex PCG."""
+    import os as _os
+
+    from femwell_b200.maxwell.waveguide import compute_modes
+
+    m, eps = strip_problem(14)
+    b0 = Basis(m, ElementTriP0(), intorder=4)
+    modes = compute_modes(b0, eps, 1.55, num_modes=3, order=2)
+    b = modes[0].basis
+    td, zd = b.split_indices()
+    for md in modes:
+        assert md.k.imag == 0
+        assert np.abs(md.E[td].imag).max() == 0 and np.abs(md.E[zd].real).max() == 0
+        assert np.abs(md.H[td].imag).max() == 0 and np.abs(md.H[zd].real).max() == 0
+
+
+@pytest.mark.parametrize("order,eps_kind,cplx", [(1, 0, False), (2, 0, False), (2, 1, True), (1, 1, False)])
+def test_error_estimator_matches_oracle(ctx, order, eps_kind, cplx):
+    """Mode.eval_error_estimator (waveguide.py:473-502) on a solved mode and on a random field."""
+    from femwell_b200.maxwell.waveguide import Mode, compute_modes
+
+    m, _ = strip_problem(12, jitter=0.15)
+    elem = ElementTriP0() if eps_kind == 0 else ElementDG(ElementTriP1())
+    b0 = Basis(m, elem, intorder=4)
+    eps = _make_eps(m, eps_kind, cplx, seed=7)
+    modes = compute_modes(b0, eps, 1.55, num_modes=1, order=order)
+    md = modes[0]
+    b = md.basis
+    ed = b.element_dofs.astype(np.int64)
+    eta = md.eval_error_estimator()
+    ref = fo.eval_error_estimator(m.p, m.t, ed, order, md.E, eps_kind, eps)
+    assert eta.shape == (m.nelements,) and np.all(eta >= 0)
+    assert np.abs(eta - ref).max() < 1e-10 * ref.max()
+    # the indicator concentrates where the field is: the element with the largest value touches the core region
+    c = m.centroids()[:, int(np.argmax(eta))]
+    assert abs(c[0]) < 0.6 and -0.3 < c[1] < 0.6
+    rng = np.random.default_rng(5)
+    E = rng.standard_normal(b.N) + 1j * rng.standard_normal(b.N)
+    rnd = Mode(frequency=1.0, k=1.0, basis_epsilon_r=md.basis_epsilon_r, epsilon_r=eps, basis=b, E=E, H=E)
+    ref2 = fo.eval_error_estimator(m.p, m.t, ed, order, E, eps_kind, eps)
+    assert np.abs(rnd.eval_error_estimator() - ref2).max() < 1e-11 * ref2.max()
