@@ -63,7 +63,7 @@ class FwTimings(C.Structure):
         ("total_ms", c_f64), ("download_ms", c_f64), ("element_kernel_launches", c_i64),
         ("kernel_launches", c_i64), ("nnz_structural", c_i64),
         ("lu_solve_entries", c_i64), ("lu_factor_flops", c_f64), ("pcg_iterations", c_i64),
-        ("pcg_rel_residual", c_f64), ("hfield_ms", c_f64),
+        ("pcg_rel_residual", c_f64), ("hfield_ms", c_f64), ("mass_direct_blocks", c_i64),
     ]
 
     def as_dict(self):

@@ -270,6 +270,7 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
   upload_staged(h, sp.t.p, sp.h_t.data(), sp.h_t.size() * sizeof(int));
   upload_staged(h, sp.edofs.p, sp.h_edofs.data(), sp.h_edofs.size() * sizeof(int));
   upload_staged(h, sp.is_z.p, isz.data(), isz.size());
+  sp.h_is_z = isz;
   FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
   sp.valid = true;
   h.generic.valid = false;
@@ -323,6 +324,10 @@ int fw_set_option(fw_handle* hh, int32_t option, int32_t value) {
   switch (option) {
     case FW_OPT_ELIMINATE_ZEROS:
       hh->h.eliminate_zeros = value != 0;
+      break;
+    case FW_OPT_MASS_SOLVER:
+      FW_REQUIRE(value >= 0 && value <= 2, "mass solver: 0 auto, 1 PCG, 2 direct");
+      hh->h.mass_solver = value;
       break;
     case FW_OPT_PCG_TOL_EXP:
       FW_REQUIRE(value >= 1 && value <= 15, "PCG tolerance exponent out of range (1..15)");

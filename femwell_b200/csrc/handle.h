@@ -35,6 +35,7 @@ struct Space {
   std::vector<double> vec, sc, X, W;
   std::vector<double> h_p;
   std::vector<int> h_t, h_edofs;
+  std::vector<uint8_t> h_is_z;  // [n] 1 for Lagrange (E_z) dofs (host copy of is_z)
   DevBuf<double> p;
   DevBuf<int> t, edofs;
   DevBuf<uint8_t> is_z;  // [n] 1 for Lagrange (E_z) dofs
@@ -60,6 +61,7 @@ struct Handle {
   Pattern pat;
   bool has_symbolic = false;
   bool eliminate_zeros = true;  // export semantics of scipy's coo.eliminate_zeros()
+  int mass_solver = 0;          // FW_OPT_MASS_SOLVER: 0 PCG with direct fallback, 1 PCG only, 2 direct (sparse LU)
   double pcg_tol = 1e-10;       // relative residual of the H-field mass solves (FW_OPT_PCG_TOL_EXP)
   Values A, B, Mass, C0, C1;
   // mass matrix without the structurally-zero cross blocks (own compact CSR; used by the PCG of the H field)

@@ -73,6 +73,9 @@ void lu_analyse_prefetch(Handle& h, const std::vector<uint8_t>& active, int leaf
 // factor OP = alphaA * A + alphaB * B (values on the structural pattern h.pat)
 void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements);
 void lu_factor(Handle& h, double alphaA_re, double alphaA_im, double alphaB_re, double alphaB_im, bool complex_arith);
+// the same for any two value arrays on the structural pattern (the H-field fallback factors the mass matrix)
+void lu_factor_values(Handle& h, const Values& VA, const Values& VB, double alphaA_re, double alphaA_im,
+                      double alphaB_re, double alphaB_im, bool complex_arith);
 // solve OP x = b for nrhs right-hand sides given in ORIGINAL dof order on the device
 // (b, x: [nrhs][n] of the LU scalar type; x[inactive] = 0).  b and x may alias.
 void lu_solve_dev(Handle& h, const void* b, void* x, int nrhs);

@@ -760,7 +760,7 @@ __global__ void __launch_bounds__(32) k_lu_diag_inverse(FrontTab T, const int* _
 }
 
 template <class S, class V>
-static void factor_typed(Handle& h, S alphaA, S alphaB) {
+static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA, S alphaB) {
   LU& lu = *h.lu;
   LUDevice& d = *lu.dev;
   const LUSymbolic& Sy = lu.sym;
@@ -776,15 +776,15 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
   FrontTab T = d.tab();
   const Pattern& pat = h.pat;
   k_lu_scatter<S, V><<<cdiv((int64_t)pat.n * 8, 256), 256, 0, s>>>(pat.n, pat.indptr.p, pat.indices.p,
-                                                                  (const V*)h.A.v.p, (const V*)h.B.v.p, alphaA, alphaB,
+                                                                  (const V*)VA.v.p, (const V*)VB.v.p, alphaA, alphaB,
                                                                   T, d.iperm.p, d.node_of.p, F);
   FW_CHECK_CUDA(cudaGetLastError());
   // pivot threshold relative to the largest entry of the pencil
   DevBuf<double> amax;
   amax.alloc(2);
   amax.zero(s);
-  k_absmax<V><<<296, 256, 0, s>>>((const V*)h.A.v.p, pat.nnz, amax.p);
-  k_absmax<V><<<296, 256, 0, s>>>((const V*)h.B.v.p, pat.nnz, amax.p + 1);
+  k_absmax<V><<<296, 256, 0, s>>>((const V*)VA.v.p, pat.nnz, amax.p);
+  k_absmax<V><<<296, 256, 0, s>>>((const V*)VB.v.p, pat.nnz, amax.p + 1);
   double am[2] = {0, 0};
   amax.download(am, 2, s);
   FW_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -886,19 +886,25 @@ static void factor_typed(Handle& h, S alphaA, S alphaB) {
   h.tim.kernel_launches += launches;
 }
 
-void lu_factor(Handle& h, double aAr, double aAi, double aBr, double aBi, bool complex_arith) {
+void lu_factor_values(Handle& h, const Values& VA, const Values& VB, double aAr, double aAi, double aBr, double aBi,
+                      bool complex_arith) {
   FW_REQUIRE(h.lu && h.lu->dev, "lu_analyse must run first");
-  FW_REQUIRE(h.A.valid && h.B.valid, "A and B must be assembled");
+  FW_REQUIRE(VA.valid && VB.valid && VA.is_complex == VB.is_complex, "operators must be assembled (same scalar type)");
   LU& lu = *h.lu;
-  const bool vals_complex = h.A.is_complex;
+  const bool vals_complex = VA.is_complex;
   if (vals_complex || aAi != 0.0 || aBi != 0.0) complex_arith = true;
   lu.is_complex = complex_arith;
   if (!complex_arith)
-    factor_typed<double, double>(h, aAr, aBr);
+    factor_typed<double, double>(h, VA, VB, aAr, aBr);
   else if (!vals_complex)
-    factor_typed<cplx, double>(h, cplx{aAr, aAi}, cplx{aBr, aBi});
+    factor_typed<cplx, double>(h, VA, VB, cplx{aAr, aAi}, cplx{aBr, aBi});
   else
-    factor_typed<cplx, cplx>(h, cplx{aAr, aAi}, cplx{aBr, aBi});
+    factor_typed<cplx, cplx>(h, VA, VB, cplx{aAr, aAi}, cplx{aBr, aBi});
+}
+
+void lu_factor(Handle& h, double aAr, double aAi, double aBr, double aBi, bool complex_arith) {
+  FW_REQUIRE(h.A.valid && h.B.valid, "A and B must be assembled");
+  lu_factor_values(h, h.A, h.B, aAr, aAi, aBr, aBi, complex_arith);
 }
 
 // ---- debug export (tests only): factor arena and pivot vector

@@ -13,6 +13,7 @@
 // sums are produced by the SpMV itself.  HBM-bound: nnz*12 + ~9 k N 16 bytes per iteration, 5 launches.
 #include <algorithm>
 
+#include "lu.h"
 #include "solver.h"
 
 namespace fw {
@@ -254,8 +255,11 @@ struct CsrView {
   int n_full;       // leading dimension of those arrays
 };
 
+// returns false when the iteration does not reach the tolerance (stagnation on badly shaped meshes: the condition
+// number of the diagonally scaled Nedelec mass matrix grows with the square of the element aspect ratio) -- the
+// caller then falls back to a direct solve; X is left untouched in that case
 template <int K>
-static void mass_solve_k(Handle& h, int n, const CsrView& M, const cplx* B, cplx* X) {
+static bool mass_solve_k(Handle& h, int n, const CsrView& M, const cplx* B, cplx* X) {
   cudaStream_t s = h.stream;
   const int nblk = cdiv((int64_t)n * K, 1024);
   const int nblk_mv = cdiv(n, 256 / (2 * K));
@@ -324,19 +328,35 @@ static void mass_solve_k(Handle& h, int n, const CsrView& M, const cplx* B, cplx
     k_cg_direction<K><<<cdiv((int64_t)n * K, 256), 256, 0, s>>>(n, (double2*)pv, (const double2*)zv, d_rz[cur ^ 1], d_rz[cur]);
     cur ^= 1;
     launches += 5;
-    if ((it + 1) % check_every == 0 && check()) {
-      converged = true;
-      ++it;
-      break;
+    if ((it + 1) % check_every == 0) {
+      if (check()) {
+        converged = true;
+        ++it;
+        break;
+      }
+      // give up early when the observed rate cannot reach the tolerance within max_it iterations
+      if (it + 1 >= 48 && worst > 0 && worst < 1.0) {
+        const double need = (it + 1) * std::log(h.pcg_tol) / std::log(worst);
+        if (need > max_it) {
+          ++it;
+          break;
+        }
+      } else if (it + 1 >= 48 && !(worst < 1.0)) {
+        ++it;
+        break;
+      }
     }
   }
   if (!converged) converged = check();  // the loop may end between two checks (or without any iteration)
   tr.mark("    mass PCG: iterations");
   h.tim.pcg_iterations = std::max<int64_t>(h.tim.pcg_iterations, it);
-  if (!(worst <= h.tim.pcg_rel_residual)) h.tim.pcg_rel_residual = worst;
-  if (!converged)
-    throw Error(FW_ERR_NOCONV, "mass PCG (H field) did not converge: ||r||/||b|| = " + std::to_string(worst) + " after " +
-                                   std::to_string(it) + " iterations (tolerance " + std::to_string(h.pcg_tol) + ")");
+  if (converged && !(worst <= h.tim.pcg_rel_residual)) h.tim.pcg_rel_residual = worst;
+  if (!converged) {
+    if (getenv("FW_TRACE"))
+      fprintf(stderr, "[fw-trace]   mass PCG: gave up after %d iterations at rel. residual %.2e\n", it, worst);
+    h.tim.kernel_launches += launches;
+    return false;
+  }
   k_cg_interleave<K><<<g256, 256, 0, s>>>(n, xv, X, false, M.idx, M.n_full);
   ++launches;
   FW_CHECK_CUDA(cudaGetLastError());
@@ -344,29 +364,136 @@ static void mass_solve_k(Handle& h, int n, const CsrView& M, const cplx* B, cplx
   if (getenv("FW_TRACE"))
     fprintf(stderr, "[fw-trace]   mass PCG: %d rhs, %d iterations, rel. residual %.2e, %lld kernel launches, mass nnz %lld\n",
             K, it, worst, (long long)launches, (long long)M.nnz);
+  return true;
 }
 
 // M X = B for a real SPD CSR matrix and k <= CG_MAXK complex right-hand sides ([k][n] each); X overwritten.
-static void pcg_solve_view(Handle& h, int n_rows, const CsrView& V, int k, const cplx* B, cplx* X);
+// Returns false when the PCG does not converge (X then holds nothing useful for the rows of this system).
+static bool pcg_solve_view(Handle& h, int n_rows, const CsrView& V, int k, const cplx* B, cplx* X);
+
+[[noreturn]] static void pcg_failed(const Handle& h, const char* what) {
+  throw Error(FW_ERR_NOCONV, std::string(what) + ": the mass PCG did not converge (tolerance " + std::to_string(h.pcg_tol) + ")");
+}
+
+// ---- direct fallback for one diagonal block of the mass matrix (Nedelec or Lagrange dofs): the multifrontal LU of
+// the eigen-solve factors the block (the dofs of the other block are "inactive") -- what the reference does for every
+// mode (scipy spsolve, waveguide.py:671).  Used when the PCG stagnates: on graded meshes with elongated triangles the
+// diagonally scaled Nedelec mass matrix is ill conditioned (kappa ~ aspect ratio squared).
+__global__ void __launch_bounds__(256) k_split_re_im(int n, const cplx* __restrict__ b, double* __restrict__ out2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const cplx v = b[i];
+  out2[i] = v.re;
+  out2[(size_t)n + i] = v.im;
+}
+// X[d] (+)= (x2[0][d], x2[1][d]) for the dofs of the block
+__global__ void __launch_bounds__(256) k_merge_re_im(int n, const double* __restrict__ x2, const uint8_t* __restrict__ is_z,
+                                                     int block_z, bool add, cplx* __restrict__ X) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || (is_z[i] != 0) != (block_z != 0)) return;
+  cplx v{x2[i], x2[(size_t)n + i]};
+  if (add) v = v + X[i];
+  X[i] = v;
+}
+// r = b - M x on the rows of the block (M = full mass matrix on the structural pattern: the cross blocks are zeros)
+__global__ void __launch_bounds__(256) k_mass_residual(int n, const int* __restrict__ indptr, const int* __restrict__ indices,
+                                                       const double* __restrict__ vals, const cplx* __restrict__ x,
+                                                       const cplx* __restrict__ b, const uint8_t* __restrict__ is_z,
+                                                       int block_z, cplx* __restrict__ r, double* __restrict__ norms) {
+  __shared__ double red[8];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double rr = 0.0, bb = 0.0;
+  if (i < n) {
+    cplx res{0.0, 0.0};
+    if ((is_z[i] != 0) == (block_z != 0)) {
+      cplx acc{0.0, 0.0};
+      for (int e = indptr[i]; e < indptr[i + 1]; ++e) fma_(acc, x[indices[e]], vals[e]);
+      res = b[i] - acc;
+      rr = abs2_(res), bb = abs2_(b[i]);
+    }
+    r[i] = res;
+  }
+  rr = block_sum_256(rr, red);
+  bb = block_sum_256(bb, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&norms[0], rr);
+    atomicAdd(&norms[1], bb);
+  }
+}
+
+static void mass_solve_direct(Handle& h, bool block_z, int k, const cplx* B, cplx* X) {
+  const Space& sp = h.sp;
+  const int n = sp.n;
+  cudaStream_t s = h.stream;
+  FW_REQUIRE((int)sp.h_is_z.size() == n, "space missing");
+  Trace tr(s);
+  std::vector<uint8_t> active((size_t)n);
+  for (int d = 0; d < n; ++d) active[d] = (sp.h_is_z[d] != 0) == block_z ? 1 : 0;
+  lu_analyse(h, active, 0);
+  lu_factor_values(h, h.Mass, h.Mass, 1.0, 0.0, 0.0, 0.0, false);
+  tr.mark("    mass direct: analysis + factorisation of the block");
+  const Pattern& pat = h.pat;
+  DevBuf<double> b2, x2, rbuf, nrm;
+  b2.alloc((size_t)2 * n), x2.alloc((size_t)2 * n), rbuf.alloc((size_t)2 * n), nrm.alloc(2);
+  const int g = cdiv(n, 256);
+  for (int r = 0; r < k; ++r) {
+    const cplx* b = B + (size_t)r * n;
+    cplx* x = X + (size_t)r * n;
+    k_split_re_im<<<g, 256, 0, s>>>(n, b, b2.p);
+    lu_solve_dev(h, b2.p, x2.p, 2);
+    k_merge_re_im<<<g, 256, 0, s>>>(n, x2.p, sp.is_z.p, block_z, false, x);
+    double rel = 0.0;
+    for (int it = 0; it < 3; ++it) {  // residual check + iterative refinement
+      nrm.zero(s);
+      k_mass_residual<<<g, 256, 0, s>>>(n, pat.indptr.p, pat.indices.p, h.Mass.v.p, x, b, sp.is_z.p, block_z,
+                                        (cplx*)rbuf.p, nrm.p);
+      double nn[2];
+      nrm.download(nn, 2, s);
+      FW_CHECK_CUDA(cudaStreamSynchronize(s));
+      rel = nn[1] > 0 ? std::sqrt(nn[0] / nn[1]) : std::sqrt(nn[0]);
+      if (!std::isfinite(rel)) throw Error(FW_ERR_INVALID, "mass solve (H field): non-finite right-hand side");
+      if (rel <= h.pcg_tol || it == 2) break;
+      k_split_re_im<<<g, 256, 0, s>>>(n, (const cplx*)rbuf.p, b2.p);
+      lu_solve_dev(h, b2.p, x2.p, 2);
+      k_merge_re_im<<<g, 256, 0, s>>>(n, x2.p, sp.is_z.p, block_z, true, x);
+    }
+    if (!(rel <= std::max(h.pcg_tol, 1e-9)))
+      throw Error(FW_ERR_NOCONV, "mass solve (H field): the direct fallback misses the tolerance, ||r||/||b|| = " +
+                                     std::to_string(rel));
+    if (!(rel <= h.tim.pcg_rel_residual)) h.tim.pcg_rel_residual = rel;
+  }
+  h.lu->factored = false;  // the arena no longer holds the factors of the shifted pencil
+  FW_CHECK_CUDA(cudaGetLastError());
+  h.tim.kernel_launches += 6 * k;
+  tr.mark("    mass direct: solves");
+}
 
 void mass_solve_multi(Handle& h, int k, const cplx* B, cplx* X) {
   FW_REQUIRE(h.Mass.valid && h.MassC.valid, "mass matrix missing");
+  const bool force_direct = h.mass_solver == 2, pcg_only = h.mass_solver == 1;
   if (h.mass_split) {
     // Nedelec and Lagrange blocks as two independent systems (every dof belongs to exactly one of them)
+    int blk = 0;
     for (const Handle::MassBlock* b : {&h.MassN, &h.MassP}) {
       const CsrView V{b->indptr.p, b->indices.p, b->vals.p, b->nnz, b->pair.n ? b->pair.p : nullptr, b->idx.p, h.sp.n};
-      pcg_solve_view(h, b->n, V, k, B, X);
+      if (force_direct || !pcg_solve_view(h, b->n, V, k, B, X)) {
+        if (pcg_only) pcg_failed(h, "H field");
+        mass_solve_direct(h, blk == 1, k, B, X);
+        h.tim.mass_direct_blocks += 1;
+      }
+      ++blk;
     }
     return;
   }
-  pcg_solve_multi(h, h.sp.n, h.MassC.indptr.p, h.MassC.indices.p, h.MassC.vals.p, h.MassC.nnz, k, B, X,
-                  h.MassC.pair.n ? h.MassC.pair.p : nullptr);
+  const CsrView V{h.MassC.indptr.p, h.MassC.indices.p, h.MassC.vals.p, h.MassC.nnz,
+                  h.MassC.pair.n ? h.MassC.pair.p : nullptr, nullptr, h.sp.n};
+  if (!pcg_solve_view(h, h.sp.n, V, k, B, X)) pcg_failed(h, "H field");
 }
 
 void pcg_solve_multi(Handle& h, int n_rows, const int* indptr, const int* indices, const double* vals, int64_t nnz,
                      int k, const cplx* B, cplx* X, const int* pair) {
   const CsrView V{indptr, indices, vals, nnz, pair, nullptr, n_rows};
-  pcg_solve_view(h, n_rows, V, k, B, X);
+  if (!pcg_solve_view(h, n_rows, V, k, B, X)) pcg_failed(h, "P1 projection");
 }
 
 // ---- real packing.  With a real permittivity the modes come out of the real-arithmetic Arnoldi as real vectors, so
@@ -431,9 +558,9 @@ __global__ void __launch_bounds__(256) k_cg_unpack_real(int n, int k, const cplx
   }
 }
 
-static void pcg_solve_groups(Handle& h, int n_rows, const CsrView& V, int k, const cplx* B, cplx* X);
+static bool pcg_solve_groups(Handle& h, int n_rows, const CsrView& V, int k, const cplx* B, cplx* X);
 
-static void pcg_solve_view(Handle& h, int n_rows, const CsrView& V, int k, const cplx* B, cplx* X) {
+static bool pcg_solve_view(Handle& h, int n_rows, const CsrView& V, int k, const cplx* B, cplx* X) {
   FW_REQUIRE(k >= 1 && k <= CG_MAXK, "pcg_solve_multi: 1 <= k <= 8");
   static const bool no_pack = getenv("FW_PCG_NO_PACK") != nullptr;
   if (k >= 2 && !no_pack) {
@@ -463,33 +590,36 @@ static void pcg_solve_view(Handle& h, int n_rows, const CsrView& V, int k, const
       xp.alloc((size_t)2 * V.n_full * k2);
       const int g = cdiv(n_rows, 256);
       k_cg_pack_real<<<g, 256, 0, s>>>(n_rows, k, B, V.idx, V.n_full, sel, (cplx*)bp.p);
-      pcg_solve_groups(h, n_rows, V, k2, (const cplx*)bp.p, (cplx*)xp.p);
+      if (!pcg_solve_groups(h, n_rows, V, k2, (const cplx*)bp.p, (cplx*)xp.p)) return false;
       k_cg_unpack_real<<<g, 256, 0, s>>>(n_rows, k, (const cplx*)xp.p, V.idx, V.n_full, sel, X);
       FW_CHECK_CUDA(cudaGetLastError());
       h.tim.kernel_launches += 2;
-      return;
+      return true;
     }
   }
-  pcg_solve_groups(h, n_rows, V, k, B, X);
+  return pcg_solve_groups(h, n_rows, V, k, B, X);
 }
 
-static void pcg_solve_groups(Handle& h, int n_rows, const CsrView& V, int k, const cplx* B, cplx* X) {
+static bool pcg_solve_groups(Handle& h, int n_rows, const CsrView& V, int k, const cplx* B, cplx* X) {
   const size_t n = (size_t)V.n_full;  // stride between the systems in B and X
   // systems are solved in groups of 4 / 2 / 1 (compile-time interleave factor)
   int done = 0;
   while (done < k) {
     const int left = k - done;
+    bool ok;
     if (left >= 4) {
-      mass_solve_k<4>(h, n_rows, V, B + done * n, X + done * n);
+      ok = mass_solve_k<4>(h, n_rows, V, B + done * n, X + done * n);
       done += 4;
     } else if (left >= 2) {
-      mass_solve_k<2>(h, n_rows, V, B + done * n, X + done * n);
+      ok = mass_solve_k<2>(h, n_rows, V, B + done * n, X + done * n);
       done += 2;
     } else {
-      mass_solve_k<1>(h, n_rows, V, B + done * n, X + done * n);
+      ok = mass_solve_k<1>(h, n_rows, V, B + done * n, X + done * n);
       done += 1;
     }
+    if (!ok) return false;
   }
+  return true;
 }
 
 }  // namespace fw

@@ -211,6 +211,7 @@ void hfield_multi_dev(Handle& h, int k, const cplx* E_dev, const cplx* betas, do
   Timer th(h.stream);
   h.tim.pcg_iterations = 0;
   h.tim.pcg_rel_residual = 0.0;
+  h.tim.mass_direct_blocks = 0;
   assemble_aux(h);
   tr.mark("  hfield: aux operators");
   const int n = h.sp.n;

@@ -67,7 +67,11 @@ enum {
   FW_OPT_ELIMINATE_ZEROS = 0,
   /* relative residual 10^-value of the H-field mass solves (block PCG replacing the spsolve of waveguide.py:671);
    * default 10: the reference's H carries complex64 rounding (1e-7, :658,:666)                                  */
-  FW_OPT_PCG_TOL_EXP = 1
+  FW_OPT_PCG_TOL_EXP = 1,
+  /* H-field mass solves: 0 (default) block PCG, falling back to the sparse LU of the mass block when the PCG stagnates
+   * (elongated triangles: the Nedelec mass matrix is ill conditioned); 1 PCG only (FW_ERR_NOCONV on stagnation);
+   * 2 always the direct solve (what the reference does: spsolve, waveguide.py:671)                              */
+  FW_OPT_MASS_SOLVER = 2
 };
 int fw_set_option(fw_handle* h, int32_t option, int32_t value);
 
@@ -236,6 +240,7 @@ typedef struct {
   int64_t pcg_iterations;
   double pcg_rel_residual;
   double hfield_ms;      /* calculate_hfield part of postprocess_ms                                             */
+  int64_t mass_direct_blocks; /* mass blocks that went through the direct (sparse LU) solve in the last H-field     */
 } fw_timings;
 int fw_get_timings(fw_handle* h, fw_timings* t);
 
