@@ -110,7 +110,7 @@ EXPORTS = [
     "fw_symbolic", "fw_assemble_waveguide", "fw_matrix_nnz", "fw_matrix_export", "fw_coo_to_csr",
     "fw_coo_to_csr_export", "fw_matrix_spmv", "fw_bench_spmv", "fw_eigs", "fw_eigs_csr", "fw_lu_factor_shifted", "fw_lu_solve",
     "fw_postprocess_modes", "fw_hfield", "fw_functional", "fw_error_estimator", "fw_intensity", "fw_poynting", "fw_overlap_cross", "fw_energy_current_density", "fw_compute_modes", "fw_get_timings",
-    "fw_host_dense_eig", "fw_debug_lu_symbolic", "fw_debug_lu_symbolic_get", "fw_debug_lu_get",
+    "fw_host_dense_eig", "fw_debug_lu_symbolic", "fw_debug_lu_symbolic_get", "fw_debug_lu_analysis", "fw_debug_lu_analysis_get", "fw_debug_lu_get",
 ]
 
 _lib = None

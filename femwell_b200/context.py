@@ -162,6 +162,24 @@ class Context:
         L.check(self.lib.fw_coo_to_csr_export(self._h, L.ptr(indptr), L.ptr(indices), L.ptr(out)))
         return sp.csr_matrix((out, indices, indptr), shape=(n_rows, n_rows))
 
+    def debug_lu_analysis(self, dirichlet=None, leaf_elements=0) -> dict:
+        """tests: run the sparse-LU analysis of the current space on the device and download its tables"""
+        d = None if dirichlet is None else L.as_i32(dirichlet)
+        sizes = np.zeros(8, dtype=np.int64)
+        L.check(self.lib.fw_debug_lu_analysis(self._h, 0 if d is None else d.size, L.ptr(d), int(leaf_elements),
+                                              L.ptr(sizes)))
+        na, nn, nl, nbl = (int(x) for x in sizes[:4])
+        out = dict(n_active=na, n_nodes=nn, n_levels=nl, factor_entries=int(sizes[4]), max_m=int(sizes[6]),
+                   max_ns=int(sizes[7]))
+        for name, which, size, dt in [("perm", 0, na, np.int32), ("iperm", 1, self.n, np.int32),
+                                      ("node_of", 2, na, np.int32), ("m", 7, nn, np.int32), ("ns", 8, nn, np.int32),
+                                      ("own_start", 9, nn, np.int32), ("blist", 10, nbl, np.int32),
+                                      ("rel", 11, nbl, np.int32), ("blist_off", 21, nn, np.int64)]:
+            a = np.zeros(max(size, 1), dtype=dt)
+            L.check(self.lib.fw_debug_lu_analysis_get(self._h, which, L.ptr(a)))
+            out[name] = a[:size]
+        return out
+
     # ---------------------------------------------------------------- LU / eigs
     def lu_factor(self, sigma, dirichlet=None, leaf_elements=0):
         d = None if dirichlet is None else L.as_i32(dirichlet)

@@ -917,6 +917,35 @@ int fw_debug_lu_symbolic_get(int32_t which, void* out) {
   FW_API_END
 }
 
+int fw_debug_lu_analysis(fw_handle* hh, int32_t n_dirichlet, const int32_t* dirichlet, int32_t leaf_elements,
+                         int64_t* sizes) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && sizes && (n_dirichlet == 0 || dirichlet), "NULL argument");
+  Handle& h = hh->h;
+  FW_CHECK_CUDA(cudaSetDevice(h.device));
+  current_pool() = &h.pool;
+  FW_REQUIRE(h.sp.valid, "fw_set_space must be called first");
+  std::vector<uint8_t> active((size_t)h.sp.n, 1);
+  for (int i = 0; i < n_dirichlet; ++i) {
+    FW_REQUIRE(dirichlet[i] >= 0 && dirichlet[i] < h.sp.n, "dirichlet dof out of range");
+    active[dirichlet[i]] = 0;
+  }
+  h.lu.reset();  // never reuse: this call exists to look at a fresh analysis
+  lu_analyse(h, active, leaf_elements);
+  const LUSymbolic& S = h.lu->sym;
+  sizes[0] = S.n_active, sizes[1] = S.n_nodes, sizes[2] = S.n_levels, sizes[3] = S.work_entries - S.n_active;
+  sizes[4] = S.factor_entries, sizes[5] = S.work_entries, sizes[6] = S.max_m, sizes[7] = S.max_ns;
+  FW_API_END
+}
+int fw_debug_lu_analysis_get(fw_handle* hh, int32_t which, void* out) {
+  FW_API_BEGIN
+  FW_REQUIRE(hh && out, "NULL argument");
+  FW_CHECK_CUDA(cudaSetDevice(hh->h.device));
+  current_pool() = &hh->h.pool;
+  lu_debug_analysis_download(hh->h, which, out);
+  FW_API_END
+}
+
 int fw_debug_lu_get(fw_handle* hh, int32_t which, void* out) {
   FW_API_BEGIN
   FW_REQUIRE(hh && out, "NULL argument");

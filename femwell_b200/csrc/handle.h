@@ -113,6 +113,9 @@ void upload_staged(Handle& h, void* dev_dst, const void* host_src, size_t bytes)
 
 // ---- scan / sort / COO->CSR (sort.cu)
 void exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, DevBuf<uint32_t>& tmp, cudaStream_t s);
+// stable LSD radix sort of (key, payload) pairs by the low `bits` bits; the result ends up in keys_a / pay_a
+void radix_sort_pairs_dev(Handle& h, DevBuf<uint64_t>& keys_a, DevBuf<uint64_t>& keys_b, DevBuf<uint32_t>& pay_a,
+                          DevBuf<uint32_t>& pay_b, int64_t n, int bits, bool payload_iota);
 void build_pattern_from_keys(Pattern& pat, DevBuf<uint64_t>& keys, DevBuf<uint32_t>& payload, int64_t n_coo,
                              int n_rows, int col_bits, Handle& h);
 void symbolic_space(Handle& h);

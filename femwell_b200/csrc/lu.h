@@ -45,6 +45,10 @@ void lu_symbolic_build(LUSymbolic& S, int n, int nb, int ne, const int* edofs, c
                        const uint8_t* active, int leaf_elements);
 
 struct LUDevice;  // device-side mirrors (lu_numeric.cu)
+struct LU;
+// the same analysis on the device (lu_symbolic_gpu.cu): fills lu.sym (small host arrays) and lu.dev (device tables)
+void lu_symbolic_build_gpu(Handle& h, LU& lu, const std::vector<uint8_t>& active, int leaf_elements);
+void lu_debug_analysis_download(Handle& h, int which, void* out);
 
 struct LU {
   LUSymbolic sym;

@@ -72,11 +72,21 @@ static void lu_host_analysis(const Handle& h, LU& lu) {
   }
 }
 
+static void lu_analyse_finish(Handle& h);
+
 static bool lu_reusable(const Handle& h, const std::vector<uint8_t>& active, int leaf_elements) {
   return h.lu && h.lu->dev && h.lu->leaf_key == leaf_elements && h.lu->active_key == active;
 }
 
+// The analysis runs on the device (lu_symbolic_gpu.cu); FW_HOST_ANALYSIS=1 selects the threaded host version
+// (lu_symbolic.cpp, same results bit by bit), which is also what the CPU tests exercise.
+static bool host_analysis() {
+  static const bool v = getenv("FW_HOST_ANALYSIS") != nullptr;
+  return v;
+}
+
 void lu_analyse_prefetch(Handle& h, const std::vector<uint8_t>& active, int leaf_elements) {
+  if (!host_analysis()) return;  // nothing to overlap: the device analysis takes a few milliseconds
   // an analysis with the same keys may already be running (started by fw_set_space from fw_analysis_hint)
   if (h.lu_prefetch && h.lu_prefetch->lu && h.lu_prefetch->lu->leaf_key == leaf_elements &&
       h.lu_prefetch->lu->active_key == active)
@@ -111,6 +121,15 @@ void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements
     return;
   }
   Trace tr(h.stream);
+  cudaStream_t s = h.stream;
+  if (!host_analysis()) {
+    h.lu.reset(new LU());
+    h.lu->active_key = active;
+    h.lu->leaf_key = leaf_elements;
+    lu_symbolic_build_gpu(h, *h.lu, active, leaf_elements);
+    lu_analyse_finish(h);
+    return;
+  }
   if (pf && pf->lu && pf->lu->leaf_key == leaf_elements && pf->lu->active_key == active) {
     if (!pf->err.empty()) throw Error(FW_ERR_INTERNAL, pf->err);
     h.lu = std::move(pf->lu);
@@ -125,7 +144,6 @@ void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements
   lu.dev.reset(new LUDevice(h.lu_arena));
   LUDevice& d = *lu.dev;
   const LUSymbolic& S = lu.sym;
-  cudaStream_t s = h.stream;
   UpGuard up_guard(&h);
   up(d.iperm, S.iperm, s);
   up(d.perm, S.perm, s);
@@ -148,6 +166,17 @@ void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements
   }
   up(d.level_nodes, S.level_nodes, s);
   d.active.upload(active.data(), active.size(), s);
+  FW_CHECK_CUDA(cudaStreamSynchronize(s));
+  tr.mark("lu analyse: upload");
+  lu_analyse_finish(h);
+}
+
+// work arrays of the numeric phase + storage layout of the inverted diagonal blocks (both analysis paths)
+static void lu_analyse_finish(Handle& h) {
+  LU& lu = *h.lu;
+  LUDevice& d = *lu.dev;
+  const LUSymbolic& S = lu.sym;
+  cudaStream_t s = h.stream;
   d.piv.alloc((size_t)std::max(1, S.n_active));
   d.rowperm.alloc((size_t)std::max(1, S.n_active));
   d.counters.alloc(4);
@@ -169,7 +198,6 @@ void lu_analyse(Handle& h, const std::vector<uint8_t>& active, int leaf_elements
     d.dinv_entries = tot;
   }
   FW_CHECK_CUDA(cudaStreamSynchronize(s));
-  tr.mark("lu analyse: upload");
 }
 
 // ------------------------------------------------------------------------------ scatter of OP into fronts

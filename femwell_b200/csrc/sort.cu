@@ -219,6 +219,13 @@ static void radix_sort_pairs(DevBuf<uint64_t>& keys_a, DevBuf<uint64_t>& keys_b,
   FW_CHECK_CUDA(cudaGetLastError());
 }
 
+// exported for the device-side nested-dissection analysis (lu_symbolic_gpu.cu)
+void radix_sort_pairs_dev(Handle& h, DevBuf<uint64_t>& keys_a, DevBuf<uint64_t>& keys_b, DevBuf<uint32_t>& pay_a,
+                          DevBuf<uint32_t>& pay_b, int64_t n, int bits, bool payload_iota) {
+  DevBuf<uint32_t> hist;
+  radix_sort_pairs(keys_a, keys_b, pay_a, pay_b, n, bits, payload_iota, hist, h.scan_tmp, h.stream);
+}
+
 // ------------------------------------------------------------------------------ pattern from sorted keys
 __global__ void k_heads(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ flag) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -250,6 +250,11 @@ int fw_host_dense_eig(int32_t n, const double* a_c128_colmajor, double* w_c128, 
 int fw_debug_lu_symbolic(int32_t n, int32_t nb, int32_t ne, const int32_t* edofs, const double* cx,
                          const double* cy, const uint8_t* active, int32_t leaf_elements, int64_t* sizes8);
 int fw_debug_lu_symbolic_get(int32_t which, void* out);
+/* tests only: device tables of the current sparse-LU analysis; which as fw_debug_lu_symbolic_get (0 perm, 1 iperm,
+ * 2 node_of, 7 m, 8 ns, 9 own_start, 10 blist, 11 rel: int32; 21 blist_off: int64); sizes8 as fw_debug_lu_symbolic */
+int fw_debug_lu_analysis(fw_handle* h, int32_t n_dirichlet, const int32_t* dirichlet, int32_t leaf_elements,
+                         int64_t* sizes8);
+int fw_debug_lu_analysis_get(fw_handle* h, int32_t which, void* out);
 /* tests only: which = 0 factor arena (f64/c128, sum m^2 entries), 1 pivot vector (int32, n_active) */
 int fw_debug_lu_get(fw_handle* h, int32_t which, void* out);
 

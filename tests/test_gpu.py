@@ -996,3 +996,26 @@ def test_mass_solve_direct_fallback_matches_pcg_and_rescues_elongated_meshes(ctx
                                 mode.k0 * speed_of_light, b.N)
     assert np.linalg.norm(mode.H - H_ref) < 1e-8 * np.linalg.norm(H_ref)
     assert abs(mode.calculate_power() - 1) < 1e-9
+
+
+@pytest.mark.parametrize("order,n,leaf,dirichlet", [(2, 12, 16, False), (1, 17, 8, True), (2, 21, 4, True),
+                                                    (2, 9, 32, False), (2, 150, 0, False)])
+def test_device_lu_analysis_equals_host_analysis(ctx, order, n, leaf, dirichlet):
+    """The nested-dissection analysis runs on the GPU (lu_symbolic_gpu.cu); the threaded host version
+    (lu_symbolic.cpp, exercised by the CPU suite) must produce the same tables bit by bit: integer work."""
+    from mf_emulator import lu_symbolic
+
+    m, _ = strip_problem(n)
+    b = Basis(m, ElementTriP0(), intorder=4).with_element(mode_element(order))
+    act = np.ones(b.N, dtype=np.uint8)
+    D = b.get_dofs(None) if dirichlet else None
+    if dirichlet:
+        act[D] = 0
+    ctx.set_space(b)
+    G = ctx.debug_lu_analysis(D, leaf)
+    c = (m.p[:, m.t[0]] + m.p[:, m.t[1]] + m.p[:, m.t[2]]) / 3.0
+    S = lu_symbolic(b.N, b.element_dofs, c[0], c[1], act, leaf if leaf else 16)
+    for key in ("n_active", "n_nodes", "n_levels", "factor_entries", "max_m", "max_ns"):
+        assert G[key] == S[key], key
+    for key in ("perm", "iperm", "node_of", "m", "ns", "own_start", "blist", "rel", "blist_off"):
+        assert np.array_equal(np.asarray(G[key], dtype=np.int64), np.asarray(S[key], dtype=np.int64)), key
