@@ -1,7 +1,7 @@
 // Register-tiled FP64 / C128 GEMM for the trailing updates of the multifrontal LU (large fronts).
 //   C[r0:, r0:] -= L[r0:, kbeg:kbeg+klen] * U[kbeg:kbeg+klen, r0:]       (column-major front, ld = m)
-// FP64 has no tcgen05 path (the 5th-gen tensor cores stop at TF32), so this is a SIMT kernel on the FP64
-// pipe: CTA tile 16*MT x 16*MT (MT = 8 for f64 -> 128 x 128, MT = 4 for c128 -> 64 x 64), 256 threads, every
+// FP64 has no tcgen05 path (the 5th-gen tensor cores stop at TF32); the f64 update runs on the FP64 tensor
+// instruction of the legacy path (mma.sync m8n8k4 = DMMA, second half of this file), c128 on this SIMT kernel: CTA tile 16*MT x 16*MT (MT = 8 for f64 -> 128 x 128, MT = 4 for c128 -> 64 x 64), 256 threads, every
 // thread an MT x MT register tile split into 2 x 2 sub-blocks of MT/2 so that shared-memory reads are 128-bit
 // and conflict free, k-chunks of 16 double-buffered through registers (global loads of chunk i+1 are in
 // flight while chunk i is multiplied).  Shared-memory bandwidth and the FP64 pipe are balanced at this tile
@@ -127,9 +127,160 @@ __global__ void __launch_bounds__(256) k_lu_gemm_big(FrontTab T, const int* __re
   }
 }
 
+// ------------------------------------------------------------------------------ FP64 tensor-core variant (DMMA)
+// The same update on mma.sync.aligned.m8n8k4.f64 (SASS: DMMA).  Measured on B200 (scripts/microbench/fp64_peak.cu):
+// DMMA issues at 37.1 TFLOP/s from registers, DFMA tops out at 33.9 -- the ceiling is the same FP64 pipe, but one DMMA
+// replaces 8 DFMA per lane and needs two operand registers instead of an 8 x 8 register tile: the SIMT kernel above
+// needs 244 registers (one CTA of 8 warps per SM, FP64 pipe 16 % busy), this one 64 accumulator registers per lane.
+//   CTA tile 128 x 128, 512 threads = 4 x 4 warps, warp tile 32 x 32 = 4 x 4 mma tiles, k-chunks of 16 through a
+//   3-stage cp.async pipeline (8-byte copies with zero fill at the ragged edges: front rows are only 8-byte aligned).
+//   Shared layouts make every fragment load conflict free: As[k][r] with row length 132 and Bs[c][k] with row
+//   length 20 (both = 4 mod 16 doubles), so the 16 lanes of a half warp hit 16 distinct 8-byte banks.
+constexpr int DM_TM = 128, DM_KC = 16, DM_LDA = DM_TM + 4, DM_LDB = DM_KC + 4, DM_STAGES = 3, DM_THREADS = 512;
+constexpr int DM_STAGE_DOUBLES = DM_KC * DM_LDA + DM_TM * DM_LDB;
+
+__device__ __forceinline__ void cp_async8_zfill(double* smem, const double* gmem, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes));
+}
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <bool SCHUR>
+__global__ void __launch_bounds__(DM_THREADS, 1) k_lu_gemm_dmma(FrontTab T, const int* __restrict__ nodes, int kstep,
+                                                                double* __restrict__ F) {
+  extern __shared__ __align__(16) double dm_smem[];
+  const int node = nodes[blockIdx.x];
+  const int m = T.m[node], ns = T.ns[node];
+  const int k0 = SCHUR ? 0 : kstep * PW;
+  if (k0 >= ns) return;
+  const int klen = SCHUR ? ns : min(PW, ns - k0);
+  const int r0 = SCHUR ? ns : k0 + klen;
+  const int nrem = m - r0;
+  if (nrem <= 0) return;
+  const int nt = (nrem + DM_TM - 1) / DM_TM;
+  const int ti = blockIdx.y, tj = blockIdx.z;
+  if (ti >= nt || tj >= nt) return;
+  const int rbase = r0 + ti * DM_TM, cbase = r0 + tj * DM_TM;
+  if (!SCHUR && rbase >= ns && cbase >= ns) return;  // tile entirely inside S22
+  double* Fn = F + T.front_off[node];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int g = lane >> 2, q = lane & 3;
+
+  auto issue = [&](int chunk, int stage) {
+    double* As = dm_smem + (size_t)stage * DM_STAGE_DOUBLES;
+    double* Bs = As + DM_KC * DM_LDA;
+    const int kc = chunk * DM_KC;
+#pragma unroll
+    for (int it = 0; it < DM_KC * DM_TM / DM_THREADS; ++it) {
+      const int idx = tid + it * DM_THREADS;
+      {
+        const int r = idx % DM_TM, k = idx / DM_TM;
+        const int gr = rbase + r, gk = kc + k;
+        const bool ok = gr < m && gk < klen;
+        cp_async8_zfill(As + k * DM_LDA + r, ok ? Fn + gr + (long long)(k0 + gk) * m : Fn, ok);
+      }
+      {
+        const int k = idx % DM_KC, c = idx / DM_KC;
+        const int gc = cbase + c, gk = kc + k;
+        const bool ok = gc < m && gk < klen;
+        cp_async8_zfill(Bs + c * DM_LDB + k, ok ? Fn + (k0 + gk) + (long long)gc * m : Fn, ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int nchunk = (klen + DM_KC - 1) / DM_KC;
+  issue(0, 0);
+  if (nchunk > 1)
+    issue(1, 1);
+  else
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  for (int c = 0; c < nchunk; ++c) {
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    __syncthreads();  // chunk c has landed for everybody; stage (c + 2) % 3 was last read in iteration c - 1
+    if (c + 2 < nchunk)
+      issue(c + 2, (c + 2) % DM_STAGES);
+    else
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    const double* As = dm_smem + (size_t)(c % DM_STAGES) * DM_STAGE_DOUBLES;
+    const double* Bs = As + DM_KC * DM_LDA;
+#pragma unroll
+    for (int kk = 0; kk < DM_KC / 4; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[(kk * 4 + q) * DM_LDA + wm * 32 + i * 8 + g];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[(wn * 32 + j * 8 + g) * DM_LDB + kk * 4 + q];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  // C -= acc: lane holds rows g of every 8 x 8 tile, columns 2 q and 2 q + 1
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int gc = cbase + wn * 32 + j * 8 + 2 * q + h;
+      if (gc >= m) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gr = rbase + wm * 32 + i * 8 + g;
+        if (gr < m && (SCHUR || gr < ns || gc < ns)) {
+          double* dst = Fn + gr + (long long)gc * m;
+          *dst = *dst - acc[i][j][h];
+        }
+      }
+    }
+  }
+}
+
+static void lu_gemm_dmma_launch(FrontTab T, const int* nodes, int nfront, int kstep, double* F, int max_rem, bool schur,
+                                cudaStream_t s) {
+  constexpr size_t smem = sizeof(double) * DM_STAGES * DM_STAGE_DOUBLES;
+  const int nt = (max_rem + DM_TM - 1) / DM_TM;
+  if (nt <= 0) return;
+  static bool configured[64] = {};
+  if (first_use_on_device(configured)) {
+    FW_CHECK_CUDA(cudaFuncSetAttribute(k_lu_gemm_dmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FW_CHECK_CUDA(cudaFuncSetAttribute(k_lu_gemm_dmma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  if (schur)
+    k_lu_gemm_dmma<true><<<dim3(nfront, nt, nt), DM_THREADS, smem, s>>>(T, nodes, kstep, F);
+  else
+    k_lu_gemm_dmma<false><<<dim3(nfront, nt, nt), DM_THREADS, smem, s>>>(T, nodes, kstep, F);
+}
+
+template <class S>
+static bool try_dmma(FrontTab, const int*, int, int, S*, int, bool, cudaStream_t) {
+  return false;
+}
+template <>
+bool try_dmma<double>(FrontTab T, const int* nodes, int nfront, int kstep, double* F, int max_rem, bool schur,
+                      cudaStream_t s) {
+  static const bool off = getenv("FW_NO_DMMA") != nullptr;
+  if (off) return false;
+  lu_gemm_dmma_launch(T, nodes, nfront, kstep, F, max_rem, schur, s);
+  return true;
+}
+
 template <class S>
 void lu_gemm_big_launch(FrontTab T, const int* nodes, int nfront, int kstep, S* F, int max_rem, bool schur,
                         cudaStream_t s) {
+  if (try_dmma<S>(T, nodes, nfront, kstep, F, max_rem, schur, s)) return;
   constexpr int TM = 16 * Gemm2Cfg<S>::MT;
   constexpr size_t smem = sizeof(S) * 2 * G2_KC * (TM + TM + 2);
   const int nt = (max_rem + TM - 1) / TM;
