@@ -50,10 +50,27 @@ struct LU;
 void lu_symbolic_build_gpu(Handle& h, LU& lu, const std::vector<uint8_t>& active, int leaf_elements);
 void lu_debug_analysis_download(Handle& h, int which, void* out);
 
+// One forward + backward substitution is ~60 dependent kernel launches with fixed arguments for a fixed (rhs, solution)
+// pointer pair; the Arnoldi loop repeats it ~50 times per factorisation.  The launch sequence is captured into a CUDA
+// graph the second time a pointer pair is seen and replayed afterwards (invalidated by every new factorisation).
+struct SolveGraph {
+  const void* b = nullptr;
+  void* x = nullptr;
+  int nrhs = 0;
+  int uses = 0;
+  cudaGraphExec_t exec = nullptr;
+};
+
 struct LU {
   LUSymbolic sym;
   bool is_complex = false;
   bool factored = false;
+  std::vector<SolveGraph> graphs;
+  void drop_graphs() {
+    for (auto& g : graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
   int perturbed = 0;
   std::vector<uint8_t> active_key;  // the analysis is reusable while mesh, Dirichlet set and leaf size stay
   int leaf_key = 0;

@@ -19,7 +19,7 @@
 namespace fw {
 
 LU::LU() {}
-LU::~LU() {}
+LU::~LU() { drop_graphs(); }
 
 template <class S, class V>
 __device__ inline S to_(V v);
@@ -794,6 +794,7 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
   const LUSymbolic& Sy = lu.sym;
   cudaStream_t s = h.stream;
   const size_t wsc = sizeof(S) / sizeof(double);
+  lu.drop_graphs();  // captured solves refer to the previous factorisation (scalar type, buffers)
   Trace tr(s);
   d.factors.alloc((size_t)std::max<int64_t>(1, Sy.factor_entries) * wsc);
   tr.mark("lu factor: alloc");
@@ -826,6 +827,10 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
   const bool trace2 = tenv && atoi(tenv) >= 2;
   static const int big_gemm_min = getenv("FW_BIG_GEMM_MIN") ? atoi(getenv("FW_BIG_GEMM_MIN")) : 384;
   static const bool no_cluster_panel = getenv("FW_NO_CLUSTER_PANEL") != nullptr;
+  // measured at 500k triangles: the level of 16 fronts (ns ~ 1000) took 15.7 ms with the global-memory tall-panel
+  // kernel against 3.8 ms for the level of 8 fronts of half the width on the cluster kernel
+  static const int cluster_panel_max_fronts =
+      getenv("FW_CLUSTER_PANEL_MAX_FRONTS") ? atoi(getenv("FW_CLUSTER_PANEL_MAX_FRONTS")) : 64;
   // per-panel rank-32 updates: the 64x64 tile kernel (3+ CTAs per SM) beats the 128x128 one (244 registers, one CTA
   // per SM, only two K-chunks to pipeline): 69.9 vs 76.5 ms over the nine top levels; the big kernel keeps the Schur
   // updates (K = ns)
@@ -851,7 +856,7 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
         bool done = false;
         if constexpr (!scalar_traits<S>::is_complex) {
           // few, tall f64 fronts (top of the tree): one 8-CTA cluster per front, the panel lives in registers
-          if (nfront <= 8 && max_ns - k * PW <= PCL * PCL_THREADS && !no_cluster_panel) {
+          if (nfront <= cluster_panel_max_fronts && max_ns - k * PW <= PCL * PCL_THREADS && !no_cluster_panel) {
             k_lu_panel_cluster<<<nfront * PCL, PCL_THREADS, 0, s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
             done = true;
           }

@@ -1043,9 +1043,56 @@ static void solve_typed(Handle& h, const S* b, S* x) {
   h.tim.kernel_launches += launches;
 }
 
+static void lu_solve_launch(Handle& h, const void* b, void* x, int nrhs);
+
 void lu_solve_dev(Handle& h, const void* b, void* x, int nrhs) {
   FW_REQUIRE(h.lu && h.lu->factored, "LU has not been factored");
   FW_REQUIRE(nrhs == 1 || nrhs == 2, "nrhs must be 1 or 2");
+  static const bool no_graph = getenv("FW_NO_SOLVE_GRAPH") != nullptr;
+  if (no_graph || getenv("FW_TRACE")) {  // (the trace synchronises the stream between the levels)
+    lu_solve_launch(h, b, x, nrhs);
+    return;
+  }
+  LU& lu = *h.lu;
+  SolveGraph* g = nullptr;
+  for (auto& c : lu.graphs)
+    if (c.b == b && c.x == x && c.nrhs == nrhs) g = &c;
+  if (!g) {
+    if (lu.graphs.size() >= 8) lu.drop_graphs();
+    lu.graphs.push_back(SolveGraph{b, x, nrhs, 0, nullptr});
+    g = &lu.graphs.back();
+  }
+  ++g->uses;
+  if (g->exec) {
+    FW_CHECK_CUDA(cudaGraphLaunch(g->exec, h.stream));
+    h.tim.kernel_launches += 1;
+    return;
+  }
+  if (g->uses < 2) {  // first use: eager (allocates the work buffers, sets the function attributes)
+    lu_solve_launch(h, b, x, nrhs);
+    return;
+  }
+  cudaGraph_t graph = nullptr;
+  FW_CHECK_CUDA(cudaStreamBeginCapture(h.stream, cudaStreamCaptureModeRelaxed));
+  const int64_t launches_before = h.tim.kernel_launches;
+  try {
+    lu_solve_launch(h, b, x, nrhs);
+  } catch (...) {
+    cudaStreamEndCapture(h.stream, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  h.tim.kernel_launches = launches_before;
+  FW_CHECK_CUDA(cudaStreamEndCapture(h.stream, &graph));
+  cudaGraphExec_t exec = nullptr;
+  FW_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  cudaGraphDestroy(graph);
+  g->exec = exec;
+  FW_CHECK_CUDA(cudaGraphLaunch(exec, h.stream));
+  h.tim.kernel_launches += 1;
+}
+
+static void lu_solve_launch(Handle& h, const void* b, void* x, int nrhs) {
   if (h.lu->is_complex) {
     if (nrhs == 1)
       solve_typed<cplx, 1>(h, (const cplx*)b, (cplx*)x);
