@@ -218,7 +218,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="solve", choices=["solve", "sweep"])
+    ap.add_argument("--workload", default="solve", choices=["solve", "sweep", "geometry"])
+    ap.add_argument("--geometry-n", type=int, default=224, help="--workload geometry: grid cells per side of every mesh")
     ap.add_argument("--n", type=int, default=500, help="grid cells per side (2 n^2 triangles)")
     ap.add_argument("--num-modes", type=int, default=4)
     ap.add_argument("--points-per-rank", type=int, default=4, help="--workload sweep: wavelength points per GPU per step")
@@ -272,6 +273,9 @@ def main():
 
     if args.workload == "sweep":
         run_sweep_workload(args, rank, world, local_rank, m, eps, b0, ctx, barrier, torch, dist)
+        return
+    if args.workload == "geometry":
+        run_geometry_workload(args, rank, world, local_rank, ctx, barrier, torch, dist)
         return
 
     config = {"workload": workload_text(args.n, args.num_modes),
@@ -509,6 +513,58 @@ def run_sweep_workload(args, rank, world, local_rank, m, eps, b0, ctx, barrier, 
                 "gpu_launches": int(launches), "clocks": clocks,
                 "last_point_stages_ms": {kk: vv for kk, vv in tim.items()},
                 "n_eff": [float(x) for x in table[:, 0].real], "group_index": None if ng is None else [float(x) for x in ng]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_geometry_workload(args, rank, world, local_rank, ctx, barrier, torch, dist):
+    """BASELINE metric 3, config-4 style: coupled-waveguide gap x width sweep through
+    femwell_b200.sweep.coupler_geometry_sweep -- every geometry has its OWN mesh (~100k triangles), 2 solves (3 modes),
+    2 same-mesh and 2 cross-mesh overlaps; block partition over the ranks, one all_gather per step."""
+    from femwell_b200.sweep import COUPLER_COLUMNS, coupler_geometry_sweep
+
+    ppr = args.points_per_rank
+    n_pts = ppr * world
+    gaps = np.linspace(0.1, 0.6, n_pts)
+    widths = [0.45]
+    n = args.geometry_n
+
+    def one_step():
+        return coupler_geometry_sweep(gaps, widths, n=n, order=2)
+
+    for _ in range(max(1, args.warmup)):
+        table = one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t_begin = time.perf_counter()
+    for _ in range(args.steps):
+        table = one_step()
+    barrier()
+    t_end = time.perf_counter()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([t_end - t_begin], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall = float(t.item())
+    if rank == 0:
+        tim = ctx.timings()
+        value = n_pts * args.steps / wall
+        line = {"metric": "sweep pts/s at 1-8 GPU", "value": value, "unit": "points/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": 1000.0 * wall / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": (f"coupled-waveguide geometry sweep (config-4 style): {ppr} geometries per GPU per step, "
+                                        f"each its own {n}x{n}x2 = {2 * n * n} triangle mesh, order 2, supermodes (k=2) + "
+                                        "isolated mode (k=1), 2 same-mesh + 2 cross-mesh overlaps, host mesh generation and "
+                                        "uploads inside the timed region, results all_gathered per step"),
+                           "points_per_step": n_pts},
+                "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None},
+                "gpu_launches": int(tim["kernel_launches"]) * 2 * ppr * args.steps, "clocks": clocks,
+                "last_solve_stages_ms": {kk: vv for kk, vv in tim.items()},
+                "columns": list(COUPLER_COLUMNS), "table": [[float(x) for x in row] for row in table]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -301,3 +301,151 @@ def rib_benchmark_mesh(slab_thickness: float, h0: float = 0.075, ratio: float = 
         "clad": np.nonzero(~(core | box))[0].astype(np.int32),
     }
     return m
+
+
+# ------------------------------------------------------------------ refinement (host bookkeeping)
+def adaptive_theta(est: np.ndarray, theta: float = 0.5, max: Optional[float] = None) -> np.ndarray:
+    """Elements whose indicator exceeds ``theta`` times the largest one (scikit-fem ``adaptive_theta`` as used by
+    docs/photonics/examples/refinement.py:69)."""
+    est = np.asarray(est)
+    if max is None:
+        return np.nonzero(theta * np.max(est) < est)[0]
+    return np.nonzero(theta * max < est)[0]
+
+
+def _refine_marked(mesh: MeshTri, marked: np.ndarray) -> MeshTri:
+    """Split every triangle according to its marked facets (0: keep, 1: bisect, 2: bisect twice, 3: four similar
+    children); a marked facet gets one new vertex at its midpoint, so the result is conforming as long as every
+    element with a marked facet has its longest facet marked (guaranteed by the caller's closure)."""
+    p, t, t2f, facets = mesh.p, mesh.t.astype(np.int64), mesh.t2f, mesh.facets
+    nv = mesh.nvertices
+    mid_of = np.full(mesh.nfacets, -1, dtype=np.int64)
+    mf = np.nonzero(marked)[0]
+    mid_of[mf] = nv + np.arange(mf.size)
+    pm = 0.5 * (p[:, facets[0, mf]] + p[:, facets[1, mf]])
+    p_new = np.concatenate([p, pm], axis=1)
+    # facet lengths; the reference edge of an element is its longest facet (ties: lowest local index)
+    d = p[:, facets[0]] - p[:, facets[1]]
+    flen = np.hypot(d[0], d[1])
+    el = flen[t2f]                       # (3, Ne): local edges (0,1), (1,2), (0,2)
+    lo = np.argmax(el, axis=0)           # local index of the longest edge
+    # rotate: a, b = ends of the longest edge, c = the opposite vertex
+    ends = np.array([[0, 1], [1, 2], [0, 2]])
+    opp = np.array([2, 0, 1])
+    ne = mesh.nelements
+    cols = np.arange(ne)
+    ia, ib, ic = ends[lo, 0], ends[lo, 1], opp[lo]
+    a, b, c = t[ia, cols], t[ib, cols], t[ic, cols]
+    # local edge index joining two local vertices
+    edge_of = np.full((3, 3), -1)
+    edge_of[0, 1] = edge_of[1, 0] = 0
+    edge_of[1, 2] = edge_of[2, 1] = 1
+    edge_of[0, 2] = edge_of[2, 0] = 2
+    f_ab = t2f[lo, cols]
+    f_bc = t2f[edge_of[ib, ic], cols]
+    f_ac = t2f[edge_of[ia, ic], cols]
+    mab, mbc, mac = mid_of[f_ab], mid_of[f_bc], mid_of[f_ac]
+    has_ab, has_bc, has_ac = mab >= 0, mbc >= 0, mac >= 0
+    assert not np.any((has_bc | has_ac) & ~has_ab), "closure violated: longest facet unmarked"
+    tri, parent = [], []
+
+    def emit(sel, *verts):
+        idx = np.nonzero(sel)[0]
+        if idx.size:
+            tri.append(np.stack([v[idx] for v in verts]))
+            parent.append(idx)
+
+    emit(~has_ab, a, b, c)
+    green = has_ab & ~has_bc & ~has_ac
+    emit(green, a, mab, c)
+    emit(green, mab, b, c)
+    blue_r = has_ab & has_bc & ~has_ac
+    emit(blue_r, a, mab, c)
+    emit(blue_r, mab, b, mbc)
+    emit(blue_r, mab, mbc, c)
+    blue_l = has_ab & ~has_bc & has_ac
+    emit(blue_l, mab, b, c)
+    emit(blue_l, a, mab, mac)
+    emit(blue_l, mab, c, mac)
+    red = has_ab & has_bc & has_ac
+    emit(red, a, mab, mac)
+    emit(red, mab, b, mbc)
+    emit(red, mac, mbc, c)
+    emit(red, mab, mbc, mac)
+    t_new = np.concatenate(tri, axis=1)
+    par = np.concatenate(parent)
+    order = np.argsort(par, kind="stable")  # children stay next to each other in parent order (spatial locality)
+    t_new, par = t_new[:, order], par[order]
+    out = MeshTri(p_new, t_new)
+    for name, els in mesh.subdomains.items():
+        flag = np.zeros(ne, dtype=bool)
+        flag[np.asarray(els, dtype=np.int64)] = True
+        out.subdomains[name] = np.nonzero(flag[par])[0].astype(np.int32)
+    if mesh.boundaries:
+        # a child facet lies on a named boundary iff both its ends are (an end of / the midpoint of) a facet of it
+        nvn = out.nvertices
+        for name, fs in mesh.boundaries.items():
+            fs = np.asarray(fs, dtype=np.int64)
+            v0, v1 = facets[0, fs].astype(np.int64), facets[1, fs].astype(np.int64)
+            mm = mid_of[fs]
+            pairs = [np.stack([v0, v1])[:, mm < 0], np.stack([v0, mm])[:, mm >= 0], np.stack([v1, mm])[:, mm >= 0]]
+            pr = np.sort(np.concatenate(pairs, axis=1), axis=0)
+            keys = pr[0] * nvn + pr[1]
+            okeys = out.facets[0].astype(np.int64) * nvn + out.facets[1].astype(np.int64)
+            out.boundaries[name] = np.nonzero(np.isin(okeys, keys))[0].astype(np.int32)
+    out.parent_elements = par.astype(np.int32)
+    return out
+
+
+def _refined(mesh: MeshTri, elements=None) -> MeshTri:
+    """``mesh.refined(elements)`` of scikit-fem as used by docs/photonics/examples/refinement.py:80: red-green-blue
+    refinement of the selected triangles (all three facets of a selected triangle are split; neighbours are closed by
+    splitting their longest facet first so that no hanging node remains); ``elements=None`` or an integer: uniform
+    red refinement (that many times).  Sub-domains and named boundaries are inherited by the children."""
+    if elements is None or isinstance(elements, (int, np.integer)):
+        times = 1 if elements is None else int(elements)
+        m = mesh
+        for _ in range(times):
+            m = _refine_marked(m, np.ones(m.nfacets, dtype=bool))
+        return m
+    els = mesh.normalize_elements(elements).astype(np.int64)
+    marked = np.zeros(mesh.nfacets, dtype=bool)
+    marked[mesh.t2f[:, els].ravel()] = True
+    d = mesh.p[:, mesh.facets[0]] - mesh.p[:, mesh.facets[1]]
+    flen = np.hypot(d[0], d[1])
+    longest = mesh.t2f[np.argmax(flen[mesh.t2f], axis=0), np.arange(mesh.nelements)]
+    while True:  # closure: an element with any marked facet must have its longest facet marked
+        touched = marked[mesh.t2f].any(axis=0)
+        need = longest[touched]
+        if marked[need].all():
+            break
+        marked[need] = True
+    return _refine_marked(mesh, marked)
+
+
+MeshTri.refined = _refined
+
+
+def coupled_waveguide_mesh(n: int, gap: float = 0.4, w_core_1: float = 0.45, w_core_2: float = 0.46,
+                           h_core: float = 0.22, w_sim: float = 4.0, h_clad: float = 1.0, h_box: float = 1.0,
+                           jitter: float = 0.15, seed: int = 1234) -> MeshTri:
+    """Two parallel strip waveguides (docs/photonics/examples/coupled_mode_theory.py:41-95, crosstalk.py:60-140) on
+    an ``n x n`` tensor grid whose lines follow every material interface.  Sub-domains ``core_1`` (left),
+    ``core_2`` (right), ``clad`` (y > 0 outside the cores), ``box`` (y < 0)."""
+    xb = sorted({-w_sim / 2, -w_core_1 - gap / 2, -gap / 2, gap / 2, w_core_2 + gap / 2, w_sim / 2})
+    yb = sorted({-h_box, 0.0, h_core, h_clad})
+    xs = graded_axis(xb, _split_cells(xb, n))
+    ys = graded_axis(yb, _split_cells(yb, n))
+    m = MeshTri.structured(xs, ys, jitter=jitter, seed=seed, frozen_x=xb, frozen_y=yb)
+    c = m.centroids()
+    in_y = (c[1] > 0) & (c[1] < h_core)
+    c1 = in_y & (c[0] > -w_core_1 - gap / 2) & (c[0] < -gap / 2)
+    c2 = in_y & (c[0] > gap / 2) & (c[0] < w_core_2 + gap / 2)
+    box = c[1] < 0
+    m.subdomains = {
+        "core_1": np.nonzero(c1)[0].astype(np.int32),
+        "core_2": np.nonzero(c2)[0].astype(np.int32),
+        "box": np.nonzero(box)[0].astype(np.int32),
+        "clad": np.nonzero(~(c1 | c2 | box))[0].astype(np.int32),
+    }
+    return m

@@ -1,4 +1,4 @@
-"""Native reader for gmsh ``.msh`` files (ASCII, format 2.2 and 4.1) -> :class:`MeshTri`.
+"""Native reader/writer for gmsh ``.msh`` files (ASCII and binary, format 2.2 and 4.1) <-> :class:`MeshTri`.
 
 Stands in for the ``meshio.read(...)`` + ``skfem.io.meshio.from_meshio`` step that precedes the hot path in
 every reference example (``femwell/mesh/mesh.py:440-453`` writes a ``.msh`` with gmsh and reads it back with
@@ -120,21 +120,141 @@ def _read_v4(sec, names):
     return ids, xyz, tris, tri_phys, lines, line_phys
 
 
+class _Cursor:
+    """byte cursor over a binary .msh file: ASCII lines and packed little/big-endian records"""
+
+    def __init__(self, data: bytes):
+        self.d, self.i, self.e = data, 0, "<"
+
+    def line(self) -> str:
+        j = self.d.index(b"\n", self.i)
+        out = self.d[self.i:j].decode("ascii", "replace").strip()
+        self.i = j + 1
+        return out
+
+    def skip_ws(self):
+        while self.i < len(self.d) and self.d[self.i:self.i + 1] in b" \r\n\t":
+            self.i += 1
+
+    def arr(self, dtype, count):
+        dt = np.dtype(dtype).newbyteorder(self.e)
+        out = np.frombuffer(self.d, dtype=dt, count=count, offset=self.i)
+        self.i += dt.itemsize * count
+        return out
+
+    def find(self, marker: str) -> bool:
+        j = self.d.find(("$" + marker).encode(), 0)
+        if j < 0:
+            return False
+        self.i = j
+        self.line()
+        return True
+
+
+def _read_binary(data: bytes, version: float):
+    """binary 2.2 / 4.1: returns the same tuple as the ASCII readers plus the physical names"""
+    c = _Cursor(data)
+    c.find("MeshFormat")
+    fmt = c.line().split()
+    size_t = np.uint64 if int(fmt[2]) == 8 else np.uint32
+    one = c.arr(np.int32, 1)[0]
+    if one != 1:
+        c.e = ">"
+        if int(np.frombuffer(data, dtype=">i4", count=1, offset=c.i - 4)[0]) != 1:
+            raise ValueError("binary .msh: cannot determine the byte order")
+    names = {}
+    if c.find("PhysicalNames"):
+        for _ in range(int(c.line())):
+            dim, tag, name = c.line().split(maxsplit=2)
+            names[(int(dim), int(tag))] = name.strip().strip('"')
+    tris, tri_phys, lines, line_phys = [], [], [], []
+    if version < 4:
+        c.find("Nodes")
+        n = int(c.line())
+        rec = c.arr(np.dtype([("id", "i4"), ("x", "f8", 3)]), n)
+        ids, xyz = rec["id"].astype(np.int64), np.array(rec["x"], dtype=np.float64)
+        c.find("Elements")
+        total, done = int(c.line()), 0
+        while done < total:
+            etype, nfollow, ntags = (int(v) for v in c.arr(np.int32, 3))
+            nn = _NODES_OF_TYPE.get(etype)
+            if nn is None:
+                raise ValueError(f"binary .msh: unsupported element type {etype}")
+            blk = c.arr(np.int32, nfollow * (1 + ntags + nn)).reshape(nfollow, 1 + ntags + nn)
+            phys = blk[:, 1] if ntags > 0 else np.zeros(nfollow, dtype=np.int32)
+            conn = blk[:, 1 + ntags:]
+            if etype == _TRI:
+                tris += conn[:, :3].tolist()
+                tri_phys += [[int(q)] if q else [] for q in phys]
+            elif etype == _LINE:
+                lines += conn[:, :2].tolist()
+                line_phys += [[int(q)] if q else [] for q in phys]
+            done += nfollow
+        return names, ids, xyz, tris, tri_phys, lines, line_phys
+    ent_phys: Dict[Tuple[int, int], List[int]] = {}
+    if c.find("Entities"):
+        counts = [int(v) for v in c.arr(size_t, 4)]
+        for dim, cnt in enumerate(counts):
+            for _ in range(cnt):
+                tag = int(c.arr(np.int32, 1)[0])
+                c.arr(np.float64, 3 if dim == 0 else 6)
+                nphys = int(c.arr(size_t, 1)[0])
+                ent_phys[(dim, tag)] = [abs(int(v)) for v in c.arr(np.int32, nphys)]
+                if dim > 0:
+                    c.arr(np.int32, int(c.arr(size_t, 1)[0]))
+    c.find("Nodes")
+    nblocks, ntotal = (int(v) for v in c.arr(size_t, 4)[:2])
+    ids = np.empty(ntotal, dtype=np.int64)
+    xyz = np.empty((ntotal, 3))
+    k = 0
+    for _ in range(nblocks):
+        dim, _tag, parametric = (int(v) for v in c.arr(np.int32, 3))
+        nb = int(c.arr(size_t, 1)[0])
+        ids[k:k + nb] = c.arr(size_t, nb).astype(np.int64)
+        width = 3 + (dim if parametric else 0)
+        xyz[k:k + nb] = c.arr(np.float64, nb * width).reshape(nb, width)[:, :3]
+        k += nb
+    c.find("Elements")
+    nblocks = int(c.arr(size_t, 4)[0])
+    for _ in range(nblocks):
+        dim, tag, etype = (int(v) for v in c.arr(np.int32, 3))
+        nb = int(c.arr(size_t, 1)[0])
+        nn = _NODES_OF_TYPE.get(etype)
+        if nn is None:
+            raise ValueError(f"binary .msh: unsupported element type {etype}")
+        blk = c.arr(size_t, nb * (1 + nn)).reshape(nb, 1 + nn).astype(np.int64)
+        phys = ent_phys.get((dim, tag), [])
+        if etype == _TRI:
+            tris += blk[:, 1:4].tolist()
+            tri_phys += [phys] * nb
+        elif etype == _LINE:
+            lines += blk[:, 1:3].tolist()
+            line_phys += [phys] * nb
+    return names, ids, xyz, tris, tri_phys, lines, line_phys
+
+
 def read_msh(path: str) -> MeshTri:
-    """Triangles + named physical groups of a gmsh ASCII ``.msh`` file (2.2 or 4.1) as a :class:`MeshTri`."""
-    with open(path, "r") as f:
-        sec = _sections(f.read())
-    if "MeshFormat" not in sec:
+    """Triangles + named physical groups of a gmsh ``.msh`` file (2.2 or 4.1, ASCII or binary) as a :class:`MeshTri`."""
+    with open(path, "rb") as f:
+        data = f.read()
+    head = data[:256].decode("ascii", "replace")
+    if not head.lstrip().startswith("$MeshFormat"):
         raise ValueError(f"{path}: not a gmsh .msh file")
-    fmt = sec["MeshFormat"][0].split()
+    fmt = head.split("\n", 2)[1].split()
     version, binary = float(fmt[0]), int(fmt[1])
-    if binary != 0:
-        raise NotImplementedError("binary .msh files are not supported (write with Mesh.Binary = 0)")
+    if binary:
+        names, ids, xyz, tris, tri_phys, lines, line_phys = _read_binary(data, version)
+        return _mesh_from_records(path, names, ids, xyz, tris, tri_phys, lines, line_phys)
+    sec = _sections(data.decode("ascii", "replace"))
     names = _physical_names(sec.get("PhysicalNames"))
     if version < 4:
         ids, xyz, tris, tri_phys, lines, line_phys = _read_v2(sec, names)
     else:
         ids, xyz, tris, tri_phys, lines, line_phys = _read_v4(sec, names)
+    return _mesh_from_records(path, names, ids, xyz, tris, tri_phys, lines, line_phys)
+
+
+def _mesh_from_records(path, names, ids, xyz, tris, tri_phys, lines, line_phys) -> MeshTri:
     if not tris:
         raise ValueError(f"{path}: no 3-node triangles found")
     # compact vertex numbering in file order (only vertices used by triangles, like from_meshio's prune)
@@ -177,36 +297,140 @@ def read_msh(path: str) -> MeshTri:
     return mesh
 
 
-def write_msh(mesh: MeshTri, path: str) -> None:
-    """Write a :class:`MeshTri` with its named sub-domains / boundaries as gmsh 2.2 ASCII (element order kept;
-    an element in several sub-domains is written with the first one)."""
+def write_msh(mesh: MeshTri, path: str, version: str = "2.2", binary: bool = False) -> None:
+    """Write a :class:`MeshTri` with its named sub-domains / boundaries as gmsh 2.2 or 4.1, ASCII or binary (element
+    order kept within a sub-domain; 2.2 keeps the global element order; an element in several sub-domains is written
+    with the first one)."""
     sub = list(mesh.subdomains.items())
     bnd = list(mesh.boundaries.items())
     tri_tag = np.zeros(mesh.nelements, dtype=np.int64)
     for k, (_, idx) in reversed(list(enumerate(sub))):
         tri_tag[np.asarray(idx, dtype=np.int64)] = 100 + k
-    with open(path, "w") as f:
-        f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$PhysicalNames\n%d\n" % (len(sub) + len(bnd)))
+    if version not in ("2.2", "4.1"):
+        raise ValueError("version must be '2.2' or '4.1'")
+    nv, ne = mesh.nvertices, mesh.nelements
+    with open(path, "wb") as f:
+        w = lambda txt: f.write(txt.encode("ascii"))  # noqa: E731
+        w("$MeshFormat\n%s %d 8\n" % (version, 1 if binary else 0))
+        if binary:
+            f.write(np.array([1], dtype="<i4").tobytes())
+            w("\n")
+        w("$EndMeshFormat\n$PhysicalNames\n%d\n" % (len(sub) + len(bnd)))
         for k, (name, _) in enumerate(bnd):
-            f.write('1 %d "%s"\n' % (1000 + k, name))
+            w('1 %d "%s"\n' % (1000 + k, name))
         for k, (name, _) in enumerate(sub):
-            f.write('2 %d "%s"\n' % (100 + k, name))
-        f.write("$EndPhysicalNames\n$Nodes\n%d\n" % mesh.nvertices)
-        for i in range(mesh.nvertices):
-            f.write("%d %.17g %.17g 0\n" % (i + 1, mesh.p[0, i], mesh.p[1, i]))
-        nlines = sum(len(idx) for _, idx in bnd)
-        f.write("$EndNodes\n$Elements\n%d\n" % (nlines + mesh.nelements))
-        eid = 1
-        for k, (_, idx) in enumerate(bnd):
-            for fi in np.asarray(idx, dtype=np.int64):
-                a, b = mesh.facets[:, fi]
-                f.write("%d 1 2 %d %d %d %d\n" % (eid, 1000 + k, 1000 + k, a + 1, b + 1))
-                eid += 1
-        for e in range(mesh.nelements):
-            a, b, c = mesh.t[:, e]
-            if tri_tag[e]:
-                f.write("%d 2 2 %d %d %d %d %d\n" % (eid, tri_tag[e], tri_tag[e], a + 1, b + 1, c + 1))
+            w('2 %d "%s"\n' % (100 + k, name))
+        w("$EndPhysicalNames\n")
+        xyz = np.zeros((nv, 3))
+        xyz[:, :2] = mesh.p.T
+        if version == "2.2":
+            w("$Nodes\n%d\n" % nv)
+            if binary:
+                rec = np.empty(nv, dtype=np.dtype([("id", "<i4"), ("x", "<f8", 3)]))
+                rec["id"], rec["x"] = np.arange(1, nv + 1), xyz
+                f.write(rec.tobytes())
+                w("\n")
             else:
-                f.write("%d 2 0 %d %d %d\n" % (eid, a + 1, b + 1, c + 1))
-            eid += 1
-        f.write("$EndElements\n")
+                for i in range(nv):
+                    w("%d %.17g %.17g 0\n" % (i + 1, mesh.p[0, i], mesh.p[1, i]))
+            nlines = sum(len(idx) for _, idx in bnd)
+            w("$EndNodes\n$Elements\n%d\n" % (nlines + ne))
+            eid = 1
+            for k, (_, idx) in enumerate(bnd):
+                fi = np.asarray(idx, dtype=np.int64)
+                if binary and fi.size:
+                    blk = np.empty((fi.size, 5), dtype="<i4")
+                    blk[:, 0] = eid + np.arange(fi.size)
+                    blk[:, 1] = blk[:, 2] = 1000 + k
+                    blk[:, 3:] = mesh.facets[:, fi].T + 1
+                    f.write(np.array([1, fi.size, 2], dtype="<i4").tobytes() + blk.tobytes())
+                elif not binary:
+                    for j in fi:
+                        a, b = mesh.facets[:, j]
+                        w("%d 1 2 %d %d %d %d\n" % (eid + 0, 1000 + k, 1000 + k, a + 1, b + 1))
+                        eid += 1
+                    continue
+                eid += fi.size
+            if binary:
+                # runs of equal tag keep the global element order
+                start = 0
+                while start < ne:
+                    stop = start + 1
+                    while stop < ne and tri_tag[stop] == tri_tag[start]:
+                        stop += 1
+                    cnt, tag = stop - start, int(tri_tag[start])
+                    ntags = 2 if tag else 0
+                    blk = np.empty((cnt, 1 + ntags + 3), dtype="<i4")
+                    blk[:, 0] = eid + np.arange(cnt)
+                    if tag:
+                        blk[:, 1] = blk[:, 2] = tag
+                    blk[:, 1 + ntags:] = mesh.t[:, start:stop].T + 1
+                    f.write(np.array([2, cnt, ntags], dtype="<i4").tobytes() + blk.tobytes())
+                    eid += cnt
+                    start = stop
+                w("\n")
+            else:
+                for e in range(ne):
+                    a, b, c = mesh.t[:, e]
+                    if tri_tag[e]:
+                        w("%d 2 2 %d %d %d %d %d\n" % (eid, tri_tag[e], tri_tag[e], a + 1, b + 1, c + 1))
+                    else:
+                        w("%d 2 0 %d %d %d\n" % (eid, a + 1, b + 1, c + 1))
+                    eid += 1
+            w("$EndElements\n")
+            return
+        # ---- 4.1: one curve entity per named boundary, one surface entity per sub-domain (+ one for the rest)
+        surf = [(100 + k, [100 + k], np.nonzero(tri_tag == 100 + k)[0]) for k in range(len(sub))]
+        rest = np.nonzero(tri_tag == 0)[0]
+        if rest.size:
+            surf.append((99, [], rest))
+        surf = [sf for sf in surf if sf[2].size]
+        curves = [(1000 + k, [1000 + k], np.asarray(idx, dtype=np.int64)) for k, (_, idx) in enumerate(bnd) if len(idx)]
+        lo, hi = xyz.min(axis=0), xyz.max(axis=0)
+        w("$Entities\n")
+        if binary:
+            f.write(np.array([0, len(curves), len(surf), 0], dtype="<u8").tobytes())
+            for tag, phys, _ in curves + surf:
+                f.write(np.array([tag], dtype="<i4").tobytes() + np.concatenate([lo, hi]).astype("<f8").tobytes()
+                        + np.array([len(phys)], dtype="<u8").tobytes() + np.array(phys, dtype="<i4").tobytes()
+                        + np.array([0], dtype="<u8").tobytes())
+            w("\n")
+        else:
+            w("0 %d %d 0\n" % (len(curves), len(surf)))
+            for tag, phys, _ in curves + surf:
+                w("%d %.17g %.17g %.17g %.17g %.17g %.17g %d %s0\n" % (tag, *lo, *hi, len(phys),
+                                                                      "".join("%d " % q for q in phys)))
+        w("$EndEntities\n$Nodes\n")
+        if binary:
+            f.write(np.array([1, nv, 1, nv], dtype="<u8").tobytes() + np.array([2, surf[0][0], 0], dtype="<i4").tobytes()
+                    + np.array([nv], dtype="<u8").tobytes() + np.arange(1, nv + 1, dtype="<u8").tobytes()
+                    + xyz.astype("<f8").tobytes())
+            w("\n")
+        else:
+            w("1 %d 1 %d\n2 %d 0 %d\n" % (nv, nv, surf[0][0], nv))
+            for i in range(nv):
+                w("%d\n" % (i + 1))
+            for i in range(nv):
+                w("%.17g %.17g 0\n" % (mesh.p[0, i], mesh.p[1, i]))
+        total = sum(c[2].size for c in curves) + ne
+        w("$EndNodes\n$Elements\n")
+        if binary:
+            f.write(np.array([len(curves) + len(surf), total, 1, total], dtype="<u8").tobytes())
+        else:
+            w("%d %d 1 %d\n" % (len(curves) + len(surf), total, total))
+        eid = 1
+        for dim, etype, ents in ((1, 1, curves), (2, 2, surf)):
+            for tag, _phys, idx in ents:
+                conn = (mesh.facets[:, idx] if dim == 1 else mesh.t[:, idx]).T.astype(np.int64) + 1
+                blk = np.concatenate([(eid + np.arange(idx.size))[:, None], conn], axis=1)
+                if binary:
+                    f.write(np.array([dim, tag, etype], dtype="<i4").tobytes() + np.array([idx.size], dtype="<u8").tobytes()
+                            + blk.astype("<u8").tobytes())
+                else:
+                    w("%d %d %d %d\n" % (dim, tag, etype, idx.size))
+                    for r in blk:
+                        w(" ".join(str(int(v)) for v in r) + "\n")
+                eid += idx.size
+        if binary:
+            w("\n")
+        w("$EndElements\n")

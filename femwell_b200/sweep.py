@@ -104,3 +104,66 @@ def group_index(wavelengths, n_eff):
     """n_g = n_eff - lambda d n_eff / d lambda by central differences (docs/math/dispersion.md:153-161)."""
     wavelengths = np.asarray(wavelengths, dtype=np.float64)
     return n_eff - wavelengths * np.gradient(n_eff, wavelengths)
+
+
+# ------------------------------------------------------------------ BASELINE config 4: coupled-waveguide geometry sweep
+COUPLER_COLUMNS = ("n_eff_sym", "n_eff_asym", "n_eff_1", "coupling_length_um", "A_into_1", "A_into_2",
+                   "crosstalk_coeff", "ref_overlap_iso", "ref_overlap_sym")
+
+
+def coupler_point(gap: float, width: float, *, n: int = 224, wavelength: float = 1.55, order: int = 2,
+                  core_index: float = 3.4777, clad_index: float = 1.444, delta_width: float = 0.01,
+                  reference_mode=None, solver_options=None):
+    """One geometry of a coupled-waveguide sweep (docs/photonics/examples/crosstalk.py:147-243 and
+    coupled_mode_theory.py:41-147): its own mesh, the two supermodes of the pair, the mode of waveguide 1 in isolation
+    (same mesh: the CSR pattern and the LU analysis of the first solve are reused), the same-mesh overlaps of the
+    isolated mode with both supermodes, the worst-case crosstalk coefficient and the coupling length.  With
+    ``reference_mode`` (a ``Mode`` on ANOTHER mesh) two cross-mesh overlaps are added (waveguide.py:737-759).
+    Returns ``(row, modes_both, modes_1)`` with ``row`` ordered as ``COUPLER_COLUMNS``."""
+    from .basis import Basis
+    from .element import ElementTriP0
+    from .maxwell.waveguide import compute_modes
+    from .mesh import coupled_waveguide_mesh
+
+    mesh = coupled_waveguide_mesh(n, gap=gap, w_core_1=width, w_core_2=width + delta_width)
+    b0 = Basis(mesh, ElementTriP0(), intorder=4)
+    eps_both = np.full(mesh.nelements, clad_index**2)
+    eps_both[mesh.subdomains["core_1"]] = core_index**2
+    eps_1 = eps_both.copy()
+    eps_both[mesh.subdomains["core_2"]] = core_index**2
+    so = dict(solver_options or {})
+    modes_both = compute_modes(b0, eps_both, wavelength, num_modes=2, order=order, solver_options=dict(so))
+    modes_1 = compute_modes(b0, eps_1, wavelength, num_modes=1, order=order, solver_options=dict(so))
+    a1 = abs(modes_1[0].calculate_overlap(modes_both[0])) ** 2
+    a2 = abs(modes_1[0].calculate_overlap(modes_both[1])) ** 2
+    c1, c2 = np.sqrt(a1 / (a1 + a2)), np.sqrt(a2 / (a1 + a2))
+    crosstalk = 4 * c1**2 * c2**2  # crosstalk.py:246-262: worst-case EME power transfer 1 - (c1^4 + c2^4 - 2 c1^2 c2^2)
+    k0 = 2 * np.pi / wavelength
+    dn = np.real(modes_both[0].n_eff - modes_both[1].n_eff)
+    lc = np.pi / (k0 * dn) if dn != 0 else np.inf  # coupled_mode_theory.py:127
+    ro_iso = ro_sym = np.nan
+    if reference_mode is not None:
+        ro_iso = abs(modes_1[0].calculate_overlap(reference_mode))
+        ro_sym = abs(modes_both[0].calculate_overlap(reference_mode))
+    row = [np.real(modes_both[0].n_eff), np.real(modes_both[1].n_eff), np.real(modes_1[0].n_eff), lc, a1, a2,
+           crosstalk, ro_iso, ro_sym]
+    return row, modes_both, modes_1
+
+
+def coupler_geometry_sweep(gaps, widths, *, n: int = 224, wavelength: float = 1.55, order: int = 2,
+                           cross_mesh: bool = True, **kw) -> np.ndarray:
+    """BASELINE config 4: ``len(gaps) x len(widths)`` coupled-waveguide geometries, block-partitioned over the ranks, one
+    geometry = one mesh + 2 solves (3 modes) + 2 same-mesh overlaps (+ 2 cross-mesh overlaps against the isolated mode of
+    the rank's first geometry when ``cross_mesh``), results all_gathered once.  Returns
+    ``(n_points, len(COUPLER_COLUMNS) + 1)`` (last column: status; NaN rows for failed points)."""
+    points = [(float(g), float(w)) for g in gaps for w in widths]
+    state = {"ref": None}
+
+    def solve_point(i, pt):
+        row, _both, m1 = coupler_point(pt[0], pt[1], n=n, wavelength=wavelength, order=order,
+                                       reference_mode=state["ref"] if cross_mesh else None, **kw)
+        if cross_mesh and state["ref"] is None:
+            state["ref"] = m1[0]  # later geometries of this rank are compared with it across meshes
+        return row
+
+    return sweep(points, solve_point, len(COUPLER_COLUMNS))

@@ -308,6 +308,47 @@ def test_msh_round_trip_keeps_mesh_and_groups(tmp_path):
         assert np.array_equal(np.sort(r.boundaries[k]), np.sort(m.boundaries[k]))
 
 
+@pytest.mark.parametrize("version,binary", [("2.2", True), ("4.1", False), ("4.1", True)])
+def test_msh_binary_and_v41_round_trip(tmp_path, version, binary):
+    """gmsh writes binary files by default when Mesh.Binary=1 (2.2: int32 records; 4.1: size_t tags, entity blocks)."""
+    from femwell_b200.msh import read_msh, write_msh
+
+    m, _ = strip_problem(7, slab_h=0.11, jitter=0.1)
+    m = m.with_boundaries({"left": lambda x: x[0] < x[0].min() + 1e-9, "top": lambda x: x[1] > x[1].max() - 1e-9})
+    path = str(tmp_path / "strip.msh")
+    write_msh(m, path, version=version, binary=binary)
+    raw = open(path, "rb").read()
+    assert raw.startswith(b"$MeshFormat\n" + version.encode() + (b" 1 8" if binary else b" 0 8"))
+    r = read_msh(path)
+    assert np.array_equal(r.p, m.p)
+    if version == "2.2":
+        assert np.array_equal(r.t, m.t)
+        for k in ("core", "slab", "box", "clad"):
+            assert np.array_equal(r.subdomains[k], m.subdomains[k])
+    else:  # 4.1 groups the elements by entity: same triangles and groups, permuted
+        key = lambda mm, idx: sorted(map(tuple, mm.t[:, idx].T.tolist()))  # noqa: E731
+        assert key(r, np.arange(r.nelements)) == key(m, np.arange(m.nelements))
+        for k in ("core", "slab", "box", "clad"):
+            assert key(r, r.subdomains[k]) == key(m, m.subdomains[k])
+    for k in ("left", "top"):
+        fk = lambda mm: sorted(map(tuple, mm.facets[:, mm.boundaries[k]].T.tolist()))  # noqa: E731
+        assert fk(r) == fk(m)
+
+
+def test_read_msh_big_endian_binary(tmp_path):
+    from femwell_b200.msh import read_msh
+
+    nodes = np.empty(3, dtype=np.dtype([("id", ">i4"), ("x", ">f8", 3)]))
+    nodes["id"], nodes["x"] = [1, 2, 3], [[0, 0, 0], [1, 0, 0], [0, 1, 0]]
+    body = (b"$MeshFormat\n2.2 1 8\n" + np.array([1], dtype=">i4").tobytes() + b"\n$EndMeshFormat\n$Nodes\n3\n"
+            + nodes.tobytes() + b"\n$EndNodes\n$Elements\n1\n" + np.array([2, 1, 0, 1, 1, 2, 3], dtype=">i4").tobytes()
+            + b"\n$EndElements\n")
+    path = tmp_path / "be.msh"
+    path.write_bytes(body)
+    m = read_msh(str(path))
+    assert m.nelements == 1 and np.array_equal(m.p, [[0, 1, 0], [0, 0, 1]])
+
+
 def test_read_msh_entity_with_two_physical_groups(tmp_path):
     """gmsh 4.1: an entity may carry several physical tags; every one of them becomes a sub-domain."""
     from femwell_b200.msh import read_msh
@@ -526,3 +567,79 @@ def test_oracle_error_estimator_of_a_constant_field_is_analytic():
         for kk in range(3):
             mom = (vec[3 + kk, k, 0] * tang[k][0] + vec[3 + kk, k, 1] * tang[k][1]) @ w
             assert abs(mom - (1.0 if k == kk else 0.0)) < 1e-14
+
+
+# ----------------------------------------------------------------------------- adaptive refinement (refinement.py:58-105)
+def _areas(m):
+    a, b, c = m.p[:, m.t[0]], m.p[:, m.t[1]], m.p[:, m.t[2]]
+    return 0.5 * np.abs((b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0]))
+
+
+def test_adaptive_refinement_is_conforming_and_keeps_groups():
+    from femwell_b200.mesh import adaptive_theta
+
+    m = MeshTri.rectangle(4, jitter=0.1).with_subdomains({"low": lambda c: c[1] < 0.5})
+    q0 = None
+    for _ in range(5):
+        sel = np.nonzero(np.hypot(*(m.centroids() - 0.3)) < 0.2)[0]
+        r = m.refined(sel)
+        assert abs(_areas(r).sum() - 1) < 1e-12
+        assert set(np.unique(r._facet_count)) <= {1, 2}  # no hanging node: every facet has one or two elements
+        bl = r.boundary_facets()
+        assert abs(np.hypot(*(r.p[:, r.facets[0, bl]] - r.p[:, r.facets[1, bl]])).sum() - 4) < 1e-12
+        assert abs(_areas(r)[r.subdomains["low"]].sum() - _areas(m)[m.subdomains["low"]].sum()) < 1e-12
+        for name in ("left", "right", "top", "bottom"):
+            fl = r.boundaries[name]
+            assert abs(np.hypot(*(r.p[:, r.facets[0, fl]] - r.p[:, r.facets[1, fl]])).sum() - 1) < 1e-12
+        # every selected triangle was split into four; shape regularity does not degrade
+        assert r.nelements >= m.nelements + 3 * sel.size
+        assert np.array_equal(np.bincount(r.parent_elements)[sel], np.full(sel.size, 4))
+        edge = np.max([np.hypot(*(r.p[:, r.t[i]] - r.p[:, r.t[j]])) for i, j in ((0, 1), (1, 2), (0, 2))], axis=0)
+        q = (_areas(r) / edge**2).min()
+        q0 = q if q0 is None else q0
+        assert q > 0.99 * q0
+        m = r
+    u = MeshTri.rectangle(3).refined()
+    assert u.nelements == 4 * 18 and u.nvertices == 16 + 33
+    assert MeshTri.rectangle(3).refined(2).nelements == 16 * 18
+    est = np.array([0.1, 1.0, 0.6, 0.49])
+    assert adaptive_theta(est, theta=0.5).tolist() == [1, 2]
+    assert adaptive_theta(est, theta=0.5, max=1.1).tolist() == [1, 2]
+
+
+def test_oracle_adaptive_loop_converges_to_the_known_answer():
+    """refinement.py:58-80 with the oracle in place of compute_modes: solve, estimate, adaptive_theta, refine.  The
+    error against the literature value must fall while only part of the mesh is refined."""
+    from femwell_b200.mesh import adaptive_theta
+
+    (ec, ecl), bnd, ref = RECT_CASES[0]
+    m = MeshTri.rectangle(6, frozen_x=[0.5], frozen_y=[0.5]).with_subdomains(
+        {"core": lambda c: (c[0] < 0.5) & (c[1] < 0.5)})
+    X, W = triangle_quadrature(2)
+    errs, nes = [], []
+    for _ in range(4):
+        eps = np.full(m.nelements, ecl)
+        eps[m.subdomains["core"]] = ec
+        fsel = np.unique(np.concatenate([m.boundaries[b] for b in bnd]))
+        r = fo.compute_modes(m.p, m.t, 0, eps, 1.5, X, W, num_modes=1, order=1, dirichlet_facets=fsel, with_h=False)
+        errs.append(abs(r.n_effs[0].real - ref))
+        nes.append(m.nelements)
+        b = Basis(m, ElementTriP0(), intorder=2).with_element(mode_element(1))
+        eta = fo.eval_error_estimator(m.p, m.t, b.element_dofs.astype(np.int64), 1, r.E[:, 0], 0, eps)
+        sel = adaptive_theta(eta, theta=0.5)
+        assert 0 < sel.size < m.nelements
+        m = m.refined(sel)
+    assert errs[-1] < 0.5 * errs[0] and nes[-1] < 16 * nes[0]
+
+
+def test_coupled_waveguide_mesh_groups():
+    from femwell_b200.mesh import coupled_waveguide_mesh
+
+    m = coupled_waveguide_mesh(40, gap=0.3, w_core_1=0.45, w_core_2=0.46)
+    a = _areas(m)
+    assert abs(a[m.subdomains["core_1"]].sum() - 0.45 * 0.22) < 1e-12
+    assert abs(a[m.subdomains["core_2"]].sum() - 0.46 * 0.22) < 1e-12
+    assert abs(a[m.subdomains["box"]].sum() - 4.0) < 1e-12
+    assert sum(v.size for v in m.subdomains.values()) == m.nelements == 3200
+    c = m.centroids()
+    assert c[0, m.subdomains["core_1"]].max() < -0.15 and c[0, m.subdomains["core_2"]].min() > 0.15

@@ -1029,3 +1029,88 @@ def test_device_lu_analysis_equals_host_analysis(ctx, order, n, leaf, dirichlet)
         assert G[key] == S[key], key
     for key in ("perm", "iperm", "node_of", "m", "ns", "own_start", "blist", "rel", "blist_off"):
         assert np.array_equal(np.asarray(G[key], dtype=np.int64), np.asarray(S[key], dtype=np.int64)), key
+
+
+# ----------------------------------------------------------------------------- adaptive refinement loop (refinement.py:58-105)
+def test_adaptive_refinement_loop_matches_oracle_and_converges(ctx):
+    """solve -> eval_error_estimator -> adaptive_theta -> mesh.refined, four rounds on rectangle case 0 (order 1, PEC
+    sides): on every (unstructured) refined mesh n_eff equals the oracle's to 1e-9 and the indicator the oracle's to
+    1e-9; the error against the literature value falls."""
+    from femwell_b200.maxwell.waveguide import compute_modes
+    from femwell_b200.mesh import adaptive_theta
+
+    (ec, ecl), bnd, ref = RECT_CASES[0]
+    m = MeshTri.rectangle(6, frozen_x=[0.5], frozen_y=[0.5]).with_subdomains(
+        {"core": lambda c: (c[0] < 0.5) & (c[1] < 0.5)})
+    errs = []
+    for it in range(4):
+        b0 = Basis(m, ElementTriP0(), intorder=2)
+        eps = np.full(m.nelements, ecl)
+        eps[m.subdomains["core"]] = ec
+        modes = compute_modes(b0, eps, 1.5, num_modes=1, order=1, metallic_boundaries=bnd)
+        md = modes[0]
+        fsel = np.unique(np.concatenate([m.boundaries[b] for b in bnd]))
+        r = fo.compute_modes(m.p, m.t, 0, eps, 1.5, md.basis.X, md.basis.W, num_modes=1, order=1,
+                             dirichlet_facets=fsel, with_h=False)
+        assert abs(md.n_eff - r.n_effs[0]) < 1e-9 * abs(r.n_effs[0]), (it, md.n_eff, r.n_effs[0])
+        errs.append(abs(md.n_eff.real - ref))
+        eta = md.eval_error_estimator()
+        eta_ref = fo.eval_error_estimator(m.p, m.t, md.basis.element_dofs.astype(np.int64), 1, md.E, 0, eps)
+        assert np.abs(eta - eta_ref).max() < 1e-9 * eta_ref.max()
+        sel = adaptive_theta(eta, theta=0.5)
+        assert 0 < sel.size < m.nelements
+        m = m.refined(sel)
+    assert errs[-1] < 0.5 * errs[0], errs
+
+
+# ----------------------------------------------------------------------------- config 4: coupled-waveguide geometry sweep
+def test_coupler_geometry_sweep_matches_oracle(ctx):
+    """BASELINE config 4 (crosstalk.py:147-243, coupled_mode_theory.py:41-147) at test size: per geometry its own mesh,
+    supermodes + isolated mode, same-mesh overlaps and two cross-mesh overlaps; n_eff 1e-9 and |overlap|^2 1e-6 vs the
+    oracle on every geometry."""
+    from femwell_b200.mesh import coupled_waveguide_mesh
+    from femwell_b200.sweep import COUPLER_COLUMNS, coupler_geometry_sweep
+
+    gaps, widths, n = [0.2, 0.35], [0.44, 0.5], 22
+    table = coupler_geometry_sweep(gaps, widths, n=n, order=2)
+    assert table.shape == (4, len(COUPLER_COLUMNS) + 1) and (table[:, -1] == 0).all()
+    col = {c: i for i, c in enumerate(COUPLER_COLUMNS)}
+    X, W = triangle_quadrature(4)
+    pts = [(g, w) for g in gaps for w in widths]
+    for row, (g, w) in zip(table, pts):
+        m = coupled_waveguide_mesh(n, gap=g, w_core_1=w, w_core_2=w + 0.01)
+        eps1 = np.full(m.nelements, 1.444**2)
+        eps1[m.subdomains["core_1"]] = 3.4777**2
+        eps2 = eps1.copy()
+        eps2[m.subdomains["core_2"]] = 3.4777**2
+        N = m.nvertices + 3 * m.nfacets + 2 * m.nelements
+        v0 = np.random.default_rng(0).uniform(-1, 1, N)
+        rb = fo.compute_modes(m.p, m.t, 0, eps2, 1.55, X, W, num_modes=2, order=2, v0=v0)
+        r1 = fo.compute_modes(m.p, m.t, 0, eps1, 1.55, X, W, num_modes=1, order=2, v0=v0)
+        nb = np.sort(rb.n_effs.real)[::-1]
+        assert abs(row[col["n_eff_sym"]] - nb[0]) < 1e-9 * nb[0]
+        assert abs(row[col["n_eff_asym"]] - nb[1]) < 1e-9 * nb[1]
+        assert abs(row[col["n_eff_1"]] - r1.n_effs[0].real) < 1e-9 * nb[0]
+        b = Basis(m, ElementTriP0(), intorder=4).with_element(mode_element(2))
+        ed = b.element_dofs.astype(np.int64)
+        order_b = np.argsort(-rb.n_effs.real)
+        ov = [abs(fo.calculate_overlap(m.p, m.t.astype(np.int64), ed, 2, X, W, r1.E[:, 0], r1.H[:, 0],
+                                       rb.E[:, j], rb.H[:, j])) ** 2 for j in order_b]
+        # compare fields only where the oracle's own vector is an eigenvector (ARPACK null(M) pollution, see above)
+        k0, zd = 2 * np.pi / 1.55, b.split_indices()[1]
+
+        def eig_residual(rr, j):
+            x = np.array(rr.E[:, j], dtype=complex)
+            x[zd] *= 1j * np.sqrt(rr.lams[j] / k0**4)
+            return np.linalg.norm(-(rr.A @ x) + rr.lams[j] * (rr.B @ x)) / np.linalg.norm(rr.A @ x)
+
+        for c, j in zip(("A_into_1", "A_into_2"), order_b):
+            if max(eig_residual(rb, j), eig_residual(r1, 0)) < 1e-9:
+                assert abs(row[col[c]] - ov[list(order_b).index(j)]) < 1e-6, (c, row[col[c]], ov)
+        assert abs(row[col["A_into_1"]] + row[col["A_into_2"]] - 1) < 0.05  # two supermodes carry the isolated mode
+        assert row[col["coupling_length_um"]] > 0 and 0 <= row[col["crosstalk_coeff"]] <= 1
+    # the first geometry is the cross-mesh reference of the others: overlap of near-identical isolated modes ~ 1
+    assert np.isnan(table[0, col["ref_overlap_iso"]])
+    assert np.all(table[1:, col["ref_overlap_iso"]] > 0.8) and np.all(table[1:, col["ref_overlap_iso"]] < 1.05)
+    # coupling gets weaker (coupling length longer) with the gap at fixed width
+    assert table[2, col["coupling_length_um"]] > table[0, col["coupling_length_um"]]
