@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 if verbose and out:
                     print(out)
     if jobs or not os.path.exists(LIB):
-        run([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"])
+        run([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"])
     return LIB
 
 

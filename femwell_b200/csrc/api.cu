@@ -193,7 +193,7 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
   FW_REQUIRE(s->nqp >= 1 && s->nqp <= MAXQ, "nqp out of range (1..12)");
   FW_REQUIRE(s->n_vertices > 0 && s->n_elements > 0 && s->n_dofs > 0, "empty mesh");
   FW_REQUIRE(s->p && s->t && s->element_dofs && s->kind && s->vec && s->sc && s->X && s->W, "NULL array");
-  Timer tu(h.stream);
+  Timer tu(h.stream, "fw:set_space upload");
   sp.order = s->order;
   sp.nv = s->n_vertices;
   sp.ne = s->n_elements;
@@ -346,7 +346,7 @@ int fw_symbolic(fw_handle* hh, int64_t* nnz) {
   Handle& h = hh->h;
   FW_CHECK_CUDA(cudaSetDevice(h.device));
   current_pool() = &h.pool;
-  Timer t(h.stream);
+  Timer t(h.stream, "fw:symbolic (COO sort + CSR pattern)");
   symbolic_space(h);
   h.tim.symbolic_ms = t.stop();
   if (nnz) *nnz = h.pat.nnz;
@@ -512,7 +512,7 @@ int fw_eigs_csr(fw_handle* hh, int32_t n, const int32_t* K_indptr, const int32_t
   current_pool() = &h.pool;
   h.tim = fw_timings{};
   {
-    Timer t(h.stream);
+    Timer t(h.stream, "fw:generic CSR setup");
     setup_generic_csr(h, n, K_indptr, K_indices, K_data, M_indptr, M_indices, M_data, is_complex != 0, coords);
     h.tim.upload_ms = t.stop();
   }
@@ -539,12 +539,12 @@ int fw_lu_factor_shifted(fw_handle* hh, double sigma_re, double sigma_im, int32_
     active[dirichlet[i]] = 0;
   }
   {
-    Timer t(h.stream);
+    Timer t(h.stream, "fw:LU analysis");
     lu_analyse(h, active, leaf_elements);
     h.tim.lu_symbolic_ms = t.stop();
   }
   {
-    Timer t(h.stream);
+    Timer t(h.stream, "fw:LU factor");
     lu_factor(h, -1.0, 0.0, sigma_re, sigma_im, h.A.is_complex || sigma_im != 0.0);
     h.tim.lu_factor_ms = t.stop();
   }
@@ -565,6 +565,13 @@ int fw_lu_solve(fw_handle* hh, int32_t rhs_is_complex, const void* b, void* x, i
   cudaStream_t s = h.stream;
   const bool lu_c = h.lu->is_complex;
   DevBuf<double> db, dx;
+  // FW_SOLVE_TIME=1: device time of the substitution pair alone (scripts/nrhs_probe.py)
+  auto timed_solve = [&](const void* bp, void* xp, int nrhs) {
+    if (!getenv("FW_SOLVE_TIME")) return lu_solve_dev(h, bp, xp, nrhs);
+    Timer t(s);
+    lu_solve_dev(h, bp, xp, nrhs);
+    fprintf(stderr, "[fw-solve] nrhs %d: %.3f ms\n", nrhs, t.stop());
+  };
   if (lu_c) {
     std::vector<double> tmp((size_t)2 * n);
     if (rhs_is_complex)
@@ -573,7 +580,7 @@ int fw_lu_solve(fw_handle* hh, int32_t rhs_is_complex, const void* b, void* x, i
       for (int i = 0; i < n; ++i) tmp[2 * (size_t)i] = ((const double*)b)[i], tmp[2 * (size_t)i + 1] = 0.0;
     db.upload(tmp.data(), tmp.size(), s);
     dx.alloc((size_t)2 * n);
-    lu_solve_dev(h, db.p, dx.p, 1);
+    timed_solve(db.p, dx.p, 1);
     std::vector<double> out((size_t)2 * n);
     dx.download(out.data(), out.size(), s);
     FW_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -584,7 +591,7 @@ int fw_lu_solve(fw_handle* hh, int32_t rhs_is_complex, const void* b, void* x, i
   } else if (!rhs_is_complex) {
     db.upload((const double*)b, (size_t)n, s);
     dx.alloc((size_t)n);
-    lu_solve_dev(h, db.p, dx.p, 1);
+    timed_solve(db.p, dx.p, 1);
     dx.download((double*)x, (size_t)n, s);
     FW_CHECK_CUDA(cudaStreamSynchronize(s));
   } else {
@@ -596,7 +603,7 @@ int fw_lu_solve(fw_handle* hh, int32_t rhs_is_complex, const void* b, void* x, i
     }
     db.upload(tmp.data(), tmp.size(), s);
     dx.alloc((size_t)2 * n);
-    lu_solve_dev(h, db.p, dx.p, 2);
+    timed_solve(db.p, dx.p, 2);
     dx.download(tmp.data(), tmp.size(), s);
     FW_CHECK_CUDA(cudaStreamSynchronize(s));
     for (int i = 0; i < n; ++i) {
@@ -619,7 +626,7 @@ int fw_postprocess_modes(fw_handle* hh, int32_t k, const double* lams, const dou
   DevBuf<double> dE, dH;
   dE.upload(X, cnt, h.stream);
   dH.alloc(cnt);
-  Timer t(h.stream);
+  Timer t(h.stream, "fw:postprocess (H field, power)");
   postprocess_modes_dev(h, k, (const std::complex<double>*)lams, dE.p, k0, omega, mu0, dE.p, dH.p,
                         (std::complex<double>*)powers);
   h.tim.postprocess_ms = t.stop();
@@ -813,7 +820,7 @@ int fw_compute_modes(fw_handle* hh, const fw_modes_params* prm, double* lams, do
   h.tim = fw_timings{};
   h.tim.upload_ms = keep_upload;
   h.tim.symbolic_ms = keep_symbolic;
-  Timer total(s);
+  Timer total(s, "fw:compute_modes");
   {
     // the host analysis of the sparse LU only needs the mesh and the Dirichlet set: start it now, it runs on worker
     // threads while the GPU sorts the COO keys and assembles
@@ -826,7 +833,7 @@ int fw_compute_modes(fw_handle* hh, const fw_modes_params* prm, double* lams, do
     lu_analyse_prefetch(h, active, prm->eigs.leaf_elements);
   }
   if (!(prm->reuse_symbolic && h.has_symbolic)) {
-    Timer t(s);
+    Timer t(s, "fw:symbolic (COO sort + CSR pattern)");
     symbolic_space(h);
     h.tim.symbolic_ms = t.stop();
   }
@@ -848,7 +855,7 @@ int fw_compute_modes(fw_handle* hh, const fw_modes_params* prm, double* lams, do
   }
   Hd.alloc(cnt);
   {
-    Timer t(s);
+    Timer t(s, "fw:postprocess (H field, power)");
     const double c0 = 299792458.0, mu0 = 1.25663706212e-06;
     postprocess_modes_dev(h, k, (const std::complex<double>*)lams, Xd.p, k0, k0 * c0, mu0, Xd.p, Hd.p,
                           (std::complex<double>*)powers);
@@ -858,7 +865,7 @@ int fw_compute_modes(fw_handle* hh, const fw_modes_params* prm, double* lams, do
   h.tim.total_ms = total.stop();
   h.tim.nnz_structural = h.pat.nnz;
   {
-    Timer t(s);
+    Timer t(s, "fw:download");
     download_staged(h, E, Xd.p, cnt * sizeof(double));
     download_staged(h, H, Hd.p, cnt * sizeof(double));
     h.tim.download_ms = t.stop();

@@ -703,7 +703,7 @@ bool eigs_shift_invert(Handle& h, const fw_eigs_params& prm, cd* lams, DevBuf<do
   cudaStream_t s = h.stream;
   if (st) memset(st, 0, sizeof(*st));
   {
-    Timer t(s);
+    Timer t(s, "fw:LU analysis");
     lu_analyse(h, active, prm.leaf_elements);
     double ms = t.stop();
     h.tim.lu_symbolic_ms = ms;
@@ -712,7 +712,7 @@ bool eigs_shift_invert(Handle& h, const fw_eigs_params& prm, cd* lams, DevBuf<do
   const cd sigma(prm.sigma_re, prm.sigma_im);
   const bool cplx_arith = h.A.is_complex || prm.sigma_im != 0.0;
   {
-    Timer t(s);
+    Timer t(s, "fw:LU factor");
     // K - sigma M = -A + sigma B
     lu_factor(h, -1.0, 0.0, prm.sigma_re, prm.sigma_im, cplx_arith);
     double ms = t.stop();
@@ -735,7 +735,7 @@ bool eigs_shift_invert(Handle& h, const fw_eigs_params& prm, cd* lams, DevBuf<do
   int refine = prm.refine > 0 ? prm.refine : 0;
   bool converged = true;
   {
-    Timer t(s);
+    Timer t(s, "fw:Arnoldi (shift-invert)");
     for (int attempt = 0; attempt < 3; ++attempt) {
       tmp = fw_eigs_stats{};
       if (!cplx_arith)

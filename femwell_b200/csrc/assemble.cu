@@ -500,7 +500,7 @@ static void assemble_ab_typed(Handle& h, int eps_kind, const void* eps_host, dou
   const double inv_radius = std::isinf(radius) ? 0.0 : 1.0 / radius;
   upload_tables(h);
   {
-    Timer tk(s);
+    Timer tk(s, "fw:element kernel K1");
     static const bool no_fast = getenv("FW_K1_GENERIC") != nullptr;
     const bool fast = inv_radius == 0.0 && eps_kind != FW_EPS_DG_P1 && !no_fast;
     h.tim.element_kernel_launches = fast ? 1 : 3;
@@ -545,7 +545,7 @@ static void assemble_ab_typed(Handle& h, int eps_kind, const void* eps_host, dou
     v->nnz_kept = -1;
   }
   {
-    Timer tr(s);
+    Timer tr(s, "fw:segmented reduce K2b");
     reduce_onto_pattern<S>(pat, bA, nullptr, 0, sp.ne, (S*)h.A.v.p, h.A.flag.p, s);
     reduce_onto_pattern<S>(pat, bB, lut_dev.p, (int)lut.size(), sp.ne, (S*)h.B.v.p, h.B.flag.p, s, pat.tt_slots.p,
                            pat.n_tt);

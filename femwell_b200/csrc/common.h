@@ -1,6 +1,7 @@
 // Shared internals of libfemwell_b200: error handling, scalar types, device buffers, handle.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cmath>
 #include <complex>
@@ -228,10 +229,17 @@ struct DevBuf {
   }
 };
 
+// CUDA-event stage timer; a named timer also opens an NVTX range (visible in nsys / ncu --nvtx timelines) that
+// closes with stop() or the destructor
 struct Timer {
   cudaEvent_t a = nullptr, b = nullptr;
   cudaStream_t s;
-  explicit Timer(cudaStream_t st) : s(st) {
+  bool range = false;
+  explicit Timer(cudaStream_t st, const char* name = nullptr) : s(st) {
+    if (name) {
+      nvtxRangePushA(name);
+      range = true;
+    }
     cudaEventCreate(&a);
     cudaEventCreate(&b);
     cudaEventRecord(a, s);
@@ -241,9 +249,14 @@ struct Timer {
     cudaEventSynchronize(b);
     float ms = 0;
     cudaEventElapsedTime(&ms, a, b);
+    if (range) {
+      nvtxRangePop();
+      range = false;
+    }
     return ms;
   }
   ~Timer() {
+    if (range) nvtxRangePop();
     if (a) cudaEventDestroy(a);
     if (b) cudaEventDestroy(b);
   }

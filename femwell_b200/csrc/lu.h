@@ -58,6 +58,7 @@ struct SolveGraph {
   void* x = nullptr;
   int nrhs = 0;
   int uses = 0;
+  int kernels = 0;  // kernel nodes of the captured sequence
   cudaGraphExec_t exec = nullptr;
 };
 

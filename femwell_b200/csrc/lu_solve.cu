@@ -1059,13 +1059,13 @@ void lu_solve_dev(Handle& h, const void* b, void* x, int nrhs) {
     if (c.b == b && c.x == x && c.nrhs == nrhs) g = &c;
   if (!g) {
     if (lu.graphs.size() >= 8) lu.drop_graphs();
-    lu.graphs.push_back(SolveGraph{b, x, nrhs, 0, nullptr});
+    lu.graphs.push_back(SolveGraph{b, x, nrhs, 0, 0, nullptr});
     g = &lu.graphs.back();
   }
   ++g->uses;
   if (g->exec) {
     FW_CHECK_CUDA(cudaGraphLaunch(g->exec, h.stream));
-    h.tim.kernel_launches += 1;
+    h.tim.kernel_launches += g->kernels;  // kernel nodes replayed by this graph launch
     return;
   }
   if (g->uses < 2) {  // first use: eager (allocates the work buffers, sets the function attributes)
@@ -1082,14 +1082,13 @@ void lu_solve_dev(Handle& h, const void* b, void* x, int nrhs) {
     if (graph) cudaGraphDestroy(graph);
     throw;
   }
-  h.tim.kernel_launches = launches_before;
+  g->kernels = (int)(h.tim.kernel_launches - launches_before);
   FW_CHECK_CUDA(cudaStreamEndCapture(h.stream, &graph));
   cudaGraphExec_t exec = nullptr;
   FW_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
   cudaGraphDestroy(graph);
   g->exec = exec;
   FW_CHECK_CUDA(cudaGraphLaunch(exec, h.stream));
-  h.tim.kernel_launches += 1;
 }
 
 static void lu_solve_launch(Handle& h, const void* b, void* x, int nrhs) {

@@ -208,7 +208,7 @@ static void mass_solve(Handle& h, const cplx* b, cplx* x) {
 // all k modes at once: rhs_i = C0 e_i + i beta_i C1 e_i, one block PCG for the k mass solves
 void hfield_multi_dev(Handle& h, int k, const cplx* E_dev, const cplx* betas, double omega, double mu0, cplx* H_dev) {
   Trace tr(h.stream);
-  Timer th(h.stream);
+  Timer th(h.stream, "fw:H field (mass solves)");
   h.tim.pcg_iterations = 0;
   h.tim.pcg_rel_residual = 0.0;
   h.tim.mass_direct_blocks = 0;
