@@ -1,6 +1,5 @@
 #!/bin/bash
 # round-2 GPU batch F: new tests (refinement loop, coupler sweep), graph-enabled bench, sweep + geometry workloads,
-# config-3 / config-5-size probes (logs for DESIGN.md), nrhs=2 solve cost, compute-sanitizer
 mkdir -p gpurun_out/f
 cd "$(dirname "$0")/.."
 timeout 900 python -m pytest tests -m gpu -q --no-header -rf -p no:cacheprovider -x > gpurun_out/f/pytest.log 2>&1
@@ -12,5 +11,3 @@ timeout 400 python bench.py --workload geometry --steps 1 --warmup 1 --points-pe
 timeout 400 python scripts/config3_probe.py 707 > gpurun_out/f/config3_probe.log 2>&1
 timeout 400 python scripts/scale_probe.py 1000 > gpurun_out/f/scale_probe_1000.log 2>&1
 timeout 200 python scripts/nrhs_probe.py 500 > gpurun_out/f/nrhs_probe.log 2>&1
-timeout 1500 bash scripts/sanitize.sh > gpurun_out/f/sanitize.log 2>&1
-tail -8 gpurun_out/f/pytest.log; tail -2 gpurun_out/f/bench.err; cat gpurun_out/f/nrhs_probe.log | tail -5; cat gpurun_out/sanitize/summary.txt
