@@ -44,6 +44,6 @@ struct LUDevice {
 // large-front GEMM (lu_gemm.cu)
 template <class S>
 void lu_gemm_big_launch(FrontTab T, const int* nodes, int nfront, int kstep, S* F, int max_rem, bool schur,
-                        cudaStream_t s);
+                        cudaStream_t s, int kw = PW);
 
 }  // namespace fw

@@ -25,7 +25,7 @@ constexpr int G2_KC = 16;
 // SCHUR = true : deferred Schur complement, S22 -= L21 U12 over the full pivot block.
 template <class S, bool SCHUR>
 __global__ void __launch_bounds__(256) k_lu_gemm_big(FrontTab T, const int* __restrict__ nodes, int kstep,
-                                                     S* __restrict__ F) {
+                                                     S* __restrict__ F, int kw) {
   constexpr int MT = Gemm2Cfg<S>::MT, H = MT / 2;
   constexpr int TM = 16 * MT;     // CTA tile edge
   constexpr int LDB = TM + 2;     // padded row length of Bs (keeps 16-byte alignment, 2-way store conflicts)
@@ -35,9 +35,9 @@ __global__ void __launch_bounds__(256) k_lu_gemm_big(FrontTab T, const int* __re
   S(*Bs)[G2_KC][LDB] = reinterpret_cast<S(*)[G2_KC][LDB]>(g2_smem + sizeof(S) * 2 * G2_KC * TM);
   const int node = nodes[blockIdx.x];
   const int m = T.m[node], ns = T.ns[node];
-  const int k0 = SCHUR ? 0 : kstep * PW;
+  const int k0 = SCHUR ? 0 : kstep * kw;  // kw: width of the column block (one panel, or an outer block)
   if (k0 >= ns) return;
-  const int klen = SCHUR ? ns : min(PW, ns - k0);
+  const int klen = SCHUR ? ns : min(kw, ns - k0);
   const int r0 = SCHUR ? ns : k0 + klen;
   const int nrem = m - r0;
   if (nrem <= 0) return;
@@ -152,13 +152,13 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 
 template <bool SCHUR>
 __global__ void __launch_bounds__(DM_THREADS, 1) k_lu_gemm_dmma(FrontTab T, const int* __restrict__ nodes, int kstep,
-                                                                double* __restrict__ F) {
+                                                                double* __restrict__ F, int kw) {
   extern __shared__ __align__(16) double dm_smem[];
   const int node = nodes[blockIdx.x];
   const int m = T.m[node], ns = T.ns[node];
-  const int k0 = SCHUR ? 0 : kstep * PW;
+  const int k0 = SCHUR ? 0 : kstep * kw;  // kw: width of the column block (one panel, or an outer block)
   if (k0 >= ns) return;
-  const int klen = SCHUR ? ns : min(PW, ns - k0);
+  const int klen = SCHUR ? ns : min(kw, ns - k0);
   const int r0 = SCHUR ? ns : k0 + klen;
   const int nrem = m - r0;
   if (nrem <= 0) return;
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(DM_THREADS, 1) k_lu_gemm_dmma(FrontTab T, cons
 }
 
 static void lu_gemm_dmma_launch(FrontTab T, const int* nodes, int nfront, int kstep, double* F, int max_rem, bool schur,
-                                cudaStream_t s) {
+                                cudaStream_t s, int kw) {
   constexpr size_t smem = sizeof(double) * DM_STAGES * DM_STAGE_DOUBLES;
   const int nt = (max_rem + DM_TM - 1) / DM_TM;
   if (nt <= 0) return;
@@ -259,28 +259,28 @@ static void lu_gemm_dmma_launch(FrontTab T, const int* nodes, int nfront, int ks
     FW_CHECK_CUDA(cudaFuncSetAttribute(k_lu_gemm_dmma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   if (schur)
-    k_lu_gemm_dmma<true><<<dim3(nfront, nt, nt), DM_THREADS, smem, s>>>(T, nodes, kstep, F);
+    k_lu_gemm_dmma<true><<<dim3(nfront, nt, nt), DM_THREADS, smem, s>>>(T, nodes, kstep, F, kw);
   else
-    k_lu_gemm_dmma<false><<<dim3(nfront, nt, nt), DM_THREADS, smem, s>>>(T, nodes, kstep, F);
+    k_lu_gemm_dmma<false><<<dim3(nfront, nt, nt), DM_THREADS, smem, s>>>(T, nodes, kstep, F, kw);
 }
 
 template <class S>
-static bool try_dmma(FrontTab, const int*, int, int, S*, int, bool, cudaStream_t) {
+static bool try_dmma(FrontTab, const int*, int, int, S*, int, bool, cudaStream_t, int) {
   return false;
 }
 template <>
 bool try_dmma<double>(FrontTab T, const int* nodes, int nfront, int kstep, double* F, int max_rem, bool schur,
-                      cudaStream_t s) {
+                      cudaStream_t s, int kw) {
   static const bool off = getenv("FW_NO_DMMA") != nullptr;
   if (off) return false;
-  lu_gemm_dmma_launch(T, nodes, nfront, kstep, F, max_rem, schur, s);
+  lu_gemm_dmma_launch(T, nodes, nfront, kstep, F, max_rem, schur, s, kw);
   return true;
 }
 
 template <class S>
 void lu_gemm_big_launch(FrontTab T, const int* nodes, int nfront, int kstep, S* F, int max_rem, bool schur,
-                        cudaStream_t s) {
-  if (try_dmma<S>(T, nodes, nfront, kstep, F, max_rem, schur, s)) return;
+                        cudaStream_t s, int kw) {
+  if (try_dmma<S>(T, nodes, nfront, kstep, F, max_rem, schur, s, kw)) return;
   constexpr int TM = 16 * Gemm2Cfg<S>::MT;
   constexpr size_t smem = sizeof(S) * 2 * G2_KC * (TM + TM + 2);
   const int nt = (max_rem + TM - 1) / TM;
@@ -291,11 +291,11 @@ void lu_gemm_big_launch(FrontTab T, const int* nodes, int nfront, int kstep, S* 
     FW_CHECK_CUDA(cudaFuncSetAttribute(k_lu_gemm_big<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   if (schur)
-    k_lu_gemm_big<S, true><<<dim3(nfront, nt, nt), 256, smem, s>>>(T, nodes, kstep, F);
+    k_lu_gemm_big<S, true><<<dim3(nfront, nt, nt), 256, smem, s>>>(T, nodes, kstep, F, kw);
   else
-    k_lu_gemm_big<S, false><<<dim3(nfront, nt, nt), 256, smem, s>>>(T, nodes, kstep, F);
+    k_lu_gemm_big<S, false><<<dim3(nfront, nt, nt), 256, smem, s>>>(T, nodes, kstep, F, kw);
 }
-template void lu_gemm_big_launch<double>(FrontTab, const int*, int, int, double*, int, bool, cudaStream_t);
-template void lu_gemm_big_launch<cplx>(FrontTab, const int*, int, int, cplx*, int, bool, cudaStream_t);
+template void lu_gemm_big_launch<double>(FrontTab, const int*, int, int, double*, int, bool, cudaStream_t, int);
+template void lu_gemm_big_launch<cplx>(FrontTab, const int*, int, int, cplx*, int, bool, cudaStream_t, int);
 
 }  // namespace fw

@@ -549,13 +549,209 @@ __global__ void __cluster_dims__(PCL, 1, 1) __launch_bounds__(PCL_THREADS)
   }
 }
 
+// ------------------------------------------------------------------------------ tall panel in ONE CTA, registers
+// The cluster kernel above pays two hardware cluster barriers per pivot column (~4.7 us per column measured: the
+// 2001 pivots of the root front alone cost 9.5 ms).  This kernel keeps the whole panel on one SM: 1024 threads, every
+// thread owns R rows, the 32-column panel is processed as 32/SW LEFT-LOOKING sub-panels of SW columns that live in
+// registers (R x SW entries per thread).  Per pivot column: warp arg-max, one block barrier, every warp reduces the 32
+// warp candidates itself, the owner of the pivot row publishes its SW entries, second block barrier, rank-1 update
+// in registers.  Pivoting is IMPLICIT while the panel is factored (a chosen row is frozen where it lies, so no row
+// data moves between threads); before a sub-panel starts, the effect of the earlier pivots of this panel on its
+// columns is applied at once (small unit-lower solve of the pivot rows in shared memory, then one pass over the
+// thread's own L entries, which are L1/L2 hits).  At the end the <= 64 rows whose position changes are moved and
+// the implicit order is converted into the LAPACK-style sequential interchanges the other kernels expect.
+template <class S, int PR_THREADS, int R, int SW>
+__global__ void __launch_bounds__(PR_THREADS, 1) k_lu_panel_regs(FrontTab T, const int* __restrict__ nodes, int kstep,
+                                                                 S* __restrict__ F, int* __restrict__ piv, double thr,
+                                                                 int* __restrict__ counters) {
+  __shared__ S prow[SW];
+  __shared__ double red_v[32];
+  __shared__ int red_i[32];
+  constexpr int NW = PR_THREADS / 32;
+  __shared__ int s_orig[PW];      // panel-local row of pivot j
+  __shared__ S Ub[PW][SW];        // pivot rows j < c0 in the columns of the current sub-panel
+  __shared__ S Lpp[PW][PW + 1];   // Lpp[i][j]: multiplier of pivot row i for pivot j < i
+  __shared__ int s_pos[PW], s_occ[PW], s_chosen[PW], s_src[2 * PW], s_dst[2 * PW];
+  const int node = nodes[blockIdx.x];
+  const int m = T.m[node], ns = T.ns[node];
+  const int k0 = kstep * PW;
+  const int h = ns - k0;
+  if (k0 >= ns || h <= HWIN || h > R * PR_THREADS) return;
+  S* P = F + T.front_off[node] + k0 + (long long)k0 * m;  // P[r + c*m]
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  int froz[R];  // index of the pivot this row became, 99 while it is still a candidate
+#pragma unroll
+  for (int q = 0; q < R; ++q) froz[q] = 99;
+  for (int c0 = 0; c0 < PW; c0 += SW) {
+    S a[R][SW];
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const int i = t + q * PR_THREADS;
+#pragma unroll
+      for (int c = 0; c < SW; ++c) a[q][c] = i < h ? P[i + (long long)(c0 + c) * m] : scalar_traits<S>::zero();
+    }
+    if (c0 > 0) {
+      // ---- left-looking update of these SW columns by the pivots 0 .. c0-1 of this panel
+#pragma unroll
+      for (int q = 0; q < R; ++q)
+        if (froz[q] < c0) {
+#pragma unroll
+          for (int c = 0; c < SW; ++c) Ub[froz[q]][c] = a[q][c];
+        }
+      for (int e = t; e < PW * PW; e += PR_THREADS) {
+        const int i = e >> 5, j = e & 31;
+        if (i < c0 && j < i) Lpp[i][j] = P[s_orig[i] + (long long)j * m];
+      }
+      __syncthreads();
+      if (t < SW) {
+        for (int j = 1; j < c0; ++j) {
+          S u = Ub[j][t];
+          for (int i = 0; i < j; ++i) fnma_(u, Lpp[j][i], Ub[i][t]);
+          Ub[j][t] = u;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const int i = t + q * PR_THREADS;
+        if (i >= h) continue;
+        const int lim = min(froz[q], c0);
+        int j = 0;
+        constexpr int LU = (R * SW * (int)sizeof(S) >= 128) ? 4 : 8;  // loads in flight (register budget: 64 per thread)
+        for (; j + LU <= lim; j += LU) {
+          S l[LU];
+#pragma unroll
+          for (int u = 0; u < LU; ++u) l[u] = P[i + (long long)(j + u) * m];
+#pragma unroll
+          for (int u = 0; u < LU; ++u)
+#pragma unroll
+            for (int c = 0; c < SW; ++c) fnma_(a[q][c], l[u], Ub[j + u][c]);
+        }
+        for (; j < lim; ++j) {
+          const S l = P[i + (long long)j * m];
+#pragma unroll
+          for (int c = 0; c < SW; ++c) fnma_(a[q][c], l, Ub[j][c]);
+        }
+      }
+    }
+    // ---- right-looking elimination of the SW columns in registers
+#pragma unroll
+    for (int jj = 0; jj < SW; ++jj) {
+      const int j = c0 + jj;
+      double v = -1.0;
+      int idx = 0x7fffffff;
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const int i = t + q * PR_THREADS;
+        if (i < h && froz[q] == 99) {
+          const double av = abs1_(a[q][jj]);
+          if (av > v) v = av, idx = i;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, v, o);
+        const int oi = __shfl_down_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) v = ov, idx = oi;
+      }
+      if (lane == 0) red_v[wid] = v, red_i[wid] = idx;
+      __syncthreads();
+      double bv = lane < NW ? red_v[lane] : -1.0;
+      int pr = lane < NW ? red_i[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, pr, o);
+        if (ov > bv || (ov == bv && oi < pr)) bv = ov, pr = oi;
+      }
+      const bool tiny = !(bv >= thr);
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        if (t + q * PR_THREADS == pr) {
+          froz[q] = j;
+          // static pivot perturbation (tiny / exactly singular pivot); corrected by iterative refinement
+          if (tiny) a[q][jj] = scalar_traits<S>::from(thr, 0.0);
+#pragma unroll
+          for (int c = 0; c < SW; ++c) prow[c] = a[q][c];
+          s_orig[j] = pr;
+          if (tiny) atomicAdd(&counters[0], 1);
+          if (bv == 0.0) atomicAdd(&counters[1], 1);
+        }
+      }
+      __syncthreads();
+      const S pv = prow[jj];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        if (t + q * PR_THREADS < h && froz[q] == 99) {
+          const S l = a[q][jj] / pv;
+          a[q][jj] = l;
+#pragma unroll
+          for (int c = jj + 1; c < SW; ++c) fnma_(a[q][c], l, prow[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const int i = t + q * PR_THREADS;
+      if (i < h) {
+#pragma unroll
+        for (int c = 0; c < SW; ++c) P[i + (long long)(c0 + c) * m] = a[q][c];
+      }
+    }
+    __syncthreads();  // the sub-panel is visible to the whole CTA (Lpp gather, L reloads, final row moves)
+  }
+  // ---- implicit pivot order -> sequential interchanges (row j <-> piv[j]) and the final position of every moved row
+  if (t < PW) s_pos[t] = t, s_occ[t] = t, s_chosen[t] = 0;
+  __syncthreads();
+  if (t == 0) {
+    int* pv = piv + T.own_start[node] + k0;
+    for (int j = 0; j < PW; ++j) {
+      const int o = s_orig[j];
+      const int cur = o < PW ? s_pos[o] : o;  // rows below the top block stay put until they are chosen
+      if (o < PW) s_chosen[o] = 1;
+      pv[j] = k0 + cur;
+      const int d = s_occ[j];  // the original top row that currently sits at position j
+      if (cur != j) {
+        s_pos[d] = cur;
+        if (cur < PW) s_occ[cur] = d;
+      }
+      s_occ[j] = -1;
+    }
+    for (int j = 0; j < PW; ++j) s_src[j] = s_orig[j], s_dst[j] = j;
+    for (int d = 0; d < PW; ++d) {
+      const bool moved = !s_chosen[d] && s_pos[d] != d;
+      s_src[PW + d] = moved ? d : -1;
+      s_dst[PW + d] = moved ? s_pos[d] : -1;
+    }
+  }
+  __syncthreads();
+  constexpr int MV = 2 * PW * PW / PR_THREADS;
+  S mv[MV];
+#pragma unroll
+  for (int u = 0; u < MV; ++u) {
+    const int e = t + u * PR_THREADS, who = e >> 5, c = e & 31;
+    const int src = s_src[who];
+    mv[u] = (src >= 0 && src != s_dst[who]) ? P[src + (long long)c * m] : scalar_traits<S>::zero();
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < MV; ++u) {
+    const int e = t + u * PR_THREADS, who = e >> 5, c = e & 31;
+    const int src = s_src[who], dst = s_dst[who];
+    if (src >= 0 && src != dst) P[dst + (long long)c * m] = mv[u];
+  }
+}
+
 // ------------------------------------------------------------------------------ swaps + TRSMs
 // blockIdx.x < ctiles : thread per column c outside the panel: row interchanges, and for c right of the
 //                       panel the unit-lower solve of the U row block.
 // blockIdx.x >= ctiles: thread per row below the pivot window: X U_kk = F (L21 / L-panel rows).
+// ob > 0 (two-level blocking, outer blocks of ob panels): the unit-lower solve is applied only to the columns of the
+// current outer block; the U strip right of it is solved once per outer block by k_lu_outer_trsm.
 template <class S>
 __global__ void __launch_bounds__(128) k_lu_swap_trsm(FrontTab T, const int* __restrict__ nodes, int kstep,
-                                                      S* __restrict__ F, const int* __restrict__ piv, int ctiles) {
+                                                      S* __restrict__ F, const int* __restrict__ piv, int ctiles,
+                                                      int ob) {
   __shared__ S D[PW][PW + 1];
   __shared__ int sp[PW];
   const int node = nodes[blockIdx.x];
@@ -586,7 +782,8 @@ __global__ void __launch_bounds__(128) k_lu_swap_trsm(FrontTab T, const int* __r
         col[p] = tmp;
       }
     }
-    if (c >= k0 + w) {
+    const int jend = ob > 0 ? min(ns, (kstep / ob + 1) * ob * PW) : m;
+    if (c >= k0 + w && c < jend) {
       S x[PW];
 #pragma unroll
       for (int j = 0; j < PW; ++j) x[j] = (j < w) ? col[k0 + j] : scalar_traits<S>::zero();
@@ -621,6 +818,72 @@ __global__ void __launch_bounds__(128) k_lu_swap_trsm(FrontTab T, const int* __r
   }
 }
 
+// ------------------------------------------------------------------------------ outer-block U strip
+// Two-level blocking: after the ob panels of an outer block [j0, j0 + ow) are factored (their row interchanges are
+// already applied to every column), the U strip right of the block is solved once with the unit-lower ow x ow block:
+// thread per column, 32 rows at a time in registers, the L slab of the current 32 columns in shared memory.
+template <class S>
+__global__ void __launch_bounds__(128) k_lu_outer_trsm(FrontTab T, const int* __restrict__ nodes, int jblk, int ob,
+                                                       S* __restrict__ F) {
+  extern __shared__ __align__(16) unsigned char outer_smem[];
+  S(*Ls)[PW + 1] = reinterpret_cast<S(*)[PW + 1]>(outer_smem);  // rows of the block from the current 32 columns down
+  const int node = nodes[blockIdx.x];
+  const int m = T.m[node], ns = T.ns[node];
+  const int j0 = jblk * ob * PW;
+  if (j0 >= ns) return;
+  const int ow = min(ob * PW, ns - j0);
+  const int c = j0 + ow + blockIdx.y * 128 + threadIdx.x;
+  if (j0 + ow + (int)blockIdx.y * 128 >= m) return;
+  S* Fn = F + T.front_off[node];
+  const bool live = c < m;
+  S* col = Fn + (long long)(live ? c : 0) * m + j0;
+  for (int s0 = 0; s0 < ow; s0 += PW) {
+    const int w = min(PW, ow - s0);
+    const int rows = ow - s0;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < rows * w; idx += 128) {
+      const int r = idx % rows, cc = idx / rows;
+      Ls[r][cc] = Fn[(j0 + s0 + r) + (long long)(j0 + s0 + cc) * m];
+    }
+    __syncthreads();
+    if (!live) continue;
+    S x[PW];
+#pragma unroll
+    for (int j = 0; j < PW; ++j) x[j] = (j < w) ? col[s0 + j] : scalar_traits<S>::zero();
+#pragma unroll
+    for (int j = 1; j < PW; ++j) {
+      if (j < w) {
+#pragma unroll
+        for (int i = 0; i < j; ++i) fnma_(x[j], Ls[j][i], x[i]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PW; ++j)
+      if (j < w) col[s0 + j] = x[j];
+    int r = w;
+    for (; r + 8 <= rows; r += 8) {  // eight independent read-modify-writes in flight
+      S acc[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = col[s0 + r + u];
+#pragma unroll
+      for (int j = 0; j < PW; ++j)
+        if (j < w) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) fnma_(acc[u], Ls[r + u][j], x[j]);
+        }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) col[s0 + r + u] = acc[u];
+    }
+    for (; r < rows; ++r) {
+      S acc = col[s0 + r];
+#pragma unroll
+      for (int j = 0; j < PW; ++j)
+        if (j < w) fnma_(acc, Ls[r][j], x[j]);
+      col[s0 + r] = acc;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ trailing update
 template <class S>
 struct GemmCfg {
@@ -635,17 +898,18 @@ struct GemmCfg<cplx> {
 //                 row or a column inside the pivot block); the boundary x boundary block S22 is skipped.
 // SCHUR = true : once per front after its last panel, S22 -= L21 U12 with the full inner dimension ns, so the
 //                 Schur complement (the bulk of the flops for nb >> ns) is read and written once.
+// ob > 0: inner update of two-level blocking -- only the columns of the current outer block of ob panels.
 template <class S, bool SCHUR>
 __global__ void __launch_bounds__(256) k_lu_gemm(FrontTab T, const int* __restrict__ nodes, int kstep,
-                                                 S* __restrict__ F) {
+                                                 S* __restrict__ F, int ob = 0, int kw = PW) {
   constexpr int TM = 64, KC = GemmCfg<S>::KC;
   __shared__ S As[KC][TM];
   __shared__ S Bs[KC][TM + 1];
   const int node = nodes[blockIdx.x];
   const int m = T.m[node], ns = T.ns[node];
-  const int k0 = SCHUR ? 0 : kstep * PW;
+  const int k0 = SCHUR ? 0 : kstep * kw;  // kw: one panel, or an outer block of panels
   if (k0 >= ns) return;
-  const int w = SCHUR ? ns : min(PW, ns - k0);
+  const int w = SCHUR ? ns : min(kw, ns - k0);
   const int r0 = SCHUR ? ns : k0 + w;
   const int nrem = m - r0;
   if (nrem <= 0) return;
@@ -653,6 +917,8 @@ __global__ void __launch_bounds__(256) k_lu_gemm(FrontTab T, const int* __restri
   const int ti = blockIdx.y, tj = blockIdx.z;
   if (ti >= nt || tj >= nt) return;
   if (!SCHUR && r0 + ti * TM >= ns && r0 + tj * TM >= ns) return;  // tile entirely inside S22
+  const int cend = (!SCHUR && ob > 0) ? min(ns, (kstep / ob + 1) * ob * PW) : m;  // exclusive column limit (kw = PW)
+  if (r0 + tj * TM >= cend) return;
   S* Fn = F + T.front_off[node];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   S acc[4][4];
@@ -670,7 +936,7 @@ __global__ void __launch_bounds__(256) k_lu_gemm(FrontTab T, const int* __restri
     for (int idx = threadIdx.x; idx < KC * TM; idx += 256) {
       const int k = idx % KC, c = idx / KC;
       const int gc = cbase + c, gk = kc + k;
-      Bs[k][c] = (gc < m && gk < w) ? Fn[(k0 + gk) + (long long)gc * m] : scalar_traits<S>::zero();
+      Bs[k][c] = (gc < cend && gk < w) ? Fn[(k0 + gk) + (long long)gc * m] : scalar_traits<S>::zero();
     }
     __syncthreads();
 #pragma unroll
@@ -690,7 +956,7 @@ __global__ void __launch_bounds__(256) k_lu_gemm(FrontTab T, const int* __restri
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int gc = cbase + ty * 4 + j;
-    if (gc >= m) continue;
+    if (gc >= cend) continue;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int gr = rbase + tx * 4 + i;
@@ -827,6 +1093,18 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
   const bool trace2 = tenv && atoi(tenv) >= 2;
   static const int big_gemm_min = getenv("FW_BIG_GEMM_MIN") ? atoi(getenv("FW_BIG_GEMM_MIN")) : 384;
   static const bool no_cluster_panel = getenv("FW_NO_CLUSTER_PANEL") != nullptr;
+  static const bool no_regs_panel = getenv("FW_NO_REGS_PANEL") != nullptr;
+  // two-level blocking (outer blocks of OB panels) for levels whose pivot blocks span more than one panel
+  constexpr int OB = 4;
+  static const int blocked_min_ns = getenv("FW_BLOCKED_MIN_NS") ? atoi(getenv("FW_BLOCKED_MIN_NS")) : 33;
+  static const int big_gemm_min_outer = getenv("FW_BIG_GEMM_MIN_OUTER") ? atoi(getenv("FW_BIG_GEMM_MIN_OUTER")) : 384;
+  const size_t outer_smem = sizeof(S) * OB * PW * (PW + 1);
+  {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured))
+      FW_CHECK_CUDA(cudaFuncSetAttribute(k_lu_outer_trsm<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)outer_smem));
+  }
+  constexpr int RSW2 = scalar_traits<S>::is_complex ? 4 : 8, RSW4 = scalar_traits<S>::is_complex ? 2 : 4;
   // measured at 500k triangles: the level of 16 fronts (ns ~ 1000) took 15.7 ms with the global-memory tall-panel
   // kernel against 3.8 ms for the level of 8 fronts of half the width on the cluster kernel
   static const int cluster_panel_max_fronts =
@@ -854,7 +1132,22 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
     for (int k = 0; k < npan; ++k) {
       if (max_ns - k * PW > HWIN) {
         bool done = false;
+        {
+          // one CTA per front, the panel in registers (implicit pivoting): any number of fronts, up to 4096 rows
+          const int hmax = max_ns - k * PW;
+          // register budget: R * SW entries per thread; 512-thread CTAs (128 registers) for the taller panels
+          if (!no_regs_panel && hmax <= 4096) {
+            if (hmax <= 1024)
+              k_lu_panel_regs<S, 1024, 1, 8><<<nfront, 1024, 0, s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
+            else if (hmax <= 2048)
+              k_lu_panel_regs<S, 512, 4, RSW2><<<nfront, 512, 0, s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
+            else
+              k_lu_panel_regs<S, 512, 8, RSW4><<<nfront, 512, 0, s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
+            done = true;
+          }
+        }
         if constexpr (!scalar_traits<S>::is_complex) {
+          if (!done)
           // few, tall f64 fronts (top of the tree): one 8-CTA cluster per front, the panel lives in registers
           if (nfront <= cluster_panel_max_fronts && max_ns - k * PW <= PCL * PCL_THREADS && !no_cluster_panel) {
             k_lu_panel_cluster<<<nfront * PCL, PCL_THREADS, 0, s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
@@ -866,14 +1159,35 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
       k_lu_panel<S><<<nfront, HWIN, panel_smem, s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
       const int ctiles = (max_m + 127) / 128;
       const int rtiles = (max_m + 127) / 128;
-      k_lu_swap_trsm<S><<<dim3(nfront, ctiles + rtiles), 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles);
+      // two-level blocking: rank-32 updates stay inside the current outer block of OB panels; the rest of the front
+      // gets one rank-(32 OB) update per outer block (the 128 x 128 tensor-core GEMM needs a deep inner dimension)
+      const int ob = (max_ns >= blocked_min_ns) ? OB : 0;
+      k_lu_swap_trsm<S><<<dim3(nfront, ctiles + rtiles), 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
       const int rem = max_m - (k * PW);  // upper bound of the trailing size
       const int nt = (rem + 63) / 64;
-      if (rem >= big_gemm_min_panel)
-        lu_gemm_big_launch<S>(T, nodes, nfront, k, F, rem, false, s);
-      else if (nt > 0)
-        k_lu_gemm<S, false><<<dim3(nfront, nt, nt), 256, 0, s>>>(T, nodes, k, F);
       launches += 3;
+      if (ob == 0) {
+        if (rem >= big_gemm_min_panel)
+          lu_gemm_big_launch<S>(T, nodes, nfront, k, F, rem, false, s);
+        else if (nt > 0)
+          k_lu_gemm<S, false><<<dim3(nfront, nt, nt), 256, 0, s>>>(T, nodes, k, F, 0);
+        continue;
+      }
+      const bool last_inner = (k % ob == ob - 1) || k == npan - 1;
+      if (!last_inner) {
+        const int ct = (ob * PW - PW + 63) / 64;  // column tiles inside the outer block
+        if (nt > 0) k_lu_gemm<S, false><<<dim3(nfront, nt, ct), 256, 0, s>>>(T, nodes, k, F, ob);
+      } else {
+        const int jb = k / ob;
+        const int orem = max_m - jb * ob * PW;  // columns right of the block start (upper bound)
+        const int otiles = (orem + 127) / 128;
+        k_lu_outer_trsm<S><<<dim3(nfront, otiles), 128, outer_smem, s>>>(T, nodes, jb, ob, F);
+        if (orem >= big_gemm_min_outer)
+          lu_gemm_big_launch<S>(T, nodes, nfront, jb, F, orem, false, s, ob * PW);
+        else
+          k_lu_gemm<S, false><<<dim3(nfront, (orem + 63) / 64, (orem + 63) / 64), 256, 0, s>>>(T, nodes, jb, F, 0, ob * PW);
+        launches += 1;
+      }
     }
     if (trace2) tr.mark(("  factor lev " + std::to_string(lev) + " panels (" + std::to_string(npan) + " steps, " +
                          std::to_string(nfront) + " fronts, max m " + std::to_string(max_m) + ")").c_str());

@@ -1,0 +1,17 @@
+"""One LU factorisation at config-2 size (the command profiled under ncu for the per-kernel list of the factor)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+from common import mode_element, strip_problem
+from femwell_b200.basis import Basis
+from femwell_b200.context import Context
+from femwell_b200.element import ElementTriP0
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 500
+ctx = Context(0)
+m, eps = strip_problem(n, slab_h=0.11)
+b = Basis(m, ElementTriP0(), intorder=4).with_element(mode_element(2))
+k0 = 2 * np.pi / 1.55
+ctx.set_space(b); ctx.symbolic(); ctx.assemble(0, eps, k0)
+ctx.lu_factor(k0**2 * eps.max() * 1.1)
+print("factored", ctx.timings()["lu_factor_ms"])
