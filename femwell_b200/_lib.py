@@ -106,7 +106,7 @@ ERR_NOCONV, ERR_SINGULAR = -3, -4
 
 # every symbol include/femwell_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "fw_last_error", "fw_version", "fw_create", "fw_destroy", "fw_synchronize", "fw_set_option", "fw_set_space", "fw_set_element_subset", "fw_analysis_hint",
+    "fw_last_error", "fw_version", "fw_create", "fw_destroy", "fw_synchronize", "fw_set_option", "fw_host_alloc", "fw_host_free", "fw_set_space", "fw_set_element_subset", "fw_analysis_hint",
     "fw_symbolic", "fw_assemble_waveguide", "fw_matrix_nnz", "fw_matrix_export", "fw_coo_to_csr",
     "fw_coo_to_csr_export", "fw_matrix_spmv", "fw_bench_spmv", "fw_eigs", "fw_eigs_csr", "fw_lu_factor_shifted", "fw_lu_solve",
     "fw_postprocess_modes", "fw_hfield", "fw_functional", "fw_error_estimator", "fw_intensity", "fw_poynting", "fw_overlap_cross", "fw_energy_current_density", "fw_compute_modes", "fw_get_timings",
@@ -130,8 +130,11 @@ def load():
         lib.fw_version.restype = C.c_int
         for name in EXPORTS:
             fn = getattr(lib, name)
-            if name not in ("fw_last_error",):
+            if name not in ("fw_last_error", "fw_host_alloc"):
                 fn.restype = C.c_int
+        lib.fw_host_alloc.restype = C.c_void_p
+        lib.fw_host_alloc.argtypes = [C.c_size_t]
+        lib.fw_host_free.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
 
@@ -148,6 +151,54 @@ def check(code, partial=None):
     if code == ERR_SINGULAR:
         raise B200SingularError(code, msg)
     raise FemwellB200Error(code, msg)
+
+
+class PinnedPool:
+    """Page-locked result buffers (fw_host_alloc) recycled between solves: the D2H copy of E and H into them is one DMA
+    at bus speed.  ``empty(shape, dtype)`` returns a numpy array backed by such a buffer; the buffer goes back to the
+    pool when the array (and every view of it) has been garbage collected."""
+
+    MAX_CACHED_PER_SIZE = 4
+
+    class _Block:
+        def __init__(self, pool, ptr, nbytes, shape, typestr):
+            self._pool, self._ptr, self._nbytes = pool, ptr, nbytes
+            self.__array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+
+        def __del__(self):
+            try:
+                self._pool._give_back(self._ptr, self._nbytes)
+            except Exception:  # interpreter shutdown
+                pass
+
+    def __init__(self):
+        self._free = {}
+        self.closed = False
+
+    def empty(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        if self.closed or nbytes < (1 << 20):
+            return np.empty(shape, dtype=dtype)
+        cached = self._free.get(nbytes)
+        p = cached.pop() if cached else load().fw_host_alloc(nbytes)
+        if not p:  # no lockable memory left: a pageable array works too (staged copy)
+            return np.empty(shape, dtype=dtype)
+        return np.asarray(PinnedPool._Block(self, p, nbytes, tuple(int(v) for v in shape), dtype.str))
+
+    def _give_back(self, p, nbytes):
+        cached = self._free.setdefault(nbytes, [])
+        if self.closed or len(cached) >= self.MAX_CACHED_PER_SIZE:
+            load().fw_host_free(p)
+        else:
+            cached.append(p)
+
+    def close(self):
+        self.closed = True
+        for cached in self._free.values():
+            for p in cached:
+                load().fw_host_free(p)
+        self._free.clear()
 
 
 def ptr(a):

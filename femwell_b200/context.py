@@ -29,8 +29,11 @@ class Context:
         self._subset_key = None
         self.n = 0
         self.nnz_structural = None
+        self._pinned = L.PinnedPool()
 
     def close(self):
+        if getattr(self, "_pinned", None) is not None:
+            self._pinned.close()
         if getattr(self, "_h", None) is not None and self._h:
             self.lib.fw_destroy(self._h)
             self._h = None
@@ -335,8 +338,8 @@ class Context:
         p.eigs = self._eigs_params(k, sigma, dirichlet, v0, ncv, tol, maxiter, refine, leaf_elements, keep)
         p.reuse_symbolic = int(reuse_symbolic)
         lams = np.empty(k, dtype=np.complex128)
-        E = np.empty((k, self.n), dtype=np.complex128)
-        H = np.empty((k, self.n), dtype=np.complex128)
+        E = self._pinned.empty((k, self.n), np.complex128)  # page-locked: the result download is one DMA each
+        H = self._pinned.empty((k, self.n), np.complex128)
         powers = np.empty(k, dtype=np.complex128)
         st = L.FwEigsStats()
         L.check(self.lib.fw_compute_modes(self._h, C.byref(p), L.ptr(lams), L.ptr(E), L.ptr(H), L.ptr(powers),

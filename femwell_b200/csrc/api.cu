@@ -44,7 +44,13 @@ Handle::~Handle() {
 // chunk to its pageable destination while the next chunk is already on the bus.
 void download_staged(Handle& h, void* host_dst, const void* dev_src, size_t bytes) {
   constexpr size_t CHUNK = (size_t)32 << 20;
-  if (bytes < 4 * CHUNK) {
+  bool dst_pinned = false;
+  if (bytes >= 4 * CHUNK) {  // page-locked destination (fw_host_alloc): one DMA at bus speed, no staging copy
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, host_dst) == cudaSuccess) dst_pinned = attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();  // an unregistered pointer is not an error here
+  }
+  if (bytes < 4 * CHUNK || dst_pinned) {
     FW_CHECK_CUDA(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, h.stream));
     FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
     return;
@@ -332,6 +338,9 @@ int fw_set_option(fw_handle* hh, int32_t option, int32_t value) {
     case FW_OPT_PCG_TOL_EXP:
       FW_REQUIRE(value >= 1 && value <= 15, "PCG tolerance exponent out of range (1..15)");
       hh->h.pcg_tol = std::pow(10.0, -(double)value);
+      break;
+    case FW_OPT_START_VECTOR:
+      hh->h.smooth_v0 = value != 0;
       break;
 
     default:
@@ -843,7 +852,16 @@ int fw_compute_modes(fw_handle* hh, const fw_modes_params* prm, double* lams, do
   assemble_aux(h);
   DevBuf<double> Xd, Hd;
   std::string why;
-  const bool ok = eigs_shift_invert(h, prm->eigs, (std::complex<double>*)lams, Xd, st, &why);
+  h.v0_dev_valid = !prm->eigs.v0 && h.smooth_v0 &&
+                   smooth_start_vector(h, prm->eps_kind, prm->eps_is_complex != 0, prm->eps, h.v0_dev);
+  bool ok = false;
+  try {
+    ok = eigs_shift_invert(h, prm->eigs, (std::complex<double>*)lams, Xd, st, &why);
+  } catch (...) {
+    h.v0_dev_valid = false;
+    throw;
+  }
+  h.v0_dev_valid = false;  // one shot: fw_eigs / fw_eigs_csr keep the uniform(-1, 1) default
   const int k = prm->eigs.k;
   const size_t cnt = (size_t)k * h.sp.n * 2;
   if (!ok) {
@@ -870,6 +888,21 @@ int fw_compute_modes(fw_handle* hh, const fw_modes_params* prm, double* lams, do
     download_staged(h, H, Hd.p, cnt * sizeof(double));
     h.tim.download_ms = t.stop();
   }
+  FW_API_END
+}
+
+void* fw_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+int fw_host_free(void* p) {
+  FW_API_BEGIN
+  if (p) FW_CHECK_CUDA(cudaFreeHost(p));
   FW_API_END
 }
 

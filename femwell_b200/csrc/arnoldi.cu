@@ -397,6 +397,8 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
     if (prm.v0) {
       v0d.upload(prm.v0, (size_t)n, s);
       k_mask_real_to<<<cdiv(n, 256), 256, 0, s>>>(v0d.p, act.p, n, w);
+    } else if (h.v0_dev_valid && h.v0_dev.n >= (size_t)n) {
+      k_mask_real_to<<<cdiv(n, 256), 256, 0, s>>>(h.v0_dev.p, act.p, n, w);  // smooth default (start_vector.cu)
     } else {
       k_start_vector<<<cdiv(n, 256), 256, 0, s>>>(act.p, n, w);
     }

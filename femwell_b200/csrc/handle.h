@@ -63,6 +63,9 @@ struct Handle {
   bool eliminate_zeros = true;  // export semantics of scipy's coo.eliminate_zeros()
   int mass_solver = 0;          // FW_OPT_MASS_SOLVER: 0 PCG with direct fallback, 1 PCG only, 2 direct (sparse LU)
   double pcg_tol = 1e-10;       // relative residual of the H-field mass solves (FW_OPT_PCG_TOL_EXP)
+  bool smooth_v0 = true;        // FW_OPT_START_VECTOR: contrast-weighted smooth default start vector (start_vector.cu)
+  DevBuf<double> v0_dev;        // start vector prepared on the device for the next eigs call (fw_compute_modes)
+  bool v0_dev_valid = false;
   Values A, B, Mass, C0, C1;
   // mass matrix without the structurally-zero cross blocks (own compact CSR; used by the PCG of the H field)
   struct CompactCsr {
@@ -138,6 +141,8 @@ void upload_tables(Handle& h);
 void assemble_waveguide(Handle& h, int eps_kind, bool eps_complex, const void* eps_host, double k0, double mu_r,
                         double radius);
 void assemble_aux(Handle& h);  // Mass, C0, C1 (geometry only, f64)
+// start_vector.cu: smooth default start vector of the Arnoldi iteration; false if none applies
+bool smooth_start_vector(Handle& h, int eps_kind, bool eps_complex, const void* eps_host, DevBuf<double>& v0);
 
 // ---- CSR kernels (csr.cu)
 template <class MT, class VT>

@@ -16,6 +16,7 @@ struct FrontTab {
   const long long *front_off, *work_off, *blist_off;
   const int *blist, *rel;
   const long long* dinv_off;  // per front: offset of its inverted diagonal blocks in LUDevice::dinv, or -1
+  int pf = 0;                 // substitution kernels: L2 prefetch budget per small front in KB (0 = off)
 };
 
 struct LUDevice {
@@ -33,6 +34,8 @@ struct LUDevice {
   bool dinv_valid = false;
   DevBuf<int> counters;
   DevBuf<uint8_t> active;
+  // dataflow substitution: nodes in deepest-level-first order; tree_sync = [epoch, 4 tickets, pad, one flag per node]
+  DevBuf<int> order_fwd, tree_sync;
   explicit LUDevice(Handle::LUArena& a)
       : factors(a.factors), work(a.work), xperm(a.xperm), scratch(a.scratch), dinv(a.dinv) {}
   FrontTab tab() const {

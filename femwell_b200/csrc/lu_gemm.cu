@@ -136,8 +136,7 @@ __global__ void __launch_bounds__(256) k_lu_gemm_big(FrontTab T, const int* __re
 //   3-stage cp.async pipeline (8-byte copies with zero fill at the ragged edges: front rows are only 8-byte aligned).
 //   Shared layouts make every fragment load conflict free: As[k][r] with row length 132 and Bs[c][k] with row
 //   length 20 (both = 4 mod 16 doubles), so the 16 lanes of a half warp hit 16 distinct 8-byte banks.
-constexpr int DM_TM = 128, DM_KC = 16, DM_LDA = DM_TM + 4, DM_LDB = DM_KC + 4, DM_STAGES = 3, DM_THREADS = 512;
-constexpr int DM_STAGE_DOUBLES = DM_KC * DM_LDA + DM_TM * DM_LDB;
+constexpr int DM_KC = 16, DM_LDB = DM_KC + 4, DM_STAGES = 3;
 
 __device__ __forceinline__ void cp_async8_zfill(double* smem, const double* gmem, bool valid) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -150,9 +149,14 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                : "d"(a), "d"(b));
 }
 
-template <bool SCHUR>
-__global__ void __launch_bounds__(DM_THREADS, 1) k_lu_gemm_dmma(FrontTab T, const int* __restrict__ nodes, int kstep,
-                                                                double* __restrict__ F, int kw) {
+// TM: CTA tile edge (128: 4 x 4 warps, 512 threads, one CTA per SM -- large fronts; 64: 2 x 2 warps, 128 threads,
+// three CTAs per SM -- fronts whose trailing block is a few hundred rows, where 128-wide tiles waste up to half of
+// the tensor work on the ragged edge: ncu on level 10 of config 2 showed the math pipe saturated at 8.9 useful TFLOP/s).
+template <bool SCHUR, int TM>
+__global__ void __launch_bounds__(TM * TM / 32, TM == 128 ? 1 : 3)
+    k_lu_gemm_dmma(FrontTab T, const int* __restrict__ nodes, int kstep, double* __restrict__ F, int kw) {
+  constexpr int WM = TM / 32, THREADS = TM * TM / 32, LDA = TM + 4;
+  constexpr int STAGE_DOUBLES = DM_KC * LDA + TM * DM_LDB;
   extern __shared__ __align__(16) double dm_smem[];
   const int node = nodes[blockIdx.x];
   const int m = T.m[node], ns = T.ns[node];
@@ -162,28 +166,28 @@ __global__ void __launch_bounds__(DM_THREADS, 1) k_lu_gemm_dmma(FrontTab T, cons
   const int r0 = SCHUR ? ns : k0 + klen;
   const int nrem = m - r0;
   if (nrem <= 0) return;
-  const int nt = (nrem + DM_TM - 1) / DM_TM;
+  const int nt = (nrem + TM - 1) / TM;
   const int ti = blockIdx.y, tj = blockIdx.z;
   if (ti >= nt || tj >= nt) return;
-  const int rbase = r0 + ti * DM_TM, cbase = r0 + tj * DM_TM;
+  const int rbase = r0 + ti * TM, cbase = r0 + tj * TM;
   if (!SCHUR && rbase >= ns && cbase >= ns) return;  // tile entirely inside S22
   double* Fn = F + T.front_off[node];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp & 3, wn = warp >> 2;
+  const int wm = warp % WM, wn = warp / WM;
   const int g = lane >> 2, q = lane & 3;
 
   auto issue = [&](int chunk, int stage) {
-    double* As = dm_smem + (size_t)stage * DM_STAGE_DOUBLES;
-    double* Bs = As + DM_KC * DM_LDA;
+    double* As = dm_smem + (size_t)stage * STAGE_DOUBLES;
+    double* Bs = As + DM_KC * LDA;
     const int kc = chunk * DM_KC;
 #pragma unroll
-    for (int it = 0; it < DM_KC * DM_TM / DM_THREADS; ++it) {
-      const int idx = tid + it * DM_THREADS;
+    for (int it = 0; it < DM_KC * TM / THREADS; ++it) {
+      const int idx = tid + it * THREADS;
       {
-        const int r = idx % DM_TM, k = idx / DM_TM;
+        const int r = idx % TM, k = idx / TM;
         const int gr = rbase + r, gk = kc + k;
         const bool ok = gr < m && gk < klen;
-        cp_async8_zfill(As + k * DM_LDA + r, ok ? Fn + gr + (long long)(k0 + gk) * m : Fn, ok);
+        cp_async8_zfill(As + k * LDA + r, ok ? Fn + gr + (long long)(k0 + gk) * m : Fn, ok);
       }
       {
         const int k = idx % DM_KC, c = idx / DM_KC;
@@ -214,13 +218,13 @@ __global__ void __launch_bounds__(DM_THREADS, 1) k_lu_gemm_dmma(FrontTab T, cons
       issue(c + 2, (c + 2) % DM_STAGES);
     else
       asm volatile("cp.async.commit_group;\n" ::: "memory");
-    const double* As = dm_smem + (size_t)(c % DM_STAGES) * DM_STAGE_DOUBLES;
-    const double* Bs = As + DM_KC * DM_LDA;
+    const double* As = dm_smem + (size_t)(c % DM_STAGES) * STAGE_DOUBLES;
+    const double* Bs = As + DM_KC * LDA;
 #pragma unroll
     for (int kk = 0; kk < DM_KC / 4; ++kk) {
       double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[(kk * 4 + q) * DM_LDA + wm * 32 + i * 8 + g];
+      for (int i = 0; i < 4; ++i) a[i] = As[(kk * 4 + q) * LDA + wm * 32 + i * 8 + g];
 #pragma unroll
       for (int j = 0; j < 4; ++j) b[j] = Bs[(wn * 32 + j * 8 + g) * DM_LDB + kk * 4 + q];
 #pragma unroll
@@ -248,20 +252,32 @@ __global__ void __launch_bounds__(DM_THREADS, 1) k_lu_gemm_dmma(FrontTab T, cons
   }
 }
 
-static void lu_gemm_dmma_launch(FrontTab T, const int* nodes, int nfront, int kstep, double* F, int max_rem, bool schur,
-                                cudaStream_t s, int kw) {
-  constexpr size_t smem = sizeof(double) * DM_STAGES * DM_STAGE_DOUBLES;
-  const int nt = (max_rem + DM_TM - 1) / DM_TM;
+template <int TM>
+static void lu_gemm_dmma_launch_tm(FrontTab T, const int* nodes, int nfront, int kstep, double* F, int max_rem,
+                                   bool schur, cudaStream_t s, int kw) {
+  constexpr size_t smem = sizeof(double) * DM_STAGES * (DM_KC * (TM + 4) + TM * DM_LDB);
+  constexpr int THREADS = TM * TM / 32;
+  const int nt = (max_rem + TM - 1) / TM;
   if (nt <= 0) return;
   static bool configured[64] = {};
   if (first_use_on_device(configured)) {
-    FW_CHECK_CUDA(cudaFuncSetAttribute(k_lu_gemm_dmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FW_CHECK_CUDA(cudaFuncSetAttribute(k_lu_gemm_dmma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FW_CHECK_CUDA(cudaFuncSetAttribute(k_lu_gemm_dmma<true, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FW_CHECK_CUDA(cudaFuncSetAttribute(k_lu_gemm_dmma<false, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   if (schur)
-    k_lu_gemm_dmma<true><<<dim3(nfront, nt, nt), DM_THREADS, smem, s>>>(T, nodes, kstep, F, kw);
+    k_lu_gemm_dmma<true, TM><<<dim3(nfront, nt, nt), THREADS, smem, s>>>(T, nodes, kstep, F, kw);
   else
-    k_lu_gemm_dmma<false><<<dim3(nfront, nt, nt), DM_THREADS, smem, s>>>(T, nodes, kstep, F, kw);
+    k_lu_gemm_dmma<false, TM><<<dim3(nfront, nt, nt), THREADS, smem, s>>>(T, nodes, kstep, F, kw);
+}
+
+static void lu_gemm_dmma_launch(FrontTab T, const int* nodes, int nfront, int kstep, double* F, int max_rem, bool schur,
+                                cudaStream_t s, int kw) {
+  // trailing blocks below ~900 rows: 64 x 64 tiles (less ragged-edge waste, three CTAs per SM)
+  static const int small_max = getenv("FW_DMMA64_MAX") ? atoi(getenv("FW_DMMA64_MAX")) : 900;
+  if (max_rem <= small_max)
+    lu_gemm_dmma_launch_tm<64>(T, nodes, nfront, kstep, F, max_rem, schur, s, kw);
+  else
+    lu_gemm_dmma_launch_tm<128>(T, nodes, nfront, kstep, F, max_rem, schur, s, kw);
 }
 
 template <class S>

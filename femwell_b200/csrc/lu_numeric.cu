@@ -197,6 +197,17 @@ static void lu_analyse_finish(Handle& h) {
     up64(d.dinv_off, doff, s);
     d.dinv_entries = tot;
   }
+  {
+    // dataflow substitution (lu_solve.cu): nodes deepest level first, one completion flag per node
+    std::vector<int> order;
+    order.reserve((size_t)S.n_nodes);
+    for (int lev = S.n_levels - 1; lev >= 0; --lev)
+      for (int q = S.level_start[lev]; q < S.level_start[lev + 1]; ++q) order.push_back(S.level_nodes[q]);
+    if (order.empty()) order.push_back(0);
+    up(d.order_fwd, order, s);
+    d.tree_sync.alloc((size_t)S.n_nodes + 8);
+    d.tree_sync.zero(s);
+  }
   FW_CHECK_CUDA(cudaStreamSynchronize(s));
 }
 
@@ -274,8 +285,10 @@ __global__ void __launch_bounds__(256) k_lu_extend_add(FrontTab T, const int* __
 }
 
 // ------------------------------------------------------------------------------ panel (pivot window) kernel
-template <class S>
-__global__ void __launch_bounds__(HWIN) k_lu_panel(FrontTab T, const int* __restrict__ nodes, int kstep,
+// WIN: rows of the shared-memory window = threads of the CTA (64 / 128 for the levels of small fronts, where the
+// 66 KB window of 256 rows would leave three CTAs per SM with most of their threads idle)
+template <class S, int WIN>
+__global__ void __launch_bounds__(WIN) k_lu_panel(FrontTab T, const int* __restrict__ nodes, int kstep,
                                                    S* __restrict__ F, int* __restrict__ piv, double thr,
                                                    int* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -286,10 +299,10 @@ __global__ void __launch_bounds__(HWIN) k_lu_panel(FrontTab T, const int* __rest
   if (ns - k0 > HWIN) return;  // tall panels: k_lu_panel_tall (pivot search over all fully-summed rows)
   const int w = min(PW, ns - k0);
   const int hw = ns - k0;
-  constexpr int LD = HWIN + 1;
+  constexpr int LD = WIN + 1;
   S* a = reinterpret_cast<S*>(smem_raw);              // a[c*LD + r]
-  __shared__ double red_v[HWIN / 32];
-  __shared__ int red_i[HWIN / 32];
+  __shared__ double red_v[WIN / 32];
+  __shared__ int red_i[WIN / 32];
   __shared__ int s_piv;
   S* Fn = F + T.front_off[node];
   const int t = threadIdx.x;
@@ -312,7 +325,7 @@ __global__ void __launch_bounds__(HWIN) k_lu_panel(FrontTab T, const int* __rest
     if (t == 0) {
       double bv = red_v[0];
       int bi = red_i[0];
-      for (int q = 1; q < HWIN / 32; ++q)
+      for (int q = 1; q < WIN / 32; ++q)
         if (red_v[q] > bv || (red_v[q] == bv && red_i[q] < bi)) bv = red_v[q], bi = red_i[q];
       s_piv = bi;
       piv[T.own_start[node] + k0 + j] = k0 + bi;
@@ -634,8 +647,19 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_lu_panel_regs(FrontTab T, con
         }
       }
     }
-    // ---- right-looking elimination of the SW columns in registers
+    // rows frozen by an earlier sub-panel now hold their final U entries of these columns
 #pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const int i = t + q * PR_THREADS;
+      if (i < h && froz[q] < c0) {
+#pragma unroll
+        for (int c = 0; c < SW; ++c) P[i + (long long)(c0 + c) * m] = a[q][c];
+      }
+    }
+    // ---- right-looking elimination of the SW columns in registers.  The columns SHIFT left by one after every
+    //      pivot, so the current column is always a[.][0]: the loop body is the same for every column (compact
+    //      code: the fully unrolled variant was instruction-fetch bound) and all register indices stay static.
+#pragma unroll 1
     for (int jj = 0; jj < SW; ++jj) {
       const int j = c0 + jj;
       double v = -1.0;
@@ -644,7 +668,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_lu_panel_regs(FrontTab T, con
       for (int q = 0; q < R; ++q) {
         const int i = t + q * PR_THREADS;
         if (i < h && froz[q] == 99) {
-          const double av = abs1_(a[q][jj]);
+          const double av = abs1_(a[q][0]);
           if (av > v) v = av, idx = i;
         }
       }
@@ -670,32 +694,33 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_lu_panel_regs(FrontTab T, con
         if (t + q * PR_THREADS == pr) {
           froz[q] = j;
           // static pivot perturbation (tiny / exactly singular pivot); corrected by iterative refinement
-          if (tiny) a[q][jj] = scalar_traits<S>::from(thr, 0.0);
+          if (tiny) a[q][0] = scalar_traits<S>::from(thr, 0.0);
 #pragma unroll
-          for (int c = 0; c < SW; ++c) prow[c] = a[q][c];
+          for (int c = 0; c < SW; ++c) {
+            prow[c] = a[q][c];
+            if (c < SW - jj) P[pr + (long long)(j + c) * m] = a[q][c];  // the pivot row is final: U entries
+          }
           s_orig[j] = pr;
           if (tiny) atomicAdd(&counters[0], 1);
           if (bv == 0.0) atomicAdd(&counters[1], 1);
         }
       }
       __syncthreads();
-      const S pv = prow[jj];
+      const S inv = scalar_traits<S>::one() / prow[0];
 #pragma unroll
       for (int q = 0; q < R; ++q) {
-        if (t + q * PR_THREADS < h && froz[q] == 99) {
-          const S l = a[q][jj] / pv;
-          a[q][jj] = l;
+        const int i = t + q * PR_THREADS;
+        if (i < h && froz[q] == 99) {
+          const S l = a[q][0] * inv;
+          P[i + (long long)j * m] = l;
 #pragma unroll
-          for (int c = jj + 1; c < SW; ++c) fnma_(a[q][c], l, prow[c]);
+          for (int c = 1; c < SW; ++c) {
+            S x = a[q][c];
+            fnma_(x, l, prow[c]);
+            a[q][c - 1] = x;
+          }
+          a[q][SW - 1] = scalar_traits<S>::zero();
         }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < R; ++q) {
-      const int i = t + q * PR_THREADS;
-      if (i < h) {
-#pragma unroll
-        for (int c = 0; c < SW; ++c) P[i + (long long)(c0 + c) * m] = a[q][c];
       }
     }
     __syncthreads();  // the sub-panel is visible to the whole CTA (Lpp gather, L reloads, final row moves)
@@ -748,7 +773,10 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_lu_panel_regs(FrontTab T, con
 // blockIdx.x >= ctiles: thread per row below the pivot window: X U_kk = F (L21 / L-panel rows).
 // ob > 0 (two-level blocking, outer blocks of ob panels): the unit-lower solve is applied only to the columns of the
 // current outer block; the U strip right of it is solved once per outer block by k_lu_outer_trsm.
-template <class S>
+// GATHER: the interchanges as one gather (two rounds of independent loads; 150 registers) -- levels of few fronts,
+// where the chain of w dependent read-modify-writes through L2 is what the step waits for; the sequential form keeps
+// the register count (and the occupancy) of the levels with thousands of small fronts.
+template <class S, bool GATHER>
 __global__ void __launch_bounds__(128) k_lu_swap_trsm(FrontTab T, const int* __restrict__ nodes, int kstep,
                                                       S* __restrict__ F, const int* __restrict__ piv, int ctiles,
                                                       int ob) {
@@ -771,32 +799,90 @@ __global__ void __launch_bounds__(128) k_lu_swap_trsm(FrontTab T, const int* __r
   if (threadIdx.x < w) sp[threadIdx.x] = piv[T.own_start[node] + k0 + threadIdx.x];
   __syncthreads();
   if (col_role) {
-    const int c = tile * 128 + threadIdx.x;
-    if (c >= m || (c >= k0 && c < k0 + w)) return;
-    S* col = Fn + (long long)c * m;
-    for (int j = 0; j < w; ++j) {
-      const int p = sp[j];
-      if (p != k0 + j) {
-        S tmp = col[k0 + j];
-        col[k0 + j] = col[p];
-        col[p] = tmp;
-      }
-    }
     const int jend = ob > 0 ? min(ns, (kstep / ob + 1) * ob * PW) : m;
-    if (c >= k0 + w && c < jend) {
+    if constexpr (GATHER) {
+    // The w sequential interchanges (row k0+j <-> sp[j]) as ONE gather: 64 threads trace the interchanges backwards
+      // to find which original row ends at each of the w top positions (s_top) and at every partner position below
+      // the top block (s_far; always an original top row).  A column then needs two rounds of independent loads
+      // instead of a chain of w dependent read-modify-writes through L2.
+      __shared__ int s_top[PW], s_far[PW];
+      if (threadIdx.x < 2 * PW) {
+        const int j = threadIdx.x & (PW - 1);
+        int pos = threadIdx.x < PW ? k0 + j : (j < w ? sp[j] : -1);
+        const bool wanted = j < w && (threadIdx.x < PW || pos >= k0 + w);
+        if (wanted) {
+          for (int i = w - 1; i >= 0; --i) {
+            const int a = k0 + i, b = sp[i];
+            pos = pos == a ? b : (pos == b ? a : pos);
+          }
+        }
+        if (threadIdx.x < PW)
+          s_top[j] = wanted ? pos : k0 + j;
+        else
+          s_far[j] = wanted ? pos : -1;
+      }
+      __syncthreads();
+      const int c = tile * 128 + threadIdx.x;
+      if (c >= m || (c >= k0 && c < k0 + w)) return;
+      S* col = Fn + (long long)c * m;
       S x[PW];
 #pragma unroll
-      for (int j = 0; j < PW; ++j) x[j] = (j < w) ? col[k0 + j] : scalar_traits<S>::zero();
+      for (int j = 0; j < PW; ++j) x[j] = (j < w) ? col[s_top[j]] : scalar_traits<S>::zero();
 #pragma unroll
-      for (int j = 1; j < PW; ++j) {
-        if (j < w) {
+      for (int ch = 0; ch < PW; ch += 8) {
+        S y[8];
 #pragma unroll
-          for (int i = 0; i < j; ++i) fnma_(x[j], D[j][i], x[i]);
+        for (int u = 0; u < 8; ++u) {
+          const int f = (ch + u < w) ? s_far[ch + u] : -1;
+          y[u] = f >= 0 ? col[f] : scalar_traits<S>::zero();
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (ch + u < w && s_far[ch + u] >= 0) col[sp[ch + u]] = y[u];
+      }
+        if (c >= k0 + w && c < jend) {
+#pragma unroll
+        for (int j = 1; j < PW; ++j) {
+          if (j < w) {
+#pragma unroll
+            for (int i = 0; i < j; ++i) fnma_(x[j], D[j][i], x[i]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < PW; ++j)
+          if (j < w) col[k0 + j] = x[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < PW; ++j)
+          if (j < w && s_top[j] != k0 + j) col[k0 + j] = x[j];
+      }
+    } else {
+      const int c = tile * 128 + threadIdx.x;
+      if (c >= m || (c >= k0 && c < k0 + w)) return;
+      S* col = Fn + (long long)c * m;
+      for (int j = 0; j < w; ++j) {
+        const int p = sp[j];
+        if (p != k0 + j) {
+          S tmp = col[k0 + j];
+          col[k0 + j] = col[p];
+          col[p] = tmp;
         }
       }
+      if (c >= k0 + w && c < jend) {
+        S x[PW];
 #pragma unroll
-      for (int j = 0; j < PW; ++j)
-        if (j < w) col[k0 + j] = x[j];
+        for (int j = 0; j < PW; ++j) x[j] = (j < w) ? col[k0 + j] : scalar_traits<S>::zero();
+#pragma unroll
+        for (int j = 1; j < PW; ++j) {
+          if (j < w) {
+#pragma unroll
+            for (int i = 0; i < j; ++i) fnma_(x[j], D[j][i], x[i]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < PW; ++j)
+          if (j < w) col[k0 + j] = x[j];
+      }
     }
   } else {
     const int r = k0 + hw + tile * 128 + threadIdx.x;
@@ -1085,19 +1171,23 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
   FW_CHECK_CUDA(cudaStreamSynchronize(s));
   const double scale = absv_(alphaA) * am[0] + absv_(alphaB) * am[1];
   const double thr = 1e-13 * (scale > 0 ? scale : 1.0);
-  const size_t panel_smem = (size_t)PW * (HWIN + 1) * sizeof(S);
-  FW_CHECK_CUDA(cudaFuncSetAttribute(k_lu_panel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
+  auto panel_smem = [](int win) { return (size_t)PW * (win + 1) * sizeof(S); };
+  FW_CHECK_CUDA(cudaFuncSetAttribute(k_lu_panel<S, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem(256)));
+  FW_CHECK_CUDA(cudaFuncSetAttribute(k_lu_panel<S, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem(128)));
   int64_t launches = 3;
   // trailing blocks at least this wide use the 128x128 register-tiled GEMM (FW_BIG_GEMM_MIN to experiment)
   const char* tenv = getenv("FW_TRACE");
   const bool trace2 = tenv && atoi(tenv) >= 2;
-  static const int big_gemm_min = getenv("FW_BIG_GEMM_MIN") ? atoi(getenv("FW_BIG_GEMM_MIN")) : 384;
+  // (the tensor-core GEMM has a 64 x 64 tile variant for trailing blocks below ~900 rows, lu_gemm.cu)
+  static const int big_gemm_min = getenv("FW_BIG_GEMM_MIN") ? atoi(getenv("FW_BIG_GEMM_MIN")) : 48;
+  static const int swap_gather_max_fronts =
+      getenv("FW_SWAP_GATHER_MAX_FRONTS") ? atoi(getenv("FW_SWAP_GATHER_MAX_FRONTS")) : 512;
   static const bool no_cluster_panel = getenv("FW_NO_CLUSTER_PANEL") != nullptr;
   static const bool no_regs_panel = getenv("FW_NO_REGS_PANEL") != nullptr;
   // two-level blocking (outer blocks of OB panels) for levels whose pivot blocks span more than one panel
   constexpr int OB = 4;
   static const int blocked_min_ns = getenv("FW_BLOCKED_MIN_NS") ? atoi(getenv("FW_BLOCKED_MIN_NS")) : 33;
-  static const int big_gemm_min_outer = getenv("FW_BIG_GEMM_MIN_OUTER") ? atoi(getenv("FW_BIG_GEMM_MIN_OUTER")) : 384;
+  static const int big_gemm_min_outer = getenv("FW_BIG_GEMM_MIN_OUTER") ? atoi(getenv("FW_BIG_GEMM_MIN_OUTER")) : 96;
   const size_t outer_smem = sizeof(S) * OB * PW * (PW + 1);
   {
     static bool configured[64] = {};
@@ -1156,13 +1246,24 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
         }
         if (!done) k_lu_panel_tall<S><<<nfront, TALL_THREADS, 0, s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
       }
-      k_lu_panel<S><<<nfront, HWIN, panel_smem, s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
+      {
+        const int hmax = max_ns - k * PW;  // tallest remaining pivot block of the level
+        if (hmax <= 64)
+          k_lu_panel<S, 64><<<nfront, 64, panel_smem(64), s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
+        else if (hmax <= 128)
+          k_lu_panel<S, 128><<<nfront, 128, panel_smem(128), s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
+        else
+          k_lu_panel<S, 256><<<nfront, 256, panel_smem(256), s>>>(T, nodes, k, F, d.piv.p, thr, d.counters.p);
+      }
       const int ctiles = (max_m + 127) / 128;
       const int rtiles = (max_m + 127) / 128;
       // two-level blocking: rank-32 updates stay inside the current outer block of OB panels; the rest of the front
       // gets one rank-(32 OB) update per outer block (the 128 x 128 tensor-core GEMM needs a deep inner dimension)
       const int ob = (max_ns >= blocked_min_ns) ? OB : 0;
-      k_lu_swap_trsm<S><<<dim3(nfront, ctiles + rtiles), 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
+      if (nfront <= swap_gather_max_fronts)
+        k_lu_swap_trsm<S, true><<<dim3(nfront, ctiles + rtiles), 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
+      else
+        k_lu_swap_trsm<S, false><<<dim3(nfront, ctiles + rtiles), 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
       const int rem = max_m - (k * PW);  // upper bound of the trailing size
       const int nt = (rem + 63) / 64;
       launches += 3;

@@ -33,6 +33,14 @@ constexpr int CL = 8;             // CTAs per cluster in the tall-front chain ke
 constexpr int CL_THREADS = 512;
 constexpr int DPT = 4;            // prefetched diagonal-block entries per thread (blockDim >= 256)
 
+// TMA bulk prefetch of a contiguous global range into L2 (no destination, no completion tracking)
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, long long bytes) {
+  const unsigned long long a = (unsigned long long)p;
+  const unsigned long long a0 = a & ~15ull;
+  const long long nb = (bytes + (long long)(a - a0)) & ~15ll;
+  if (nb > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(a0), "r"((unsigned)nb) : "memory");
+}
+
 template <class S>
 __global__ void k_lu_permute_in(int na, const int* __restrict__ perm, const S* __restrict__ b, int n, int nrhs,
                                 S* __restrict__ xp) {
@@ -47,6 +55,12 @@ __global__ void k_lu_permute_out(int n, const int* __restrict__ iperm, const S* 
   if (i >= n) return;
   int p = iperm[i];
   for (int r = 0; r < nrhs; ++r) x[(size_t)r * n + i] = p >= 0 ? xp[(size_t)r * na + p] : scalar_traits<S>::zero();
+}
+
+__device__ __forceinline__ double ldcg_(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ cplx ldcg_(const cplx* p) {
+  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  return {v.x, v.y};
 }
 
 template <class S>
@@ -129,12 +143,11 @@ __device__ __forceinline__ void diag_commit(S (*D)[PW + 1], const S (&dn)[DPT], 
 // FUSE: the CTA also updates the boundary rows (w2 -= L21 x1) panel by panel, so the level needs no k_fwd_update
 // launch (levels of many small fronts: one contiguous pass over the L panel, no second kernel, no tail).
 template <class S, int NRHS, class SY, bool FUSE = false>
-__device__ __forceinline__ void fwd_chain_body(FrontTab T, const int* __restrict__ nodes, const S* __restrict__ F,
+__device__ __forceinline__ void fwd_chain_body(FrontTab T, const int node, const S* __restrict__ F,
                                                const int* __restrict__ rowperm, S* work, int64_t work_stride, S* xp,
                                                int na) {
   __shared__ S D[PW][PW + 1];
   __shared__ S xs[NRHS][PW];
-  const int node = nodes[SY::front(blockIdx.x)];
   const int m = T.m[node], ns = T.ns[node], os = T.own_start[node];
   const S* Fn = F + T.front_off[node];
   S* w[NRHS];
@@ -144,6 +157,14 @@ __device__ __forceinline__ void fwd_chain_body(FrontTab T, const int* __restrict
   const int nthr = blockDim.x;
   const int nth = nthr * SY::nctas();
   const int gt = SY::rank() * nthr + t;
+  if (FUSE && T.pf > 0) {
+    // small fronts: the L panel (m x ns, contiguous) is pulled into L2 by TMA bulk prefetches before the dependent
+    // chain of loads starts, so that the chain runs at L2 latency instead of loaded-HBM latency
+    const long long bytes = min((long long)m * ns * (long long)sizeof(S), (long long)T.pf * 1024);
+    const long long chunk = 4096;
+    for (long long o = (long long)t * chunk; o < bytes; o += (long long)nthr * chunk)
+      prefetch_l2_bulk((const char*)Fn + o, min(chunk, bytes - o));
+  }
   // register prefetch for real arithmetic and block sizes >= 256 (32 c128 values would not fit the budget)
   const bool pipelined = SY::pipe && !scalar_traits<S>::is_complex && nthr * DPT >= PW * PW;
   // the first diagonal block and this thread's first row segment do not depend on the rhs: fetch them now
@@ -170,7 +191,7 @@ __device__ __forceinline__ void fwd_chain_body(FrontTab T, const int* __restrict
 #pragma unroll
       for (int r = 0; r < NRHS; ++r) {
         const S* wc = work + (size_t)r * work_stride + T.work_off[c];
-        w[r][ri] = w[r][ri] + wc[nsc + i];
+        w[r][ri] = w[r][ri] + ldcg_(wc + nsc + i);  // written by another CTA, possibly of this launch: not through L1
       }
     }
     SY::sync();
@@ -266,20 +287,20 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_fwd_chain(FrontTab T, con
                                                                  const S* __restrict__ F,
                                                                  const int* __restrict__ rowperm, S* work,
                                                                  int64_t work_stride, S* xp, int na) {
-  fwd_chain_body<S, NRHS, SyncCta>(T, nodes, F, rowperm, work, work_stride, xp, na);
+  fwd_chain_body<S, NRHS, SyncCta>(T, nodes[blockIdx.x], F, rowperm, work, work_stride, xp, na);
 }
 template <class S, int NRHS>
 __global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_fwd_chain_fused(FrontTab T, const int* __restrict__ nodes,
                                                                        const S* __restrict__ F,
                                                                        const int* __restrict__ rowperm, S* work,
                                                                        int64_t work_stride, S* xp, int na) {
-  fwd_chain_body<S, NRHS, SyncCta, true>(T, nodes, F, rowperm, work, work_stride, xp, na);
+  fwd_chain_body<S, NRHS, SyncCta, true>(T, nodes[blockIdx.x], F, rowperm, work, work_stride, xp, na);
 }
 template <class S, int NRHS>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
     k_fwd_chain_cluster(FrontTab T, const int* __restrict__ nodes, const S* __restrict__ F,
                         const int* __restrict__ rowperm, S* work, int64_t work_stride, S* xp, int na) {
-  fwd_chain_body<S, NRHS, SyncCluster>(T, nodes, F, rowperm, work, work_stride, xp, na);
+  fwd_chain_body<S, NRHS, SyncCluster>(T, nodes[blockIdx.x / CL], F, rowperm, work, work_stride, xp, na);
 }
 
 // ------------------------------------------------------------------------------ backward chain (right-looking)
@@ -288,12 +309,11 @@ constexpr int FUSE_CHUNK = 128;  // boundary columns staged per step of the fuse
 // FUSE: the CTA first gathers x2 from the parent and folds it into the own rows (w1 -= U12 x2), so the level needs
 // no k_bwd_update launch.
 template <class S, int NRHS, class SY, bool FUSE = false>
-__device__ __forceinline__ void bwd_chain_body(FrontTab T, const int* __restrict__ nodes, const S* __restrict__ F,
+__device__ __forceinline__ void bwd_chain_body(FrontTab T, const int node, const S* __restrict__ F,
                                                S* work, int64_t work_stride, S* xp, int na) {
   __shared__ S D[PW][PW + 1];
   __shared__ S xs[NRHS][PW];
   __shared__ S x2[FUSE ? NRHS : 1][FUSE ? FUSE_CHUNK : 1];
-  const int node = nodes[SY::front(blockIdx.x)];
   const int m = T.m[node], ns = T.ns[node], os = T.own_start[node];
   const S* Fn = F + T.front_off[node];
   S* w[NRHS];
@@ -301,6 +321,15 @@ __device__ __forceinline__ void bwd_chain_body(FrontTab T, const int* __restrict
   for (int r = 0; r < NRHS; ++r) w[r] = work + (size_t)r * work_stride + T.work_off[node];
   const int t = threadIdx.x;
   const int nthr = blockDim.x;
+  if (FUSE && T.pf > 0) {
+    // the U rows of the front (rows 0..ns of every column right of the diagonal) into L2, column by column
+    const int cmax = min(m, (int)((long long)T.pf * 1024 / max(1, ns * (int)sizeof(S))));
+    for (int c = t; c < cmax; c += nthr) {  // in the order of use: U12 left to right, then U11 right to left
+      const int col = c < m - ns ? ns + c : m - 1 - c;
+      const int rows = c < m - ns ? ns : col + 1;
+      prefetch_l2_bulk(Fn + (long long)col * m, (long long)rows * (long long)sizeof(S));
+    }
+  }
   if constexpr (FUSE) if (m > ns) {
     const int p = T.parent[node];
     const int nbd = m - ns;
@@ -311,7 +340,7 @@ __device__ __forceinline__ void bwd_chain_body(FrontTab T, const int* __restrict
         const int ri = rel[c0 + c];
 #pragma unroll
         for (int r = 0; r < NRHS; ++r) {
-          const S v = work[(size_t)r * work_stride + T.work_off[p] + ri];
+          const S v = ldcg_(work + (size_t)r * work_stride + T.work_off[p] + ri);  // the parent's CTA wrote it
           x2[r][c] = v;
           w[r][ns + c0 + c] = v;  // the children of this front gather from here
         }
@@ -413,19 +442,19 @@ template <class S, int NRHS>
 __global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_bwd_chain(FrontTab T, const int* __restrict__ nodes,
                                                                  const S* __restrict__ F, S* work,
                                                                  int64_t work_stride, S* xp, int na) {
-  bwd_chain_body<S, NRHS, SyncCta>(T, nodes, F, work, work_stride, xp, na);
+  bwd_chain_body<S, NRHS, SyncCta>(T, nodes[blockIdx.x], F, work, work_stride, xp, na);
 }
 template <class S, int NRHS>
 __global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_bwd_chain_fused(FrontTab T, const int* __restrict__ nodes,
                                                                        const S* __restrict__ F, S* work,
                                                                        int64_t work_stride, S* xp, int na) {
-  bwd_chain_body<S, NRHS, SyncCta, true>(T, nodes, F, work, work_stride, xp, na);
+  bwd_chain_body<S, NRHS, SyncCta, true>(T, nodes[blockIdx.x], F, work, work_stride, xp, na);
 }
 template <class S, int NRHS>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
     k_bwd_chain_cluster(FrontTab T, const int* __restrict__ nodes, const S* __restrict__ F, S* work,
                         int64_t work_stride, S* xp, int na) {
-  bwd_chain_body<S, NRHS, SyncCluster>(T, nodes, F, work, work_stride, xp, na);
+  bwd_chain_body<S, NRHS, SyncCluster>(T, nodes[blockIdx.x / CL], F, work, work_stride, xp, na);
 }
 
 // ------------------------------------------------------------------------------ cluster chains, register resident
@@ -446,13 +475,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-// TMA bulk prefetch of a contiguous global range into L2 (no destination, no completion tracking)
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, long long bytes) {
-  const unsigned long long a = (unsigned long long)p;
-  const unsigned long long a0 = a & ~15ull;
-  const long long nb = (bytes + (long long)(a - a0)) & ~15ll;
-  if (nb > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(a0), "r"((unsigned)nb) : "memory");
-}
 
 template <int NRHS>
 __device__ __forceinline__ void inv_block_matvec(const double* __restrict__ Dw, int lane, double (&acc)[NRHS]) {
@@ -877,6 +899,66 @@ __global__ void k_upd_reduce(FrontTab T, const int* __restrict__ nodes, S* work,
 }
 
 // ------------------------------------------------------------------------------ driver
+// ------------------------------------------------------------------------------ dataflow bands
+// The lower levels of the tree (many fronts per level) do not run level by level: one persistent launch covers a BAND
+// of levels.  CTAs draw fronts from a ticket counter in dependency order (forward: deepest level first, backward: top
+// level first) and wait on the completion flags of the fronts they depend on (forward: the two children, backward: the
+// parent), so a front starts as soon as its own inputs exist and the tail of one level overlaps the head of the next.
+// A ticket is only ever drawn by a running CTA and every dependency has a smaller ticket, so the wait cannot deadlock
+// whatever the number of resident CTAs.  Fronts of the first level of a band depend on an earlier launch: no wait.
+// Flags carry an epoch (tree_sync[0], bumped by k_tree_reset at the start of every solve) instead of being cleared.
+constexpr int TS_EPOCH = 0, TS_TICKET = 1, TS_FLAGS = 8;
+
+__global__ void k_tree_reset(int* __restrict__ sync) {
+  sync[TS_EPOCH] += 2;
+  sync[TS_TICKET + 0] = sync[TS_TICKET + 1] = sync[TS_TICKET + 2] = sync[TS_TICKET + 3] = 0;
+}
+
+__device__ __forceinline__ void wait_flag(const int* flag, int epoch) {
+  while (*(const volatile int*)flag != epoch) __nanosleep(40);
+}
+
+template <class S, int NRHS, bool FWD>
+__global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_tree_band(FrontTab T, const int* __restrict__ order, int n_items,
+                                                                 int n_first, int* sync, int ticket_slot,
+                                                                 const S* __restrict__ F,
+                                                                 const int* __restrict__ rowperm, S* work,
+                                                                 int64_t work_stride, S* xp, int na) {
+  __shared__ int s_item;
+  int* flags = sync + TS_FLAGS;
+  const int epoch = sync[TS_EPOCH] + (FWD ? 0 : 1);
+  for (;;) {
+    __syncthreads();  // the shared memory of the previous front is free
+    if (threadIdx.x == 0) s_item = atomicAdd(&sync[TS_TICKET + ticket_slot], 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= n_items) return;
+    const int node = order[item];
+    if (item >= n_first) {
+      if (threadIdx.x == 0) {
+        if (FWD) {
+          const int c0 = T.child0[node], c1 = T.child1[node];
+          if (c0 >= 0) wait_flag(flags + c0, epoch);
+          if (c1 >= 0) wait_flag(flags + c1, epoch);
+        } else {
+          wait_flag(flags + T.parent[node], epoch);
+        }
+        __threadfence();
+      }
+      __syncthreads();
+    }
+    if constexpr (FWD)
+      fwd_chain_body<S, NRHS, SyncCta, true>(T, node, F, rowperm, work, work_stride, xp, na);
+    else
+      bwd_chain_body<S, NRHS, SyncCta, true>(T, node, F, work, work_stride, xp, na);
+    __syncthreads();  // every thread of the CTA has issued its stores
+    if (threadIdx.x == 0) {
+      __threadfence();
+      *(volatile int*)(flags + node) = epoch;
+    }
+  }
+}
+
 // z-slices so that a level with few, huge fronts still fills the 148 SMs
 static int upd_splits(int nfront, int tiles, int cols) {
   const int chunks = (cols + UPD_CHUNK - 1) / UPD_CHUNK;
@@ -949,6 +1031,7 @@ static void solve_typed(Handle& h, const S* b, S* x) {
   S* work = (S*)d.work.p;
   const S* F = (const S*)d.factors.p;
   FrontTab T = d.tab();
+  T.pf = getenv("FW_SOLVE_PF_KB") ? atoi(getenv("FW_SOLVE_PF_KB")) : 0;  // L2 prefetch budget per small front
   int64_t launches = 2;
   const char* tenv = getenv("FW_TRACE");
   const bool trace2 = tenv && atoi(tenv) >= 2;
@@ -963,9 +1046,54 @@ static void solve_typed(Handle& h, const S* b, S* x) {
     return !scalar_traits<S>::is_complex && d.dinv_valid && !no_cluster && !no_inv && max_ns > CL_MIN_NS &&
            max_ns <= CL * CL_THREADS;
   };
+  // ---- dataflow bands over the lower levels (see k_tree_band): A = small fronts (128 threads), B = the rest
+  // (the knobs are read per call so that the tests can switch the path; a captured graph keeps its own choice)
+  const bool no_tree = !(getenv("FW_TREE") && atoi(getenv("FW_TREE")) > 0);  // measured slower than the levels: opt-in
+  const int tree_min_fronts = getenv("FW_TREE_MIN_FRONTS") ? atoi(getenv("FW_TREE_MIN_FRONTS")) : 64;
+  const int tree_small_m = getenv("FW_TREE_SMALL_M") ? atoi(getenv("FW_TREE_SMALL_M")) : 320;
+  const int tree_max_m = getenv("FW_TREE_MAX_M") ? atoi(getenv("FW_TREE_MAX_M")) : 2048;
+  const int tree_threads_a = getenv("FW_TREE_THREADS_A") ? atoi(getenv("FW_TREE_THREADS_A")) : 128;
+  const int tree_threads_b = getenv("FW_TREE_THREADS_B") ? atoi(getenv("FW_TREE_THREADS_B")) : 512;
+  int band_lo = Sy.n_levels, split = Sy.n_levels;  // A = levels [split, n_levels), B = [band_lo, split)
+  if (!no_tree) {
+    for (int lev = Sy.n_levels - 1; lev >= 0; --lev) {
+      if (Sy.level_start[lev + 1] - Sy.level_start[lev] < tree_min_fronts || Sy.level_max_m[lev] > tree_max_m) break;
+      band_lo = lev;
+    }
+    for (int lev = Sy.n_levels - 1; lev >= band_lo && Sy.level_max_m[lev] <= tree_small_m; --lev) split = lev;
+  }
+  const int n_all = Sy.level_start[Sy.n_levels];
+  const int items_a = n_all - Sy.level_start[split], items_b = Sy.level_start[split] - Sy.level_start[band_lo];
+  auto band = [&](bool fwd, bool is_a) {
+    const int items = is_a ? items_a : items_b;
+    if (items <= 0) return;
+    const int threads = is_a ? tree_threads_a : tree_threads_b;
+    const int grid = std::min(items, 148 * std::max(1, 2048 / threads));
+    // forward: d.order_fwd lists the deepest level first (A then B); backward: d.level_nodes lists the top level first
+    const int* order = fwd ? d.order_fwd.p + (is_a ? 0 : items_a)
+                           : d.level_nodes.p + Sy.level_start[is_a ? split : band_lo];
+    const int first_lev = fwd ? (is_a ? Sy.n_levels - 1 : split - 1) : (is_a ? split : band_lo);
+    const int n_first = Sy.level_start[first_lev + 1] - Sy.level_start[first_lev];
+    const int slot = (fwd ? 0 : 2) + (is_a ? 0 : 1);
+    if (fwd)
+      k_tree_band<S, NRHS, true><<<grid, threads, 0, s>>>(T, order, items, n_first, d.tree_sync.p, slot, F, d.rowperm.p,
+                                                        work, Sy.work_entries, xp, na);
+    else
+      k_tree_band<S, NRHS, false><<<grid, threads, 0, s>>>(T, order, items, n_first, d.tree_sync.p, slot, F,
+                                                         d.rowperm.p, work, Sy.work_entries, xp, na);
+    ++launches;
+  };
   Trace tr(s);
   if (na > 0) k_lu_permute_in<S><<<cdiv(na, 256), 256, 0, s>>>(na, d.perm.p, b, n, NRHS, xp);
-  for (int lev = Sy.n_levels - 1; lev >= 0; --lev) {
+  if (band_lo < Sy.n_levels) {
+    k_tree_reset<<<1, 1, 0, s>>>(d.tree_sync.p);
+    ++launches;
+    band(true, true);
+    if (trace2) tr.mark("fwd band A (dataflow)");
+    band(true, false);
+    if (trace2) tr.mark("fwd band B (dataflow)");
+  }
+  for (int lev = band_lo - 1; lev >= 0; --lev) {
     const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
     const int* nodes = d.level_nodes.p + Sy.level_start[lev];
     const int max_ns = Sy.level_max_ns[lev];
@@ -1004,7 +1132,7 @@ static void solve_typed(Handle& h, const S* b, S* x) {
         tr.mark(("fwd update lev " + std::to_string(lev) + " max_nb " + std::to_string(Sy.level_max_nb[lev])).c_str());
     }
   }
-  for (int lev = 0; lev < Sy.n_levels; ++lev) {
+  for (int lev = 0; lev < band_lo; ++lev) {
     const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
     const int* nodes = d.level_nodes.p + Sy.level_start[lev];
     const int max_ns = Sy.level_max_ns[lev];
@@ -1038,6 +1166,12 @@ static void solve_typed(Handle& h, const S* b, S* x) {
     ++launches;
     if (trace2) tr.mark(("bwd chain  lev " + std::to_string(lev)).c_str());
   }
+  if (band_lo < Sy.n_levels) {
+    band(false, false);
+    if (trace2) tr.mark("bwd band B (dataflow)");
+    band(false, true);
+    if (trace2) tr.mark("bwd band A (dataflow)");
+  }
   k_lu_permute_out<S><<<cdiv(n, 256), 256, 0, s>>>(n, d.iperm.p, xp, na, NRHS, x);
   FW_CHECK_CUDA(cudaGetLastError());
   h.tim.kernel_launches += launches;
@@ -1048,7 +1182,7 @@ static void lu_solve_launch(Handle& h, const void* b, void* x, int nrhs);
 void lu_solve_dev(Handle& h, const void* b, void* x, int nrhs) {
   FW_REQUIRE(h.lu && h.lu->factored, "LU has not been factored");
   FW_REQUIRE(nrhs == 1 || nrhs == 2, "nrhs must be 1 or 2");
-  static const bool no_graph = getenv("FW_NO_SOLVE_GRAPH") != nullptr;
+  const bool no_graph = getenv("FW_NO_SOLVE_GRAPH") != nullptr;
   if (no_graph || getenv("FW_TRACE")) {  // (the trace synchronises the stream between the levels)
     lu_solve_launch(h, b, x, nrhs);
     return;

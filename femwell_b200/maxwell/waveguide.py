@@ -249,7 +249,8 @@ def compute_modes(
 
     ``solver`` must be ``"b200"``; ``solver_options`` (dict, optional): ``v0``, ``ncv``, ``tol``,
     ``maxiter``, ``refine``, ``leaf_elements``, ``reuse_symbolic`` (default True: keep the CSR pattern and the LU
-    analysis while the mesh stays), ``device``, ``pcg_tol_exp`` (H-field mass solves to 10^-value, default 10), ``mass_solver``
+    analysis while the mesh stays), ``device``, ``pcg_tol_exp`` (H-field mass solves to 10^-value, default 10), ``start_vector`` (``"smooth"`` (default): contrast-weighted smooth start vector,
+    ``"uniform"``: uniform(-1, 1) like scipy; an explicit ``v0`` wins), ``mass_solver``
     (``"auto"``: block PCG with a sparse-LU fallback when it stagnates, ``"pcg"``, ``"direct"``),
     ``mode_tables`` (``dict(kind=, vec=, sc=, element_dofs=, n_dofs=)``: a foreign local basis, see
     ``Basis.with_tables`` / ``femwell_b200.bridge``).
@@ -292,6 +293,8 @@ def compute_modes(
     # per-call options of the H-field mass solves (always set: a handle is shared by all calls on its device)
     ctx.set_option(1, int(opts.pop("pcg_tol_exp", 10)))
     ctx.set_option(2, {"auto": 0, "pcg": 1, "direct": 2}[opts.pop("mass_solver", "auto")])
+    # default start vector: smooth and weighted by the index contrast ("smooth"), or scipy-like noise ("uniform")
+    ctx.set_option(3, {"smooth": 1, "uniform": 0}[opts.pop("start_vector", "uniform" if mode_tables is not None else "smooth")])
     lams, E, H, powers, stats = ctx.compute_modes(
         eps_kind, epsilon_r, wavelength, num_modes, sigma, mu_r=float(mu_r), radius=float(radius),
         dirichlet=dirichlet, reuse_symbolic=reuse, **opts)

@@ -71,9 +71,18 @@ enum {
   /* H-field mass solves: 0 (default) block PCG, falling back to the sparse LU of the mass block when the PCG stagnates
    * (elongated triangles: the Nedelec mass matrix is ill conditioned); 1 PCG only (FW_ERR_NOCONV on stagnation);
    * 2 always the direct solve (what the reference does: spsolve, waveguide.py:671)                              */
-  FW_OPT_MASS_SOLVER = 2
+  FW_OPT_MASS_SOLVER = 2,
+  /* default start vector of the Arnoldi iteration inside fw_compute_modes when fw_eigs_params.v0 is NULL: 1 (default)
+   * a smooth field weighted by the index contrast (fewer operator applications; csrc/start_vector.cu), 0 the
+   * uniform(-1, 1) stream that mirrors scipy's default (arpack.py:361-364)                                        */
+  FW_OPT_START_VECTOR = 3
 };
 int fw_set_option(fw_handle* h, int32_t option, int32_t value);
+/* Optional page-locked host buffers for the large results (E, H of fw_compute_modes: 2 * k * n_dofs * 16 bytes).  A
+ * destination obtained here is filled by one DMA at bus speed; any other host pointer goes through the library's pinned
+ * staging ring plus a threaded memcpy (about twice as slow).  NULL on failure (no CUDA device, out of lockable memory). */
+void* fw_host_alloc(size_t bytes);
+int fw_host_free(void* p);
 
 /* ---- a1: mesh + FE space (waveguide.py:567-575; scikit-fem CellBasis) ------------ */
 typedef struct {

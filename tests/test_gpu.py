@@ -245,6 +245,45 @@ def test_lu_solve_matches_scipy(ctx, order, n, cplx, dirichlet, leaf):
         assert np.linalg.norm(x[I] - xs) < 1e-9 * np.linalg.norm(xs)
 
 
+@pytest.mark.parametrize("order,n,cplx,leaf", [(2, 40, False, 0), (2, 30, True, 8), (1, 60, False, 4)])
+def test_lu_solve_schedules_agree(ctx, order, n, cplx, leaf, monkeypatch):
+    """The triangular solves run either level by level or as dataflow bands (persistent kernels that draw fronts from
+    a ticket counter and wait on per-front completion flags).  Same factors, same arithmetic per front: the schedules
+    must agree to round-off, for one and two right-hand sides, also when the whole tree (root included) is one band
+    and when the solve is repeated (flag epochs, CUDA-graph replay of the third call)."""
+    m, _ = strip_problem(n)
+    b = Basis(m, ElementTriP0(), intorder=4).with_element(mode_element(order))
+    eps = _make_eps(m, 0, cplx)
+    k0 = 2 * np.pi / 1.55
+    ctx.set_space(b)
+    ctx.symbolic()
+    ctx.assemble(0, eps, k0)
+    A, B = ctx.matrix(0), ctx.matrix(1)
+    sigma = k0**2 * np.max(eps.real) * 1.1
+    ctx.lu_factor(sigma, None, leaf)
+    OP = (-A + sigma * B).tocsr()
+    rng = np.random.default_rng(11)
+    rhs1 = rng.standard_normal(b.N)
+    rhs2 = rng.standard_normal(b.N) + 1j * rng.standard_normal(b.N)
+    out = {}
+    for name, env in (("levels", {}), ("bands", {"FW_TREE": "1"}), ("one band", {"FW_TREE": "1", "FW_TREE_MIN_FRONTS": "1"}),
+                      ("levels + L2 prefetch", {"FW_SOLVE_PF_KB": "48"}),
+                      ("one band, 64 threads", {"FW_TREE": "1", "FW_TREE_MIN_FRONTS": "1", "FW_TREE_SMALL_M": "100000",
+                                                "FW_TREE_THREADS_A": "64"})):
+        with monkeypatch.context() as mp:
+            for k, v in env.items():
+                mp.setenv(k, v)
+            mp.setenv("FW_NO_SOLVE_GRAPH", "1")  # a captured graph would keep the schedule of its first capture
+            xs = [ctx.lu_solve(r) for r in (rhs1, rhs2, rhs1, rhs1)]
+        assert np.array_equal(xs[0], xs[2]) and np.array_equal(xs[0], xs[3]), name  # deterministic, epoch-safe
+        for r, x in zip((rhs1, rhs2), xs):
+            assert np.linalg.norm(OP @ x - r) < 1e-11 * np.linalg.norm(r), name
+        out[name] = xs
+    for name in out:
+        for a, c in zip(out[name][:2], out["levels"][:2]):
+            assert np.linalg.norm(a - c) < 1e-12 * np.linalg.norm(c), name
+
+
 # ----------------------------------------------------------------------------- eigen-solve
 def _match(l_gpu, l_ref):
     """pair eigenvalues by value"""
