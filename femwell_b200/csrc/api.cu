@@ -854,6 +854,9 @@ int fw_compute_modes(fw_handle* hh, const fw_modes_params* prm, double* lams, do
   std::string why;
   h.v0_dev_valid = !prm->eigs.v0 && h.smooth_v0 &&
                    smooth_start_vector(h, prm->eps_kind, prm->eps_is_complex != 0, prm->eps, h.v0_dev);
+  if (getenv("FW_TRACE"))
+    fprintf(stderr, "[fw-trace] start vector: user v0 %d, option %d, smooth vector ready %d\n", prm->eigs.v0 != nullptr,
+            (int)h.smooth_v0, (int)h.v0_dev_valid);
   bool ok = false;
   try {
     ok = eigs_shift_invert(h, prm->eigs, (std::complex<double>*)lams, Xd, st, &why);

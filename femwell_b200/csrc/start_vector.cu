@@ -37,10 +37,9 @@ __device__ inline double eps_re_(const double* __restrict__ eps, int e) {
 template <int EPSKIND, bool CPLX>
 __global__ void k_sv_eps_range(int ne, const double* __restrict__ eps, unsigned long long* __restrict__ range) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= ne) return;
-  const unsigned long long v = enc_(eps_re_<EPSKIND, CPLX>(eps, e));
-  // one atomic per warp
-  unsigned long long lo = v, hi = v;
+  // one atomic per warp (every lane takes part in the shuffles: lanes past the end carry neutral values)
+  unsigned long long lo = ~0ull, hi = 0ull;
+  if (e < ne) lo = hi = enc_(eps_re_<EPSKIND, CPLX>(eps, e));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const unsigned long long a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);

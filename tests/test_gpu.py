@@ -1153,3 +1153,28 @@ def test_coupler_geometry_sweep_matches_oracle(ctx):
     assert np.all(table[1:, col["ref_overlap_iso"]] > 0.8) and np.all(table[1:, col["ref_overlap_iso"]] < 1.05)
     # coupling gets weaker (coupling length longer) with the gap at fixed width
     assert table[2, col["coupling_length_um"]] > table[0, col["coupling_length_um"]]
+
+
+def test_smooth_start_vector_gives_the_same_modes_in_fewer_steps(ctx):
+    """Default start vector of compute_modes: a smooth field weighted by the index contrast (csrc/start_vector.cu)
+    instead of scipy's uniform(-1, 1) noise.  Same eigenvalues (1e-11), not more operator applications; an element
+    count that is not a multiple of the warp size exercises the ragged reductions; repeated calls are bit-identical."""
+    from femwell_b200.maxwell.waveguide import compute_modes
+
+    m, eps = strip_problem(25, slab_h=0.11)
+    assert m.nelements % 32 != 0
+    b0 = Basis(m, ElementTriP0(), intorder=4)
+    res = {}
+    for sv in ("uniform", "smooth", "smooth"):
+        modes = compute_modes(b0, eps, 1.55, num_modes=3, order=2, solver_options={"start_vector": sv})
+        res.setdefault(sv, []).append((modes.n_effs.copy(), modes.stats["n_op"], modes[0].E.copy()))
+    (nu, opu, _), (ns, ops, Es), (ns2, ops2, Es2) = res["uniform"][0], res["smooth"][0], res["smooth"][1]
+    assert np.abs(nu - ns).max() < 1e-11 * np.abs(nu).max()
+    assert ops <= opu, (ops, opu)
+    assert ops == ops2 and np.array_equal(ns, ns2) and np.array_equal(Es, Es2)
+    # complex DG-P1 epsilon goes through the same kernels
+    eps_c = _make_eps(m, 1, True, seed=3)
+    b1 = Basis(m, ElementDG(ElementTriP1()), intorder=4)
+    a = compute_modes(b1, eps_c, 1.55, num_modes=1, order=1, solver_options={"start_vector": "uniform"})
+    c = compute_modes(b1, eps_c, 1.55, num_modes=1, order=1)
+    assert abs(a.n_effs[0] - c.n_effs[0]) < 1e-11 * abs(a.n_effs[0])
