@@ -99,7 +99,7 @@ struct Handle {
   bool hint_valid = false;
   // big LU buffers live here so that they survive a new space / analysis (no 25 GB cudaFree + cudaMalloc per solve)
   struct LUArena {
-    DevBuf<double> factors, work, xperm, scratch, dinv;
+    DevBuf<double> factors, work, xperm, scratch, dinv, tinv, tinv_tmp;
   } lu_arena;
   // pinned staging ring for large device -> pageable-host copies (results E, H)
   void* pinned[2] = {nullptr, nullptr};

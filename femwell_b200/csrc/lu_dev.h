@@ -17,6 +17,7 @@ struct FrontTab {
   const int *blist, *rel;
   const long long* dinv_off;  // per front: offset of its inverted diagonal blocks in LUDevice::dinv, or -1
   int pf = 0;                 // substitution kernels: L2 prefetch budget per small front in KB (0 = off)
+  const long long* tinv_off = nullptr;  // per front: offset of inv(L11), inv(U11) (2 ns^2 entries) in LUDevice::tinv, or -1
 };
 
 struct LUDevice {
@@ -32,17 +33,36 @@ struct LUDevice {
   DevBuf<double>& dinv;
   int64_t dinv_entries = 0;
   bool dinv_valid = false;
+  // selective inversion (lu_tinv.cu): explicit inverses of the whole pivot blocks L11 (unit lower) and U11 of the fronts
+  // of the upper levels, so that their substitution "chains" become dense triangular matrix-vector products
+  DevBuf<long long> tinv_off;
+  DevBuf<double>&tinv, &tinv_tmp;
+  int64_t tinv_entries = 0;
+  int tinv_min_level_ns = 0;  // levels whose largest pivot block reaches this size carry the inverses
+  bool tinv_valid = false;
   DevBuf<int> counters;
   DevBuf<uint8_t> active;
   // dataflow substitution: nodes in deepest-level-first order; tree_sync = [epoch, 4 tickets, pad, one flag per node]
   DevBuf<int> order_fwd, tree_sync;
   explicit LUDevice(Handle::LUArena& a)
-      : factors(a.factors), work(a.work), xperm(a.xperm), scratch(a.scratch), dinv(a.dinv) {}
+      : factors(a.factors), work(a.work), xperm(a.xperm), scratch(a.scratch), dinv(a.dinv), tinv(a.tinv),
+        tinv_tmp(a.tinv_tmp) {}
   FrontTab tab() const {
-    return FrontTab{m.p, ns.p, own_start.p, parent.p, child0.p, child1.p, front_off.p, work_off.p, blist_off.p,
-                    blist.p, rel.p, dinv_off.p};
+    FrontTab t{m.p, ns.p, own_start.p, parent.p, child0.p, child1.p, front_off.p, work_off.p, blist_off.p,
+               blist.p, rel.p, dinv_off.p};
+    t.tinv_off = tinv_off.p;
+    return t;
   }
 };
+
+// selective inversion (lu_tinv.cu)
+constexpr int TINV_DEFAULT_MIN_NS = 200;  // (pivot blocks of the lower levels are too ill conditioned: residual 5e-10 at 100)
+bool tinv_level(const LUSymbolic& S, const LUDevice& d, int lev);
+void tinv_build(Handle& h, LUDevice& d, const LUSymbolic& S);  // after the numeric factorisation (f64 only)
+template <int NRHS>
+void tinv_forward_level(Handle& h, LUDevice& d, const LUSymbolic& S, int lev, double* work, double* xp, int na);
+template <int NRHS>
+void tinv_backward_level(Handle& h, LUDevice& d, const LUSymbolic& S, int lev, double* work, double* xp, int na);
 
 // large-front GEMM (lu_gemm.cu)
 template <class S>

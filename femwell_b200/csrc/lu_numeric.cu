@@ -198,6 +198,24 @@ static void lu_analyse_finish(Handle& h) {
     d.dinv_entries = tot;
   }
   {
+    // storage for inv(L11), inv(U11) of the fronts of the upper levels (selective inversion, lu_tinv.cu)
+    d.tinv_min_level_ns = getenv("FW_TINV_MIN_NS") ? atoi(getenv("FW_TINV_MIN_NS")) : TINV_DEFAULT_MIN_NS;
+    std::vector<int64_t> toff((size_t)std::max(1, S.n_nodes), -1);
+    int64_t tot = 0;
+    for (int lev = 0; lev < S.n_levels; ++lev) {
+      if (S.level_max_ns[lev] < d.tinv_min_level_ns || getenv("FW_NO_TINV")) continue;
+      for (int q = S.level_start[lev]; q < S.level_start[lev + 1]; ++q) {
+        const int node = S.level_nodes[q];
+        if (S.ns[node] == 0) continue;
+        toff[node] = tot;
+        tot += (int64_t)2 * S.ns[node] * S.ns[node];
+      }
+    }
+    up64(d.tinv_off, toff, s);
+    d.tinv_entries = tot;
+    d.tinv_valid = false;
+  }
+  {
     // dataflow substitution (lu_solve.cu): nodes deepest level first, one completion flag per node
     std::vector<int> order;
     order.reserve((size_t)S.n_nodes);
@@ -1320,6 +1338,13 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
     }
     d.dinv_valid = true;
     tr.mark("lu factor: diagonal-block inverses");
+  }
+  d.tinv_valid = false;
+  if constexpr (!scalar_traits<S>::is_complex) {
+    if (d.tinv_entries > 0) {
+      tinv_build(h, d, Sy);
+      tr.mark("lu factor: pivot-block inverses (selective inversion)");
+    }
   }
   FW_CHECK_CUDA(cudaGetLastError());
   int cnt[4] = {0, 0, 0, 0};

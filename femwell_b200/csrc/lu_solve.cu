@@ -1037,6 +1037,7 @@ static void solve_typed(Handle& h, const S* b, S* x) {
   const bool trace2 = tenv && atoi(tenv) >= 2;
   const bool no_cluster = getenv("FW_NO_CLUSTER") != nullptr;
   const bool no_inv = getenv("FW_NO_DINV") != nullptr;
+  const bool no_tinv = getenv("FW_NO_TINV_SOLVE") != nullptr;
   // levels of many small fronts: chain and off-diagonal update in one kernel (FW_FUSE_MAX_M=0 disables)
   static const int fuse_max_m = getenv("FW_FUSE_MAX_M") ? atoi(getenv("FW_FUSE_MAX_M")) : 512;
   // forward fused kernel: two rows per thread (blockDim = m / 2) doubles the fronts in flight per SM -- the kernel is
@@ -1098,8 +1099,14 @@ static void solve_typed(Handle& h, const S* b, S* x) {
     const int* nodes = d.level_nodes.p + Sy.level_start[lev];
     const int max_ns = Sy.level_max_ns[lev];
     // measured (500k triangles): forward fusion pays only when the pivot block spans several panels
-    const bool fuse = Sy.level_max_m[lev] <= fuse_max_m && nfront >= 296 && max_ns >= 64;
-    if (fuse)
+    bool tinv = false;  // pivot-block solves as triangular matrix-vector products (selective inversion, lu_tinv.cu)
+    if constexpr (!scalar_traits<S>::is_complex) tinv = !no_tinv && tinv_level(Sy, d, lev);
+    const bool fuse = !tinv && Sy.level_max_m[lev] <= fuse_max_m && nfront >= 296 && max_ns >= 64;
+    if (tinv) {
+      if constexpr (!scalar_traits<S>::is_complex) {
+        tinv_forward_level<NRHS>(h, d, Sy, lev, work, xp, na);
+      }
+    } else if (fuse)
       k_fwd_chain_fused<S, NRHS><<<nfront, chain_threads(Sy.level_max_m[lev] / fuse_tdiv), 0, s>>>(T, nodes, F, d.rowperm.p, work,
                                                                                     Sy.work_entries, xp, na);
     else if (use_inv(max_ns))
@@ -1136,7 +1143,9 @@ static void solve_typed(Handle& h, const S* b, S* x) {
     const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
     const int* nodes = d.level_nodes.p + Sy.level_start[lev];
     const int max_ns = Sy.level_max_ns[lev];
-    const bool fuse = Sy.level_max_m[lev] <= fuse_max_m && nfront >= 296;
+    bool tinv = false;
+    if constexpr (!scalar_traits<S>::is_complex) tinv = !no_tinv && tinv_level(Sy, d, lev);
+    const bool fuse = !tinv && Sy.level_max_m[lev] <= fuse_max_m && nfront >= 296;
     if (Sy.level_max_nb[lev] > 0 && !fuse) {
       const int tiles = std::max(1, (max_ns + UPD_ROWS - 1) / UPD_ROWS);
       const int max_nb = Sy.level_max_nb[lev];
@@ -1154,7 +1163,11 @@ static void solve_typed(Handle& h, const S* b, S* x) {
       }
       if (trace2) tr.mark(("bwd update lev " + std::to_string(lev)).c_str());
     }
-    if (fuse)
+    if (tinv) {
+      if constexpr (!scalar_traits<S>::is_complex) {
+        tinv_backward_level<NRHS>(h, d, Sy, lev, work, xp, na);
+      }
+    } else if (fuse)
       k_bwd_chain_fused<S, NRHS><<<nfront, chain_threads(std::max(max_ns, 64)), 0, s>>>(T, nodes, F, work, Sy.work_entries,
                                                                                      xp, na);
     else if (use_inv(max_ns))

@@ -268,6 +268,7 @@ def test_lu_solve_schedules_agree(ctx, order, n, cplx, leaf, monkeypatch):
     out = {}
     for name, env in (("levels", {}), ("bands", {"FW_TREE": "1"}), ("one band", {"FW_TREE": "1", "FW_TREE_MIN_FRONTS": "1"}),
                       ("levels + L2 prefetch", {"FW_SOLVE_PF_KB": "48"}),
+                      ("levels, substitution chains instead of inverse pivot blocks", {"FW_NO_TINV_SOLVE": "1"}),
                       ("one band, 64 threads", {"FW_TREE": "1", "FW_TREE_MIN_FRONTS": "1", "FW_TREE_SMALL_M": "100000",
                                                 "FW_TREE_THREADS_A": "64"})):
         with monkeypatch.context() as mp:
@@ -281,7 +282,7 @@ def test_lu_solve_schedules_agree(ctx, order, n, cplx, leaf, monkeypatch):
         out[name] = xs
     for name in out:
         for a, c in zip(out[name][:2], out["levels"][:2]):
-            assert np.linalg.norm(a - c) < 1e-12 * np.linalg.norm(c), name
+            assert np.linalg.norm(a - c) < 1e-11 * np.linalg.norm(c), name
 
 
 # ----------------------------------------------------------------------------- eigen-solve
