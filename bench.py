@@ -350,8 +350,9 @@ def main():
     peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     tt = stats["timings"]
 
-    def ncu_traffic(csv_name, kernel_substr, n_expected=None):
-        """DRAM bytes (read + write) per launch of a kernel from a committed `ncu --set full` summary, or None"""
+    def ncu_traffic(csv_name, kernel_substr, n_expected=None, total=False):
+        """DRAM bytes (read + write) per launch of a kernel from a committed `ncu --set full` summary, or None;
+        total=True: the sum over all rows (a launch UNIT made of many kernels, e.g. one substitution pair)"""
         try:
             import csv
 
@@ -359,11 +360,11 @@ def main():
             hdr, units = rows[0], rows[1]
             ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            sel = [r for r in rows[2:] if kernel_substr in r[1]]
+            sel = [r for r in rows[2:] if kernel_substr in r[0] or (len(r) > 1 and kernel_substr in r[1])]
             if not sel:
                 return None
             tot = [float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0) for r in sel]
-            return float(np.mean(tot))
+            return float(np.sum(tot)) if total else float(np.mean(tot))
         except Exception:
             return None
 
@@ -372,10 +373,11 @@ def main():
     t_pair = float(np.sum(solve_ms)) / 1000.0 / max(1.0, solve_pairs)
     solve_bytes = float(tt["lu_solve_entries"]) * sv
     solve_achieved = solve_bytes / t_pair / 1e9 if t_pair > 0 else 0.0
-    roofline = {"kernel": "sparse-LU triangular solves (k_fwd/bwd_chain*, k_fwd/bwd_update, k_*_chain_inv): one forward + "
-                          "backward substitution pair per Arnoldi step, ~60 launches per pair",
+    roofline = {"kernel": "sparse-LU triangular solves (k_fwd/bwd_chain_fused, k_fwd/bwd_chain, k_fwd/bwd_update, "
+                          "k_tinv_matvec on the inverse pivot blocks of the top levels): one forward + backward "
+                          "substitution pair per Arnoldi step, ~75 kernel nodes replayed as one CUDA graph",
                 "bound": "hbm", "achieved": solve_achieved, "peak": peak, "unit": "GB/s", "frac": solve_achieved / peak,
-                "traffic": ncu_traffic("ncu_r02_solve_full.csv", "chain"),
+                "traffic": ncu_traffic("ncu_r02_solve_pair_full.csv", "k_", total=True),
                 "algorithmic_bytes_per_launch": solve_bytes, "seconds_per_launch": t_pair,
                 "launch_unit": "one solve pair (all its kernels); L and U entries of every front read once: "
                                "sum(m^2 - (m-ns)^2) x 8 B from the analysis tables",
@@ -385,7 +387,9 @@ def main():
     alg_k1 = algorithmic_bytes_element_kernel(m.nelements, m.nvertices, 14, 8, sv, 8)
     t_elem = float(np.mean(elem_ms)) / 1000.0
     n_k1 = int(tt.get("element_kernel_launches", 1))
-    fp64_peak = 37.0  # TFLOP/s: B200 FP64 datasheet figure -- MEASURED_PEAKS.json has no FP64 entry (stated fallback)
+    # TFLOP/s: measured on this pool with scripts/microbench/fp64_peak.cu (DMMA m8n8k4 from registers, 37.1; DFMA 33.9;
+    # profiles/fp64_peak_r02.log) -- MEASURED_PEAKS.json has no FP64 entry
+    fp64_peak = 37.1
     t_fac = float(np.mean(factor_ms)) / 1000.0
     rooflines = {
         "element_kernel_K1": {"kernel": "k_element_blocks_const" if n_k1 == 1 else "k_element_blocks (3 launches)",
@@ -394,12 +398,14 @@ def main():
                                                                                          "k_element_blocks_const"),
                               "algorithmic_bytes_per_launch": alg_k1 / n_k1, "seconds_per_launch": t_elem / n_k1,
                               "share_of_step": t_elem * 1000.0 / float(np.mean(dev_ms))},
-        "lu_factor": {"kernel": "multifrontal LU numeric phase (panel / TRSM / GEMM / extend-add kernels)",
+        "lu_factor": {"kernel": "multifrontal LU numeric phase (panel / TRSM / DMMA GEMM / extend-add kernels, pivot-block "
+                                "inverses)",
                       "bound": "fp64", "achieved": tt["lu_factor_flops"] / t_fac / 1e12 if t_fac > 0 else 0.0,
                       "peak": fp64_peak, "unit": "TFLOP/s",
                       "frac": (tt["lu_factor_flops"] / t_fac / 1e12 / fp64_peak) if t_fac > 0 else 0.0,
                       "flops_per_factorisation": tt["lu_factor_flops"], "seconds": t_fac,
-                      "peak_source": "datasheet FP64 (no measured FP64 peak in MEASURED_PEAKS.json)",
+                      "peak_source": "measured FP64 tensor (DMMA) peak, profiles/fp64_peak_r02.log (no FP64 entry in "
+                                     "MEASURED_PEAKS.json)",
                       "share_of_step": t_fac * 1000.0 / float(np.mean(dev_ms))},
     }
     try:

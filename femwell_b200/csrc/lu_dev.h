@@ -56,7 +56,8 @@ struct LUDevice {
 };
 
 // selective inversion (lu_tinv.cu)
-constexpr int TINV_DEFAULT_MIN_NS = 200;  // (pivot blocks of the lower levels are too ill conditioned: residual 5e-10 at 100)
+constexpr int TINV_DEFAULT_MIN_NS = 110;
+bool tinv_level_static(const LUSymbolic& S, int min_ns, int lev);
 bool tinv_level(const LUSymbolic& S, const LUDevice& d, int lev);
 void tinv_build(Handle& h, LUDevice& d, const LUSymbolic& S);  // after the numeric factorisation (f64 only)
 template <int NRHS>

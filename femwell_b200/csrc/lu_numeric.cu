@@ -203,7 +203,7 @@ static void lu_analyse_finish(Handle& h) {
     std::vector<int64_t> toff((size_t)std::max(1, S.n_nodes), -1);
     int64_t tot = 0;
     for (int lev = 0; lev < S.n_levels; ++lev) {
-      if (S.level_max_ns[lev] < d.tinv_min_level_ns || getenv("FW_NO_TINV")) continue;
+      if (!tinv_level_static(S, d.tinv_min_level_ns, lev) || getenv("FW_NO_TINV")) continue;
       for (int q = S.level_start[lev]; q < S.level_start[lev + 1]; ++q) {
         const int node = S.level_nodes[q];
         if (S.ns[node] == 0) continue;

@@ -18,8 +18,14 @@
 
 namespace fw {
 
+// Levels that carry inverse pivot blocks: pivot blocks of at least tinv_min_level_ns rows, and never the three deepest
+// levels of the tree -- the pivot blocks of the leaf fronts (interior dofs of a few elements of the shifted, indefinite
+// pencil) are too ill conditioned for explicit inverses: with them the solve residual rose from 9e-13 to 5e-10.
+bool tinv_level_static(const LUSymbolic& S, int min_ns, int lev) {
+  return S.level_max_ns[lev] >= min_ns && lev < S.n_levels - 3;
+}
 bool tinv_level(const LUSymbolic& S, const LUDevice& d, int lev) {
-  return d.tinv_valid && S.level_max_ns[lev] >= d.tinv_min_level_ns;
+  return d.tinv_valid && tinv_level_static(S, d.tinv_min_level_ns, lev);
 }
 
 // ------------------------------------------------------------------------------ 32 x 32 diagonal blocks
@@ -241,7 +247,7 @@ void tinv_build(Handle& h, LUDevice& d, const LUSymbolic& S) {
   }
   for (int lev = 0; lev < S.n_levels; ++lev) {
     const int max_ns = S.level_max_ns[lev];
-    if (max_ns < d.tinv_min_level_ns) continue;
+    if (!tinv_level_static(S, d.tinv_min_level_ns, lev)) continue;
     const int nfront = S.level_start[lev + 1] - S.level_start[lev];
     const int* nodes = d.level_nodes.p + S.level_start[lev];
     const int npan = (max_ns + PW - 1) / PW;

@@ -1,0 +1,23 @@
+"""One LU factorisation + ONE forward/backward substitution pair at config-2 size, no CUDA graph: the command profiled
+under `ncu --set full` for the DRAM traffic of the whole pair (bench.py roofline.traffic)."""
+import os, sys
+os.environ["FW_NO_SOLVE_GRAPH"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+from common import mode_element, strip_problem
+from femwell_b200.basis import Basis
+from femwell_b200.context import Context
+from femwell_b200.element import ElementTriP0
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 500
+ctx = Context(0)
+m, eps = strip_problem(n, slab_h=0.11)
+b = Basis(m, ElementTriP0(), intorder=4).with_element(mode_element(2))
+k0 = 2 * np.pi / 1.55
+ctx.set_space(b); ctx.symbolic(); ctx.assemble(0, eps, k0)
+sigma = k0**2 * eps.max() * 1.1
+ctx.lu_factor(sigma)
+rhs = np.random.default_rng(0).uniform(-1, 1, b.N)
+x = ctx.lu_solve(rhs, refine=0, force_real=True)
+r = -ctx.spmv(0, x) + sigma * ctx.spmv(1, x) - rhs
+print("residual", np.linalg.norm(r) / np.linalg.norm(rhs))
