@@ -1222,9 +1222,24 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
   // updates (K = ns)
   static const int big_gemm_min_panel =
       getenv("FW_BIG_GEMM_MIN_PANEL") ? atoi(getenv("FW_BIG_GEMM_MIN_PANEL")) : (1 << 30);
+  // Experiment (FW_FACTOR_L2_MB > 0, off by default): levels of thousands of small fronts processed in CHUNKS of fronts
+  // that fit the L2 cache, so that the ~17 kernels of a level find their fronts in L2 instead of streaming the level
+  // from HBM every time (the leaf level of config 2 is 5.2 GB).  Measured SLOWER: 127 -> 145 ms (96 MB chunks) .. 189 ms
+  // (16 MB): every kernel is bound by the dependent steps inside its CTAs (~30 us), a chunk of 255 fronts is one
+  // such wave per launch -- the level needs many independent CTAs in flight, not cache residency.
+  static const int64_t l2_budget =
+      (int64_t)(getenv("FW_FACTOR_L2_MB") ? atoi(getenv("FW_FACTOR_L2_MB")) : 0) << 20;
   for (int lev = Sy.n_levels - 1; lev >= 0; --lev) {
-    const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
-    const int* nodes = d.level_nodes.p + Sy.level_start[lev];
+    const int nfront_all = Sy.level_start[lev + 1] - Sy.level_start[lev];
+    const int* nodes_all = d.level_nodes.p + Sy.level_start[lev];
+    const int64_t front_bytes = (int64_t)Sy.level_max_m[lev] * Sy.level_max_m[lev] * (int64_t)sizeof(S);
+    int chunk = nfront_all;
+    if (l2_budget > 0 && front_bytes * nfront_all > 2 * l2_budget)
+      chunk = (int)std::max<int64_t>(148, l2_budget / std::max<int64_t>(1, front_bytes));
+    const bool chunked = chunk < nfront_all;
+   for (int c0 = 0; c0 < nfront_all; c0 += chunk) {
+    const int nfront = std::min(chunk, nfront_all - c0);
+    const int* nodes = nodes_all + c0;
     if (lev + 1 < Sy.n_levels) {
       const int cnb = Sy.level_max_nb[lev + 1];
       const int nt = (cnb + 31) / 32;
@@ -1278,7 +1293,7 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
       // two-level blocking: rank-32 updates stay inside the current outer block of OB panels; the rest of the front
       // gets one rank-(32 OB) update per outer block (the 128 x 128 tensor-core GEMM needs a deep inner dimension)
       const int ob = (max_ns >= blocked_min_ns) ? OB : 0;
-      if (nfront <= swap_gather_max_fronts)
+      if (nfront_all <= swap_gather_max_fronts)
         k_lu_swap_trsm<S, true><<<dim3(nfront, ctiles + rtiles), 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
       else
         k_lu_swap_trsm<S, false><<<dim3(nfront, ctiles + rtiles), 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
@@ -1308,8 +1323,9 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
         launches += 1;
       }
     }
-    if (trace2) tr.mark(("  factor lev " + std::to_string(lev) + " panels (" + std::to_string(npan) + " steps, " +
-                         std::to_string(nfront) + " fronts, max m " + std::to_string(max_m) + ")").c_str());
+    if (trace2 && !chunked)
+      tr.mark(("  factor lev " + std::to_string(lev) + " panels (" + std::to_string(npan) + " steps, " +
+               std::to_string(nfront) + " fronts, max m " + std::to_string(max_m) + ")").c_str());
     {
       const int nt = (Sy.level_max_nb[lev] + 63) / 64;
       if (nt > 0 && npan > 0) {
@@ -1320,7 +1336,11 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
         launches += 1;
       }
     }
-    if (trace2) tr.mark(("  factor lev " + std::to_string(lev) + " schur gemm").c_str());
+    if (trace2 && !chunked) tr.mark(("  factor lev " + std::to_string(lev) + " schur gemm").c_str());
+   }  // chunks
+    if (trace2 && chunked)
+      tr.mark(("  factor lev " + std::to_string(lev) + " panels + schur gemm in chunks of " + std::to_string(chunk) +
+               " of " + std::to_string(nfront_all) + " fronts").c_str());
   }
   tr.mark("lu factor: levels");
   k_lu_compose_perm<<<cdiv(Sy.n_nodes, 64), 64, 0, s>>>(T, Sy.n_nodes, d.piv.p, d.rowperm.p);
