@@ -65,6 +65,12 @@ void tinv_forward_level(Handle& h, LUDevice& d, const LUSymbolic& S, int lev, do
 template <int NRHS>
 void tinv_backward_level(Handle& h, LUDevice& d, const LUSymbolic& S, int lev, double* work, double* xp, int na);
 
+// fused partial factorisation of small fronts (lu_front_small.cu)
+bool lu_front_small_applies(int max_ns, int max_m);
+template <class S>
+void lu_front_small_launch(FrontTab T, const int* nodes, int nfront, S* F, int* piv, double thr, int* counters,
+                           cudaStream_t s);
+
 // large-front GEMM (lu_gemm.cu)
 template <class S>
 void lu_gemm_big_launch(FrontTab T, const int* nodes, int nfront, int kstep, S* F, int max_rem, bool schur,

@@ -1252,7 +1252,13 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
     }
     const int max_ns = Sy.level_max_ns[lev], max_m = Sy.level_max_m[lev];
     const int npan = (max_ns + PW - 1) / PW;
-    for (int k = 0; k < npan; ++k) {
+    // small fronts: one CTA walks through all steps of its front (lu_front_small.cu)
+    const bool fused_small = npan > 0 && lu_front_small_applies(max_ns, max_m);
+    if (fused_small) {
+      lu_front_small_launch<S>(T, nodes, nfront, F, d.piv.p, thr, d.counters.p, s);
+      launches += 1;
+    }
+    for (int k = 0; k < (fused_small ? 0 : npan); ++k) {
       if (max_ns - k * PW > HWIN) {
         bool done = false;
         {
@@ -1328,7 +1334,7 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
                std::to_string(nfront) + " fronts, max m " + std::to_string(max_m) + ")").c_str());
     {
       const int nt = (Sy.level_max_nb[lev] + 63) / 64;
-      if (nt > 0 && npan > 0) {
+      if (nt > 0 && npan > 0 && !fused_small) {
         if (Sy.level_max_nb[lev] >= big_gemm_min)
           lu_gemm_big_launch<S>(T, nodes, nfront, 0, F, Sy.level_max_nb[lev], true, s);
         else
