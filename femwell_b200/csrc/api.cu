@@ -218,9 +218,16 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
   sp.sc.assign(s->sc, s->sc + (size_t)nb * sp.nq);
   sp.X.assign(s->X, s->X + (size_t)2 * sp.nq);
   sp.W.assign(s->W, s->W + (size_t)sp.nq);
-  sp.h_p.assign(s->p, s->p + (size_t)2 * sp.nv);
-  sp.h_t.assign(s->t, s->t + (size_t)3 * sp.ne);
-  sp.h_edofs.assign(s->element_dofs, s->element_dofs + (size_t)nb * sp.ne);
+  // host copies of the mesh are only needed by the host version of the LU analysis (FW_HOST_ANALYSIS=1)
+  const bool keep_host = getenv("FW_HOST_ANALYSIS") != nullptr;
+  sp.h_p.clear(), sp.h_t.clear(), sp.h_edofs.clear();
+  if (keep_host) {
+    sp.h_p.assign(s->p, s->p + (size_t)2 * sp.nv);
+    sp.h_t.assign(s->t, s->t + (size_t)3 * sp.ne);
+    sp.h_edofs.assign(s->element_dofs, s->element_dofs + (size_t)nb * sp.ne);
+  }
+  const int32_t* in_t = s->t;
+  const int32_t* in_ed = s->element_dofs;
   // validate indices on the host (avoids device faults on bad input) and mark the Lagrange dofs; a few threads,
   // the connectivity has 14 x Ne entries
   std::vector<uint8_t> isz((size_t)sp.n, 0);
@@ -235,13 +242,13 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
         int b = 0;
         for (int a = 0; a < 3; ++a)
           for (int e = ea; e < eb; ++e) {
-            const int v = sp.h_t[(size_t)a * sp.ne + e];
+            const int v = in_t[(size_t)a * sp.ne + e];
             b |= (v < 0 || v >= sp.nv) ? 1 : 0;
           }
         for (int l = 0; l < nb; ++l) {
           const bool z = sp.kind[l] == 1;
           for (int e = ea; e < eb; ++e) {
-            const int d = sp.h_edofs[(size_t)l * sp.ne + e];
+            const int d = in_ed[(size_t)l * sp.ne + e];
             if (d < 0 || d >= sp.n)
               b |= 2;
             else if (z)
@@ -268,13 +275,13 @@ int fw_set_space(fw_handle* hh, const fw_space* s) {
     h.generic.valid = false;
     lu_analyse_prefetch(h, active, h.hint_leaf);
   }
-  sp.p.alloc(sp.h_p.size());
-  sp.t.alloc(sp.h_t.size());
-  sp.edofs.alloc(sp.h_edofs.size());
+  sp.p.alloc((size_t)2 * sp.nv);
+  sp.t.alloc((size_t)3 * sp.ne);
+  sp.edofs.alloc((size_t)nb * sp.ne);
   sp.is_z.alloc(isz.size());
-  upload_staged(h, sp.p.p, sp.h_p.data(), sp.h_p.size() * sizeof(double));
-  upload_staged(h, sp.t.p, sp.h_t.data(), sp.h_t.size() * sizeof(int));
-  upload_staged(h, sp.edofs.p, sp.h_edofs.data(), sp.h_edofs.size() * sizeof(int));
+  upload_staged(h, sp.p.p, s->p, (size_t)2 * sp.nv * sizeof(double));
+  upload_staged(h, sp.t.p, s->t, (size_t)3 * sp.ne * sizeof(int));
+  upload_staged(h, sp.edofs.p, s->element_dofs, (size_t)nb * sp.ne * sizeof(int));
   upload_staged(h, sp.is_z.p, isz.data(), isz.size());
   sp.h_is_z = isz;
   FW_CHECK_CUDA(cudaStreamSynchronize(h.stream));
