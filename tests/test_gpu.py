@@ -1179,3 +1179,43 @@ def test_smooth_start_vector_gives_the_same_modes_in_fewer_steps(ctx):
     a = compute_modes(b1, eps_c, 1.55, num_modes=1, order=1, solver_options={"start_vector": "uniform"})
     c = compute_modes(b1, eps_c, 1.55, num_modes=1, order=1)
     assert abs(a.n_effs[0] - c.n_effs[0]) < 1e-11 * abs(a.n_effs[0])
+
+
+def test_pattern_from_incidence_equals_full_sort_and_falls_back_on_high_valence(ctx, monkeypatch):
+    """The structural pattern of the FE space is built from the dof -> element incidence (one warp-level sort per row);
+    the full radix sort of all COO keys is the fallback for rows with more than 512 candidates.  Both must give the
+    same CSR pattern AND the same values bit for bit (same summation order), and a vertex of valence 40 (560
+    candidates at order 2) must take the fallback transparently."""
+    k0 = 2 * np.pi / 1.55
+    m, eps = strip_problem(18, jitter=0.15)
+    b = Basis(m, ElementTriP0(), intorder=4).with_element(mode_element(2))
+    mats = []
+    for full in (False, True):
+        with monkeypatch.context() as mp:
+            if full:
+                mp.setenv("FW_SYMBOLIC_FULL_SORT", "1")
+            ctx.set_space(b)
+            ctx.symbolic()
+            ctx.assemble(0, eps, k0)
+            mats.append((ctx.matrix(0, eliminate_zeros=False), ctx.matrix(1, eliminate_zeros=False)))
+    for (a, c) in zip(mats[0], mats[1]):
+        assert np.array_equal(a.indptr, c.indptr) and np.array_equal(a.indices, c.indices)
+        assert np.array_equal(a.data, c.data)
+    # a fan of 40 triangles around one vertex
+    nfan = 40
+    ang = np.linspace(0, 2 * np.pi, nfan, endpoint=False)
+    p = np.concatenate([[[0.0], [0.0]], np.stack([np.cos(ang), np.sin(ang)]) * (1 + 0.1 * np.cos(3 * ang))], axis=1)
+    t = np.stack([np.zeros(nfan, dtype=int), 1 + np.arange(nfan), 1 + (np.arange(nfan) + 1) % nfan])
+    fan = MeshTri(p, t)
+    bf = Basis(fan, ElementTriP0(), intorder=4).with_element(mode_element(2))
+    epsf = np.linspace(1.0, 2.0, nfan)
+    ctx.set_space(bf)
+    ctx.symbolic()
+    ctx.assemble(0, epsf, k0)
+    A, B = ctx.matrix(0), ctx.matrix(1)
+    Ar, Br = _oracle_AB(fan, bf, 0, epsf, k0)
+    for M, R in ((A, Ar), (B, Br)):
+        d, _ = csr_rel_diff(M, R)
+        assert d < 1e-12
+        ok, _n = _pattern_diff_is_roundoff(M, R)
+        assert ok
