@@ -744,7 +744,8 @@ bool eigs_shift_invert(Handle& h, const fw_eigs_params& prm, cd* lams, DevBuf<do
   bool converged = true;
   {
     Timer t(s, "fw:Arnoldi (shift-invert)");
-    for (int attempt = 0; attempt < 3; ++attempt) {
+    int refine_retries = 0;
+    for (int attempt = 0; attempt < 4 && refine_retries < 3; ++attempt) {
       tmp = fw_eigs_stats{};
       if (!cplx_arith)
         eigs_typed<double, double>(h, prm, refine, active, sigma, lams, X_dev, &tmp);
@@ -764,7 +765,14 @@ bool eigs_shift_invert(Handle& h, const fw_eigs_params& prm, cd* lams, DevBuf<do
         break;
       }
       if (prm.refine != 0 || tmp.max_residual <= RESID_RETRY) break;
-      refine = attempt + 1;
+      if (attempt == 0 && h.lu && !h.lu->no_tinv && !cplx_arith) {
+        // first retry: same solver without the inverse pivot blocks (lu_tinv.cu) -- substitution chains are backward
+        // stable where an explicit inverse of an ill-conditioned pivot block is not
+        h.lu->no_tinv = true;
+        h.lu->drop_graphs();
+        continue;
+      }
+      refine = ++refine_retries;
     }
     double ms = t.stop();
     h.tim.arnoldi_ms = ms;

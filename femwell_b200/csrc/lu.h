@@ -73,6 +73,9 @@ struct LU {
     graphs.clear();
   }
   int perturbed = 0;
+  // set by the eigen-solver when its residual check failed: the substitutions fall back from the inverse pivot blocks of
+  // the upper levels to substitution chains (backward stable) for the retry; cleared by the next factorisation
+  bool no_tinv = false;
   std::vector<uint8_t> active_key;  // the analysis is reusable while mesh, Dirichlet set and leaf size stay
   int leaf_key = 0;
   std::unique_ptr<LUDevice> dev;

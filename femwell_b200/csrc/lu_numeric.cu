@@ -1165,6 +1165,7 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
   cudaStream_t s = h.stream;
   const size_t wsc = sizeof(S) / sizeof(double);
   lu.drop_graphs();  // captured solves refer to the previous factorisation (scalar type, buffers)
+  lu.no_tinv = false;
   Trace tr(s);
   d.factors.alloc((size_t)std::max<int64_t>(1, Sy.factor_entries) * wsc);
   tr.mark("lu factor: alloc");

@@ -1037,7 +1037,7 @@ static void solve_typed(Handle& h, const S* b, S* x) {
   const bool trace2 = tenv && atoi(tenv) >= 2;
   const bool no_cluster = getenv("FW_NO_CLUSTER") != nullptr;
   const bool no_inv = getenv("FW_NO_DINV") != nullptr;
-  const bool no_tinv = getenv("FW_NO_TINV_SOLVE") != nullptr;
+  const bool no_tinv = getenv("FW_NO_TINV_SOLVE") != nullptr || lu.no_tinv;
   // levels of many small fronts: chain and off-diagonal update in one kernel (FW_FUSE_MAX_M=0 disables)
   static const int fuse_max_m = getenv("FW_FUSE_MAX_M") ? atoi(getenv("FW_FUSE_MAX_M")) : 512;
   // forward fused kernel: two rows per thread (blockDim = m / 2) doubles the fronts in flight per SM -- the kernel is

@@ -22,6 +22,7 @@ namespace fw {
 // levels of the tree -- the pivot blocks of the leaf fronts (interior dofs of a few elements of the shifted, indefinite
 // pencil) are too ill conditioned for explicit inverses: with them the solve residual rose from 9e-13 to 5e-10.
 bool tinv_level_static(const LUSymbolic& S, int min_ns, int lev) {
+  if (getenv("FW_TINV_ALL_LEVELS")) return S.level_max_ns[lev] >= min_ns;  // tests: exercise the accuracy fallback
   return S.level_max_ns[lev] >= min_ns && lev < S.n_levels - 3;
 }
 bool tinv_level(const LUSymbolic& S, const LUDevice& d, int lev) {

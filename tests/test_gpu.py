@@ -1219,3 +1219,23 @@ def test_pattern_from_incidence_equals_full_sort_and_falls_back_on_high_valence(
         assert d < 1e-12
         ok, _n = _pattern_diff_is_roundoff(M, R)
         assert ok
+
+
+def test_inverse_pivot_blocks_fall_back_to_substitution_when_the_residual_check_fails(ctx, monkeypatch):
+    """Selective inversion (lu_tinv.cu) keeps the leaf levels out because their pivot blocks are ill conditioned.  With
+    every level forced in, the eigen-solver's residual check must still deliver modes to 1e-9: either the inverses were
+    accurate enough on this mesh, or the first retry switches the substitutions back to chains."""
+    from femwell_b200.maxwell.waveguide import compute_modes, get_context
+
+    m, eps = strip_problem(60, slab_h=0.11)
+    b0 = Basis(m, ElementTriP0(), intorder=4)
+    ref = compute_modes(b0, eps, 1.55, num_modes=3, order=2)
+    with monkeypatch.context() as mp:
+        mp.setenv("FW_TINV_ALL_LEVELS", "1")
+        mp.setenv("FW_TINV_MIN_NS", "1")
+        get_context()._space_key = None  # new analysis: the level selection is made there
+        forced = compute_modes(b0, eps, 1.55, num_modes=3, order=2)
+    get_context()._space_key = None
+    assert np.abs(forced.n_effs - ref.n_effs).max() < 1e-9 * np.abs(ref.n_effs).max()
+    assert forced.stats["max_residual"] <= 1e-10 and ref.stats["max_residual"] <= 1e-10
+    print("operator applications: default", ref.stats["n_op"], "forced", forced.stats["n_op"])
