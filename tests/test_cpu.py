@@ -643,3 +643,26 @@ def test_coupled_waveguide_mesh_groups():
     assert sum(v.size for v in m.subdomains.values()) == m.nelements == 3200
     c = m.centroids()
     assert c[0, m.subdomains["core_1"]].max() < -0.15 and c[0, m.subdomains["core_2"]].min() > 0.15
+
+
+# ----------------------------------------------------------------------------- bench.py host logic (CPU ladder)
+def test_bench_ladder_extrapolation_is_anchored_and_never_sublinear():
+    """The CPU reference arm measures a ladder of small meshes and extrapolates the largest sample by the fitted power
+    law: exact on a pure power law, never below linear scaling, anchored at the largest sample."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ne = [2592, 5000, 10082, 20000]
+    t = [3e-4 * n**1.4 for n in ne]
+    p, c = bench.fit_power_law(ne, t)
+    assert abs(p - 1.4) < 1e-9 and abs(c - 3e-4) < 1e-9
+    t_full, p2, t_lin = bench.extrapolate_ladder(list(zip(ne, t)), 500000)
+    assert abs(p2 - 1.4) < 1e-9 and abs(t_full - 3e-4 * 500000**1.4) < 1e-6 * t_full
+    assert abs(t_lin - t[-1] * 500000 / ne[-1]) < 1e-9 * t_lin and t_full > t_lin
+    # a sub-linear fit (noise on tiny samples) is clamped to linear scaling of the largest sample
+    t_full, p3, t_lin = bench.extrapolate_ladder([(1000, 1.0), (2000, 1.5)], 100000)
+    assert p3 < 1 and abs(t_full - t_lin) < 1e-12 * t_lin
+    assert "500000 triangles" in bench.workload_text(500, 4)
+    assert bench.algorithmic_bytes_element_kernel(10, 8, 14, 8, 8, 8) == 10 * 20 + 8 * 16 + 10 * (196 + 64) * 8
