@@ -181,11 +181,11 @@ static void lu_analyse_finish(Handle& h) {
   d.rowperm.alloc((size_t)std::max(1, S.n_active));
   d.counters.alloc(4);
   {
-    // storage for the inverted diagonal blocks of the fronts on cluster levels
+    // storage for the inverted diagonal blocks of all fronts (cluster chains of the tall fronts, DINV chains of the
+    // small ones; lu_solve.cu)
     std::vector<int64_t> doff((size_t)std::max(1, S.n_nodes), -1);
     int64_t tot = 0;
     for (int lev = 0; lev < S.n_levels; ++lev) {
-      if (S.level_max_ns[lev] <= CL_MIN_NS) continue;
       for (int q = S.level_start[lev]; q < S.level_start[lev + 1]; ++q) {
         const int node = S.level_nodes[q];
         const int npan = (S.ns[node] + PW - 1) / PW;
@@ -1357,9 +1357,9 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
   if (d.dinv_entries > 0 && !scalar_traits<S>::is_complex) {
     d.dinv.alloc((size_t)d.dinv_entries * wsc);
     for (int lev = 0; lev < Sy.n_levels; ++lev) {
-      if (Sy.level_max_ns[lev] <= CL_MIN_NS) continue;
       const int nfront = Sy.level_start[lev + 1] - Sy.level_start[lev];
       const int npan = (Sy.level_max_ns[lev] + PW - 1) / PW;
+      if (npan == 0) continue;
       k_lu_diag_inverse<S><<<dim3(nfront, npan), 32, 0, s>>>(T, d.level_nodes.p + Sy.level_start[lev], F, (S*)d.dinv.p);
       ++launches;
     }

@@ -112,6 +112,36 @@ struct SyncCluster {
   __device__ static void sync() { cg::this_cluster().sync(); }
 };
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// ---- DINV chains (real arithmetic, blocks of up to 128 threads): the 32 x 32 diagonal blocks come pre-inverted from
+// LUDevice::dinv (k_lu_diag_inverse, all fronts), so the 32 dependent shuffle/FMA steps of a diagonal solve become one
+// 32 x 32 matrix-vector product, and the block itself is copied with cp.async into one of two shared-memory buffers
+// one panel ahead (ncu on the leaf level of config 2: 30 % of the backward kernel sat in the eight serialised
+// load + divide iterations per thread that filled D, another 35 % at the barriers around the serial solve).
+__device__ __forceinline__ void dinv_fetch(double* buf, const double* __restrict__ src, int t, int nthr) {
+  for (int c = t; c < PW * PW / 2; c += nthr) cp_async16(buf + 2 * c, src + 2 * c);
+}
+// x = inv(D_kk) w_k by warp r (right-hand side r); Dv is column-major, ragged blocks are padded with the identity
+template <int NRHS>
+__device__ __forceinline__ void dinv_apply(const double* Dv, const double* wk, int wd, int t, double (*xs)[PW]) {
+  const int r = t >> 5, lane = t & 31;
+  const double wv = lane < wd ? wk[lane] : 0.0;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+  for (int j = 0; j < PW; j += 4) {
+    a0 = fma(Dv[(j + 0) * PW + lane], __shfl_sync(0xffffffffu, wv, j + 0), a0);
+    a1 = fma(Dv[(j + 1) * PW + lane], __shfl_sync(0xffffffffu, wv, j + 1), a1);
+    a2 = fma(Dv[(j + 2) * PW + lane], __shfl_sync(0xffffffffu, wv, j + 2), a2);
+    a3 = fma(Dv[(j + 3) * PW + lane], __shfl_sync(0xffffffffu, wv, j + 3), a3);
+  }
+  if (lane < wd) xs[r][lane] = (a0 + a1) + (a2 + a3);
+}
+
 // prefetch / commit of a 32x32 diagonal block (column-major panel of the front) through registers
 template <class S>
 __device__ __forceinline__ void diag_fetch(S (&dn)[DPT], const S* __restrict__ Fn, int m, int k0, int wd, int t,
@@ -142,11 +172,12 @@ __device__ __forceinline__ void diag_commit(S (*D)[PW + 1], const S (&dn)[DPT], 
 // ------------------------------------------------------------------------------ forward chain
 // FUSE: the CTA also updates the boundary rows (w2 -= L21 x1) panel by panel, so the level needs no k_fwd_update
 // launch (levels of many small fronts: one contiguous pass over the L panel, no second kernel, no tail).
-template <class S, int NRHS, class SY, bool FUSE = false>
+template <class S, int NRHS, class SY, bool FUSE = false, bool DINV = false>
 __device__ __forceinline__ void fwd_chain_body(FrontTab T, const int node, const S* __restrict__ F,
                                                const int* __restrict__ rowperm, S* work, int64_t work_stride, S* xp,
-                                               int na) {
-  __shared__ S D[PW][PW + 1];
+                                               int na, const double* __restrict__ dinv = nullptr) {
+  __shared__ S D[DINV ? 1 : PW][PW + 1];
+  __shared__ __align__(16) double Dv[DINV ? 2 : 1][DINV ? PW * PW : 2];
   __shared__ S xs[NRHS][PW];
   const int m = T.m[node], ns = T.ns[node], os = T.own_start[node];
   const S* Fn = F + T.front_off[node];
@@ -166,7 +197,12 @@ __device__ __forceinline__ void fwd_chain_body(FrontTab T, const int node, const
       prefetch_l2_bulk((const char*)Fn + o, min(chunk, bytes - o));
   }
   // register prefetch for real arithmetic and block sizes >= 256 (32 c128 values would not fit the budget)
-  const bool pipelined = SY::pipe && !scalar_traits<S>::is_complex && nthr * DPT >= PW * PW;
+  const bool pipelined = !DINV && SY::pipe && !scalar_traits<S>::is_complex && nthr * DPT >= PW * PW;
+  const double* dv = nullptr;
+  if constexpr (DINV) {
+    dv = dinv + T.dinv_off[node];
+    if (ns > 0) dinv_fetch(Dv[0], dv, t, nthr);  // independent of the right-hand side: in flight during the assembly
+  }
   // the first diagonal block and this thread's first row segment do not depend on the rhs: fetch them now
   S dn[DPT], ln[PW];
   const int row0 = gt;  // the fixed row of the pivot block owned by this thread (further rows: gt + c*nth)
@@ -211,7 +247,9 @@ __device__ __forceinline__ void fwd_chain_body(FrontTab T, const int node, const
   const int rlim = FUSE ? m : ns;  // rows folded by this kernel
   for (int k0 = 0; k0 < ns; k0 += PW) {
     const int wd = min(PW, ns - k0);
-    if (pipelined) {
+    if constexpr (DINV) {
+      cp_async_wait_all();
+    } else if (pipelined) {
       diag_commit<S, false>(D, dn, wd, t, nthr);
     } else {
       for (int idx = t; idx < wd * wd; idx += nthr) {
@@ -223,7 +261,11 @@ __device__ __forceinline__ void fwd_chain_body(FrontTab T, const int node, const
     // prefetch the next diagonal block while warp 0 runs the serial 32-step solve
     const int k1 = k0 + PW;
     if (pipelined && k1 < ns) diag_fetch<S>(dn, Fn, m, k1, min(PW, ns - k1), t, nthr);
-    if (t < 32 * NRHS) {  // replicated in every CTA of a cluster; rank 0 stores the result
+    if constexpr (DINV) {
+      const int kp = k0 / PW;
+      if (k1 < ns) dinv_fetch(Dv[(kp + 1) & 1], dv + (long long)(kp + 1) * PW * PW, t, nthr);
+      if (t < 32 * NRHS) dinv_apply<NRHS>(Dv[kp & 1], work + (size_t)(t >> 5) * work_stride + T.work_off[node] + k0, wd, t, xs);
+    } else if (t < 32 * NRHS) {  // replicated in every CTA of a cluster; rank 0 stores the result
       const int r = t >> 5, lane = t & 31;
       S x = lane < wd ? w[r][k0 + lane] : scalar_traits<S>::zero();
       for (int j = 0; j < wd; ++j) {
@@ -296,6 +338,16 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_fwd_chain_fused(FrontTab 
                                                                        int64_t work_stride, S* xp, int na) {
   fwd_chain_body<S, NRHS, SyncCta, true>(T, nodes[blockIdx.x], F, rowperm, work, work_stride, xp, na);
 }
+// DINV variants (f64, <= DINV_MAX_THREADS threads): see dinv_fetch / dinv_apply
+constexpr int DINV_MAX_THREADS = 128;
+template <int NRHS, bool FUSE>
+__global__ void __launch_bounds__(DINV_MAX_THREADS) k_fwd_chain_dinv(FrontTab T, const int* __restrict__ nodes,
+                                                                     const double* __restrict__ F,
+                                                                     const double* __restrict__ dinv,
+                                                                     const int* __restrict__ rowperm, double* work,
+                                                                     int64_t work_stride, double* xp, int na) {
+  fwd_chain_body<double, NRHS, SyncCta, FUSE, true>(T, nodes[blockIdx.x], F, rowperm, work, work_stride, xp, na, dinv);
+}
 template <class S, int NRHS>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
     k_fwd_chain_cluster(FrontTab T, const int* __restrict__ nodes, const S* __restrict__ F,
@@ -308,10 +360,12 @@ constexpr int FUSE_CHUNK = 128;  // boundary columns staged per step of the fuse
 
 // FUSE: the CTA first gathers x2 from the parent and folds it into the own rows (w1 -= U12 x2), so the level needs
 // no k_bwd_update launch.
-template <class S, int NRHS, class SY, bool FUSE = false>
+template <class S, int NRHS, class SY, bool FUSE = false, bool DINV = false>
 __device__ __forceinline__ void bwd_chain_body(FrontTab T, const int node, const S* __restrict__ F,
-                                               S* work, int64_t work_stride, S* xp, int na) {
-  __shared__ S D[PW][PW + 1];
+                                               S* work, int64_t work_stride, S* xp, int na,
+                                               const double* __restrict__ dinv = nullptr) {
+  __shared__ S D[DINV ? 1 : PW][PW + 1];
+  __shared__ __align__(16) double Dv[DINV ? 2 : 1][DINV ? PW * PW : 2];
   __shared__ S xs[NRHS][PW];
   __shared__ S x2[FUSE ? NRHS : 1][FUSE ? FUSE_CHUNK : 1];
   const int m = T.m[node], ns = T.ns[node], os = T.own_start[node];
@@ -329,6 +383,11 @@ __device__ __forceinline__ void bwd_chain_body(FrontTab T, const int node, const
       const int rows = c < m - ns ? ns : col + 1;
       prefetch_l2_bulk(Fn + (long long)col * m, (long long)rows * (long long)sizeof(S));
     }
+  }
+  if constexpr (DINV) {
+    // the first inv(U_kk) block does not depend on the right-hand side: in flight during the U12 pass
+    const int np = (ns + PW - 1) / PW;
+    if (np > 0) dinv_fetch(Dv[(np - 1) & 1], dinv + T.dinv_off[node] + (long long)(2 * np - 1) * PW * PW, t, nthr);
   }
   if constexpr (FUSE) if (m > ns) {
     const int p = T.parent[node];
@@ -361,18 +420,22 @@ __device__ __forceinline__ void bwd_chain_body(FrontTab T, const int node, const
   const int nth = nthr * SY::nctas();
   const int gt = SY::rank() * nthr + t;
   const int npan = (ns + PW - 1) / PW;
-  const bool pipelined = SY::pipe && !scalar_traits<S>::is_complex && nthr * DPT >= PW * PW;
+  const bool pipelined = !DINV && SY::pipe && !scalar_traits<S>::is_complex && nthr * DPT >= PW * PW;
   const int row0 = gt;
   S dn[DPT], un[PW];
   {
     const int k0 = (npan - 1) * PW;
     if (pipelined) diag_fetch<S>(dn, Fn, m, k0, min(PW, ns - k0), t, nthr);
   }
+  const double* dv = nullptr;  // inv(U_kk) blocks follow the npan inv(L_kk) blocks
+  if constexpr (DINV) dv = dinv + T.dinv_off[node] + (long long)npan * PW * PW;
   bool un_valid = false;  // un holds U[row0, panel kp] for the panel about to be processed
   for (int kp = npan - 1; kp >= 0; --kp) {
     const int k0 = kp * PW;
     const int wd = min(PW, ns - k0);
-    if (pipelined) {
+    if constexpr (DINV) {
+      cp_async_wait_all();
+    } else if (pipelined) {
       diag_commit<S, true>(D, dn, wd, t, nthr);
     } else {
       for (int idx = t; idx < wd * wd; idx += nthr) {
@@ -383,7 +446,10 @@ __device__ __forceinline__ void bwd_chain_body(FrontTab T, const int node, const
     }
     __syncthreads();
     if (pipelined && kp > 0) diag_fetch<S>(dn, Fn, m, k0 - PW, PW, t, nthr);
-    if (t < 32 * NRHS) {
+    if constexpr (DINV) {
+      if (kp > 0) dinv_fetch(Dv[(kp - 1) & 1], dv + (long long)(kp - 1) * PW * PW, t, nthr);
+      if (t < 32 * NRHS) dinv_apply<NRHS>(Dv[kp & 1], work + (size_t)(t >> 5) * work_stride + T.work_off[node] + k0, wd, t, xs);
+    } else if (t < 32 * NRHS) {
       const int r = t >> 5, lane = t & 31;
       S y = lane < wd ? w[r][k0 + lane] : scalar_traits<S>::zero();
       for (int j = wd - 1; j >= 0; --j) {
@@ -450,6 +516,13 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_bwd_chain_fused(FrontTab 
                                                                        int64_t work_stride, S* xp, int na) {
   bwd_chain_body<S, NRHS, SyncCta, true>(T, nodes[blockIdx.x], F, work, work_stride, xp, na);
 }
+template <int NRHS, bool FUSE>
+__global__ void __launch_bounds__(DINV_MAX_THREADS) k_bwd_chain_dinv(FrontTab T, const int* __restrict__ nodes,
+                                                                     const double* __restrict__ F,
+                                                                     const double* __restrict__ dinv, double* work,
+                                                                     int64_t work_stride, double* xp, int na) {
+  bwd_chain_body<double, NRHS, SyncCta, FUSE, true>(T, nodes[blockIdx.x], F, work, work_stride, xp, na, dinv);
+}
 template <class S, int NRHS>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
     k_bwd_chain_cluster(FrontTab T, const int* __restrict__ nodes, const S* __restrict__ F, S* work,
@@ -470,11 +543,6 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CL_THREADS)
 // No global-memory access sits on the dependent path any more (the first version re-read w from L2 and ran a
 // 32-step shuffle substitution per panel: 4.8 us per step; see DESIGN.md for the measured effect).
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 template <int NRHS>
 __device__ __forceinline__ void inv_block_matvec(const double* __restrict__ Dw, int lane, double (&acc)[NRHS]) {
@@ -1047,6 +1115,11 @@ static void solve_typed(Handle& h, const S* b, S* x) {
     return !scalar_traits<S>::is_complex && d.dinv_valid && !no_cluster && !no_inv && max_ns > CL_MIN_NS &&
            max_ns <= CL * CL_THREADS;
   };
+  // small fronts in real arithmetic: pre-inverted diagonal blocks + cp.async double buffer (FW_NO_DINV_CHAIN=1 disables)
+  const bool no_dinv_chain = getenv("FW_NO_DINV_CHAIN") != nullptr || lu.no_tinv;
+  auto use_dinv = [&](int threads) {
+    return !scalar_traits<S>::is_complex && d.dinv_valid && !no_dinv_chain && threads <= DINV_MAX_THREADS;
+  };
   // ---- dataflow bands over the lower levels (see k_tree_band): A = small fronts (128 threads), B = the rest
   // (the knobs are read per call so that the tests can switch the path; a captured graph keeps its own choice)
   const bool no_tree = !(getenv("FW_TREE") && atoi(getenv("FW_TREE")) > 0);  // measured slower than the levels: opt-in
@@ -1106,10 +1179,17 @@ static void solve_typed(Handle& h, const S* b, S* x) {
       if constexpr (!scalar_traits<S>::is_complex) {
         tinv_forward_level<NRHS>(h, d, Sy, lev, work, xp, na);
       }
-    } else if (fuse)
-      k_fwd_chain_fused<S, NRHS><<<nfront, chain_threads(Sy.level_max_m[lev] / fuse_tdiv), 0, s>>>(T, nodes, F, d.rowperm.p, work,
-                                                                                    Sy.work_entries, xp, na);
-    else if (use_inv(max_ns))
+    } else if (fuse) {
+      const int threads = chain_threads(Sy.level_max_m[lev] / fuse_tdiv);
+      if (use_dinv(threads)) {
+        if constexpr (!scalar_traits<S>::is_complex)
+          k_fwd_chain_dinv<NRHS, true><<<nfront, threads, 0, s>>>(T, nodes, F, d.dinv.p, d.rowperm.p, work, Sy.work_entries, xp, na);
+      } else
+        k_fwd_chain_fused<S, NRHS><<<nfront, threads, 0, s>>>(T, nodes, F, d.rowperm.p, work, Sy.work_entries, xp, na);
+    } else if (use_dinv(chain_threads(max_ns)) && !use_inv(max_ns) && !(max_ns > CL_MIN_NS && !no_cluster)) {
+      if constexpr (!scalar_traits<S>::is_complex)
+        k_fwd_chain_dinv<NRHS, false><<<nfront, chain_threads(max_ns), 0, s>>>(T, nodes, F, d.dinv.p, d.rowperm.p, work, Sy.work_entries, xp, na);
+    } else if (use_inv(max_ns))
       launch_inv_chain<S, NRHS>(true, nfront, max_ns, T, nodes, F, d, work, Sy.work_entries, xp, na, s);
     else if (max_ns > CL_MIN_NS && !no_cluster)
       k_fwd_chain_cluster<S, NRHS><<<nfront * CL, CL_THREADS, 0, s>>>(T, nodes, F, d.rowperm.p, work,
@@ -1167,10 +1247,17 @@ static void solve_typed(Handle& h, const S* b, S* x) {
       if constexpr (!scalar_traits<S>::is_complex) {
         tinv_backward_level<NRHS>(h, d, Sy, lev, work, xp, na);
       }
-    } else if (fuse)
-      k_bwd_chain_fused<S, NRHS><<<nfront, chain_threads(std::max(max_ns, 64)), 0, s>>>(T, nodes, F, work, Sy.work_entries,
-                                                                                     xp, na);
-    else if (use_inv(max_ns))
+    } else if (fuse) {
+      const int threads = chain_threads(std::max(max_ns, 64));
+      if (use_dinv(threads)) {
+        if constexpr (!scalar_traits<S>::is_complex)
+          k_bwd_chain_dinv<NRHS, true><<<nfront, threads, 0, s>>>(T, nodes, F, d.dinv.p, work, Sy.work_entries, xp, na);
+      } else
+        k_bwd_chain_fused<S, NRHS><<<nfront, threads, 0, s>>>(T, nodes, F, work, Sy.work_entries, xp, na);
+    } else if (use_dinv(chain_threads(max_ns)) && !use_inv(max_ns) && !(max_ns > CL_MIN_NS && !no_cluster)) {
+      if constexpr (!scalar_traits<S>::is_complex)
+        k_bwd_chain_dinv<NRHS, false><<<nfront, chain_threads(max_ns), 0, s>>>(T, nodes, F, d.dinv.p, work, Sy.work_entries, xp, na);
+    } else if (use_inv(max_ns))
       launch_inv_chain<S, NRHS>(false, nfront, max_ns, T, nodes, F, d, work, Sy.work_entries, xp, na, s);
     else if (max_ns > CL_MIN_NS && !no_cluster)
       k_bwd_chain_cluster<S, NRHS><<<nfront * CL, CL_THREADS, 0, s>>>(T, nodes, F, work, Sy.work_entries, xp, na);
