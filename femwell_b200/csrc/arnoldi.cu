@@ -30,7 +30,7 @@ __device__ inline cplx shfl_xor_(cplx v, int o) {
 }
 
 template <class V, class S>
-__global__ void __launch_bounds__(256) k_op_apply(int n, const int* __restrict__ indptr,
+__global__ void __launch_bounds__(256, 4) k_op_apply(int n, const int* __restrict__ indptr,
                                                   const int* __restrict__ indices, const V* __restrict__ A,
                                                   const V* __restrict__ B, S alphaA, S alphaB, bool useA,
                                                   const uint8_t* __restrict__ active, const S* __restrict__ x,
@@ -68,17 +68,34 @@ static void op_apply_impl(Handle& h, const uint8_t* active, S alphaA, S alphaB, 
 }
 
 // y = alpha * Bc x on the compact copy of B (rows/columns of inactive dofs masked; active == nullptr: none)
+// (explicit occupancy hints and batches of independent loads: see the note on upd_min_blocks in lu_solve.cu)
 template <class V, class S, int TPR>
-__global__ void __launch_bounds__(256) k_spmv_bc(int n, const int* __restrict__ indptr, const int* __restrict__ indices,
-                                                 const V* __restrict__ B, S alpha, const uint8_t* __restrict__ active,
-                                                 const S* __restrict__ x, S* __restrict__ y) {
+__global__ void __launch_bounds__(256, 4) k_spmv_bc(int n, const int* __restrict__ indptr,
+                                                    const int* __restrict__ indices, const V* __restrict__ B, S alpha,
+                                                    const uint8_t* __restrict__ active, const S* __restrict__ x,
+                                                    S* __restrict__ y) {
   const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int row = (int)(gt / TPR), l = (int)(gt % TPR);
   S acc = scalar_traits<S>::zero();
   const bool live = row < n && (!active || active[row]);
   if (live) {
     const int a = indptr[row], b = indptr[row + 1];
-    for (int k = a + l; k < b; k += TPR) {
+    int k = a + l;
+    for (; k + 3 * TPR < b; k += 4 * TPR) {  // four entries per pass: indices and values first, then the gathers
+      int c[4];
+      V bv[4];
+      S xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        c[u] = indices[k + u * TPR];
+        bv[u] = B[k + u * TPR];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xv[u] = (active && !active[c[u]]) ? scalar_traits<S>::zero() : x[c[u]];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) fma_(acc, cvt_<V, S>(bv[u]), xv[u]);
+    }
+    for (; k < b; k += TPR) {
       const int c = indices[k];
       if (active && !active[c]) continue;
       fma_(acc, cvt_<V, S>(B[k]), x[c]);
@@ -92,18 +109,41 @@ __global__ void __launch_bounds__(256) k_spmv_bc(int n, const int* __restrict__ 
 // ------------------------------------------------------------------------------ CGS2 kernels
 // partial[b*nvec + i] = sum over the rows of block b of conj(V[i][r]) * w[r]
 template <class T>
-__global__ void __launch_bounds__(256) k_multidot(const T* __restrict__ V, int nvec, int64_t ld,
-                                                  const T* __restrict__ w, int n, T* __restrict__ partial) {
+__global__ void __launch_bounds__(256, 4) k_multidot(const T* __restrict__ V, int nvec, int64_t ld,
+                                                     const T* __restrict__ w, int n, T* __restrict__ partial) {
   __shared__ T part[8][MAXV];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int64_t base = (int64_t)blockIdx.x * 1024;
   T wr[4];
+  bool ok[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     int64_t r = base + k * 256 + t;
-    wr[k] = r < n ? w[r] : scalar_traits<T>::zero();
+    ok[k] = r < n;
+    wr[k] = ok[k] ? w[r] : scalar_traits<T>::zero();
   }
-  for (int i = 0; i < nvec; ++i) {
+  // IB basis vectors per pass: 4 * IB independent loads in flight, then the warp reductions
+  constexpr int IB = scalar_traits<T>::is_complex ? 2 : 4;
+  int i = 0;
+  for (; i + IB <= nvec; i += IB) {
+    T v[IB][4];
+#pragma unroll
+    for (int q = 0; q < IB; ++q)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        v[q][k] = ok[k] ? V[(int64_t)(i + q) * ld + base + k * 256 + t] : scalar_traits<T>::zero();
+#pragma unroll
+    for (int q = 0; q < IB; ++q) {
+      T s = scalar_traits<T>::zero();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ok[k]) fma_(s, conj_(v[q][k]), wr[k]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s = s + shfl_xor_(s, o);
+      if (lane == 0) part[warp][i + q] = s;
+    }
+  }
+  for (; i < nvec; ++i) {
     const T* vi = V + (int64_t)i * ld;
     T s = scalar_traits<T>::zero();
 #pragma unroll
@@ -116,11 +156,11 @@ __global__ void __launch_bounds__(256) k_multidot(const T* __restrict__ V, int n
     if (lane == 0) part[warp][i] = s;
   }
   __syncthreads();
-  for (int i = t; i < nvec; i += 256) {
-    T s = part[0][i];
+  for (int i2 = t; i2 < nvec; i2 += 256) {
+    T s = part[0][i2];
 #pragma unroll
-    for (int q = 1; q < 8; ++q) s = s + part[q][i];
-    partial[(int64_t)blockIdx.x * nvec + i] = s;
+    for (int q = 1; q < 8; ++q) s = s + part[q][i2];
+    partial[(int64_t)blockIdx.x * nvec + i2] = s;
   }
 }
 
@@ -143,8 +183,9 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const T* __restrict__ p
 
 // w[r] -= sum_i V[i][r] * hc[i] ; optionally accumulates |w|^2 per block into nrm_partial
 template <class T>
-__global__ void __launch_bounds__(256) k_multiaxpy(T* __restrict__ w, const T* __restrict__ V, int nvec, int64_t ld,
-                                                   int n, const T* __restrict__ hc, double* __restrict__ nrm_partial) {
+__global__ void __launch_bounds__(256, 4) k_multiaxpy(T* __restrict__ w, const T* __restrict__ V, int nvec, int64_t ld,
+                                                      int n, const T* __restrict__ hc,
+                                                      double* __restrict__ nrm_partial) {
   __shared__ T sh[MAXV];
   __shared__ double red[8];
   const int t = threadIdx.x;
@@ -152,25 +193,49 @@ __global__ void __launch_bounds__(256) k_multiaxpy(T* __restrict__ w, const T* _
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * 1024;
   double nrm = 0.0;
+  // the four rows of this thread advance together, IB basis vectors per pass: 4 * IB independent loads in flight
+  // (row after row with a run-time loop over the vectors kept ONE load in flight); same summation order per row
+  constexpr int IB = scalar_traits<T>::is_complex ? 2 : 4;
+  T acc[4];
+  bool ok[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    int64_t r = base + k * 256 + t;
-    if (r < n) {
-      T acc = w[r];
-      for (int i = 0; i < nvec; ++i) fnma_(acc, V[(int64_t)i * ld + r], sh[i]);
-      w[r] = acc;
-      nrm += abs2_(acc);
-    }
+    const int64_t r = base + k * 256 + t;
+    ok[k] = r < n;
+    acc[k] = ok[k] ? w[r] : scalar_traits<T>::zero();
   }
+  int i = 0;
+  for (; i + IB <= nvec; i += IB) {
+    T v[IB][4];
+#pragma unroll
+    for (int q = 0; q < IB; ++q)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        v[q][k] = ok[k] ? V[(int64_t)(i + q) * ld + base + k * 256 + t] : scalar_traits<T>::zero();
+#pragma unroll
+    for (int q = 0; q < IB; ++q)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) fnma_(acc[k], v[q][k], sh[i + q]);
+  }
+  for (; i < nvec; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (ok[k]) fnma_(acc[k], V[(int64_t)i * ld + base + k * 256 + t], sh[i]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (ok[k]) {
+      w[base + k * 256 + t] = acc[k];
+      nrm += abs2_(acc[k]);
+    }
   if (nrm_partial) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
     if ((t & 31) == 0) red[t >> 5] = nrm;
     __syncthreads();
     if (t == 0) {
-      double s = 0;
-      for (int q = 0; q < 8; ++q) s += red[q];
-      nrm_partial[blockIdx.x] = s;
+      double s2 = 0;
+      for (int q = 0; q < 8; ++q) s2 += red[q];
+      nrm_partial[blockIdx.x] = s2;
     }
   }
 }
@@ -229,7 +294,7 @@ __global__ void k_sqnorm_partial(const T* __restrict__ v, int n, double* __restr
 
 // V[0..p) <- V[0..m) Q (Q: m x p column-major) ; V[p] <- V[m].  One thread per row.
 template <class T>
-__global__ void __launch_bounds__(128) k_basis_update(T* __restrict__ V, int64_t ld, int n, int m, int p,
+__global__ void __launch_bounds__(128, 8) k_basis_update(T* __restrict__ V, int64_t ld, int n, int m, int p,
                                                       const T* __restrict__ Q) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
@@ -249,7 +314,7 @@ __device__ inline cplx mulc_(cplx a, cplx b) { return a * b; }
 
 // X[i][r] = sum_l V[l][r] * Y[l + i*m]   (Y complex, X complex)
 template <class T>
-__global__ void __launch_bounds__(128) k_ritz_vectors(const T* __restrict__ V, int64_t ld, int n, int m, int k,
+__global__ void __launch_bounds__(128, 8) k_ritz_vectors(const T* __restrict__ V, int64_t ld, int n, int m, int k,
                                                       const cplx* __restrict__ Y, cplx* __restrict__ X) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;

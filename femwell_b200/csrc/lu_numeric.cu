@@ -231,7 +231,7 @@ static void lu_analyse_finish(Handle& h) {
 
 // ------------------------------------------------------------------------------ scatter of OP into fronts
 template <class S, class V>
-__global__ void __launch_bounds__(256) k_lu_scatter(int n, const int* __restrict__ indptr,
+__global__ void __launch_bounds__(256, 4) k_lu_scatter(int n, const int* __restrict__ indptr,
                                                     const int* __restrict__ indices, const V* __restrict__ A,
                                                     const V* __restrict__ B, S alphaA, S alphaB, FrontTab T,
                                                     const int* __restrict__ iperm, const int* __restrict__ node_of,
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256) k_lu_scatter(int n, const int* __restrict
 
 // ------------------------------------------------------------------------------ extend-add
 template <class S>
-__global__ void __launch_bounds__(256) k_lu_extend_add(FrontTab T, const int* __restrict__ nodes, int slot,
+__global__ void __launch_bounds__(256, 4) k_lu_extend_add(FrontTab T, const int* __restrict__ nodes, int slot,
                                                        S* __restrict__ F) {
   const int p = nodes[blockIdx.x];
   const int c = slot ? T.child1[p] : T.child0[p];
@@ -293,20 +293,32 @@ __global__ void __launch_bounds__(256) k_lu_extend_add(FrontTab T, const int* __
   const int i = ti * 32 + tx;
   if (i >= nbc) return;
   const int ri = rel[i];
-  for (int jj = ty; jj < 32; jj += 8) {
-    const int j = tj * 32 + jj;
-    if (j >= nbc) break;
-    const int rj = rel[j];
-    S* dst = Fp + ri + (long long)rj * mp;
-    *dst = *dst + Fc[(nsc + i) + (long long)(nsc + j) * mc];
+  // the four entries of this thread: all loads first (the targets are distinct, which the compiler cannot see)
+  long long dst[4];
+  S add[4], old[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int j = tj * 32 + ty + 8 * u;
+    dst[u] = j < nbc ? ri + (long long)rel[j] * mp : -1;
   }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int j = tj * 32 + ty + 8 * u;
+    if (dst[u] >= 0) {
+      add[u] = Fc[(nsc + i) + (long long)(nsc + j) * mc];
+      old[u] = Fp[dst[u]];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (dst[u] >= 0) Fp[dst[u]] = old[u] + add[u];
 }
 
 // ------------------------------------------------------------------------------ panel (pivot window) kernel
 // WIN: rows of the shared-memory window = threads of the CTA (64 / 128 for the levels of small fronts, where the
 // 66 KB window of 256 rows would leave three CTAs per SM with most of their threads idle)
 template <class S, int WIN>
-__global__ void __launch_bounds__(WIN) k_lu_panel(FrontTab T, const int* __restrict__ nodes, int kstep,
+__global__ void __launch_bounds__(WIN, 1024 / WIN) k_lu_panel(FrontTab T, const int* __restrict__ nodes, int kstep,
                                                    S* __restrict__ F, int* __restrict__ piv, double thr,
                                                    int* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -324,8 +336,17 @@ __global__ void __launch_bounds__(WIN) k_lu_panel(FrontTab T, const int* __restr
   __shared__ int s_piv;
   S* Fn = F + T.front_off[node];
   const int t = threadIdx.x;
-  for (int c = 0; c < w; ++c)
-    if (t < hw) a[c * LD + t] = Fn[(k0 + t) + (long long)(k0 + c) * m];
+  if (t < hw) {  // eight independent loads in flight per thread
+    for (int c0 = 0; c0 < w; c0 += 8) {
+      S v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = c0 + u < w ? Fn[(k0 + t) + (long long)(k0 + c0 + u) * m] : scalar_traits<S>::zero();
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (c0 + u < w) a[(c0 + u) * LD + t] = v[u];
+    }
+  }
   __syncthreads();
   for (int j = 0; j < w; ++j) {
     // ---- pivot search in column j, rows j..hw-1 (one row per thread)

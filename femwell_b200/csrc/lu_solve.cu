@@ -94,6 +94,13 @@ __device__ __forceinline__ void row_dot_sub(S (&acc)[NRHS], const S* __restrict_
   }
 }
 
+// Occupancy hints.  A kernel with __launch_bounds__(N) and NO minimum block count makes ptxas schedule for the smallest
+// register footprint (32 registers here): it then sinks every load of an unrolled batch down to the FMA that consumes
+// it, and ONE factor load is in flight per thread (SASS: LDG, DFMA, LDG, DFMA ...; ncu: every DFMA waits on the long
+// scoreboard).  With an explicit minimum the same source keeps the 16 loads of row_dot_sub back to back (58-64
+// registers).  Measured on the config-2 factors: substitution pair 4.30 -> 3.28 ms (profiles/occupancy_hint_r02.log).
+__host__ __device__ constexpr int upd_min_blocks(int G) { return G == 4 ? 2 : 8; }
+
 // Synchronisation policy of the chain kernels: one CTA (block barrier) or one cluster (cluster barrier).
 struct SyncCta {
   static constexpr bool pipe = false;  // small fronts: occupancy matters more than the register prefetch
@@ -325,14 +332,14 @@ __device__ __forceinline__ void fwd_chain_body(FrontTab T, const int node, const
 }
 
 template <class S, int NRHS>
-__global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_fwd_chain(FrontTab T, const int* __restrict__ nodes,
+__global__ void __launch_bounds__(SOLVE_MAX_THREADS, 2) k_fwd_chain(FrontTab T, const int* __restrict__ nodes,
                                                                  const S* __restrict__ F,
                                                                  const int* __restrict__ rowperm, S* work,
                                                                  int64_t work_stride, S* xp, int na) {
   fwd_chain_body<S, NRHS, SyncCta>(T, nodes[blockIdx.x], F, rowperm, work, work_stride, xp, na);
 }
 template <class S, int NRHS>
-__global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_fwd_chain_fused(FrontTab T, const int* __restrict__ nodes,
+__global__ void __launch_bounds__(SOLVE_MAX_THREADS, 2) k_fwd_chain_fused(FrontTab T, const int* __restrict__ nodes,
                                                                        const S* __restrict__ F,
                                                                        const int* __restrict__ rowperm, S* work,
                                                                        int64_t work_stride, S* xp, int na) {
@@ -341,7 +348,7 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_fwd_chain_fused(FrontTab 
 // DINV variants (f64, <= DINV_MAX_THREADS threads): see dinv_fetch / dinv_apply
 constexpr int DINV_MAX_THREADS = 128;
 template <int NRHS, bool FUSE>
-__global__ void __launch_bounds__(DINV_MAX_THREADS) k_fwd_chain_dinv(FrontTab T, const int* __restrict__ nodes,
+__global__ void __launch_bounds__(DINV_MAX_THREADS, 8) k_fwd_chain_dinv(FrontTab T, const int* __restrict__ nodes,
                                                                      const double* __restrict__ F,
                                                                      const double* __restrict__ dinv,
                                                                      const int* __restrict__ rowperm, double* work,
@@ -505,19 +512,19 @@ __device__ __forceinline__ void bwd_chain_body(FrontTab T, const int node, const
 }
 
 template <class S, int NRHS>
-__global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_bwd_chain(FrontTab T, const int* __restrict__ nodes,
+__global__ void __launch_bounds__(SOLVE_MAX_THREADS, 2) k_bwd_chain(FrontTab T, const int* __restrict__ nodes,
                                                                  const S* __restrict__ F, S* work,
                                                                  int64_t work_stride, S* xp, int na) {
   bwd_chain_body<S, NRHS, SyncCta>(T, nodes[blockIdx.x], F, work, work_stride, xp, na);
 }
 template <class S, int NRHS>
-__global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_bwd_chain_fused(FrontTab T, const int* __restrict__ nodes,
+__global__ void __launch_bounds__(SOLVE_MAX_THREADS, 2) k_bwd_chain_fused(FrontTab T, const int* __restrict__ nodes,
                                                                        const S* __restrict__ F, S* work,
                                                                        int64_t work_stride, S* xp, int na) {
   bwd_chain_body<S, NRHS, SyncCta, true>(T, nodes[blockIdx.x], F, work, work_stride, xp, na);
 }
 template <int NRHS, bool FUSE>
-__global__ void __launch_bounds__(DINV_MAX_THREADS) k_bwd_chain_dinv(FrontTab T, const int* __restrict__ nodes,
+__global__ void __launch_bounds__(DINV_MAX_THREADS, 8) k_bwd_chain_dinv(FrontTab T, const int* __restrict__ nodes,
                                                                      const double* __restrict__ F,
                                                                      const double* __restrict__ dinv, double* work,
                                                                      int64_t work_stride, double* xp, int na) {
@@ -831,7 +838,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS)
 // gridDim.z > 1: the column chunks are dealt round-robin to the z-slices; every slice writes its partial
 // sums to scratch[z][work_off + row] and k_upd_reduce adds them to w in a fixed order (deterministic).
 template <class S, int NRHS, int G>
-__global__ void __launch_bounds__(UPD_ROWS* G) k_fwd_update(FrontTab T, const int* __restrict__ nodes,
+__global__ void __launch_bounds__(UPD_ROWS* G, upd_min_blocks(G)) k_fwd_update(FrontTab T, const int* __restrict__ nodes,
                                                             const S* __restrict__ F, S* work, int64_t work_stride,
                                                             S* scratch) {
   constexpr int UPD_GROUPS = G;
@@ -883,7 +890,7 @@ __global__ void __launch_bounds__(UPD_ROWS* G) k_fwd_update(FrontTab T, const in
 }
 
 template <class S, int NRHS, int G>
-__global__ void __launch_bounds__(UPD_ROWS* G) k_bwd_update(FrontTab T, const int* __restrict__ nodes,
+__global__ void __launch_bounds__(UPD_ROWS* G, upd_min_blocks(G)) k_bwd_update(FrontTab T, const int* __restrict__ nodes,
                                                             const S* __restrict__ F, S* work, int64_t work_stride,
                                                             S* scratch) {
   constexpr int UPD_GROUPS = G;
@@ -987,7 +994,7 @@ __device__ __forceinline__ void wait_flag(const int* flag, int epoch) {
 }
 
 template <class S, int NRHS, bool FWD>
-__global__ void __launch_bounds__(SOLVE_MAX_THREADS) k_tree_band(FrontTab T, const int* __restrict__ order, int n_items,
+__global__ void __launch_bounds__(SOLVE_MAX_THREADS, 2) k_tree_band(FrontTab T, const int* __restrict__ order, int n_items,
                                                                  int n_first, int* sync, int ticket_slot,
                                                                  const S* __restrict__ F,
                                                                  const int* __restrict__ rowperm, S* work,

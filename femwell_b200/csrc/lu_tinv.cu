@@ -275,8 +275,8 @@ void tinv_build(Handle& h, LUDevice& d, const LUSymbolic& S) {
 // children's boundary contributions) and stage the own part in xp; the row interchanges are applied by the
 // matrix-vector kernel when it gathers its input
 template <int NRHS>
-__global__ void __launch_bounds__(256) k_tinv_fwd_prep(FrontTab T, const int* __restrict__ nodes, double* work,
-                                                       int64_t work_stride, double* xp, int na) {
+__global__ void __launch_bounds__(1024, 1) k_tinv_fwd_prep(FrontTab T, const int* __restrict__ nodes, double* work,
+                                                           int64_t work_stride, double* xp, int na) {
   const int node = nodes[blockIdx.x];
   const int m = T.m[node], ns = T.ns[node], os = T.own_start[node];
   double* w[NRHS];
@@ -292,13 +292,30 @@ __global__ void __launch_bounds__(256) k_tinv_fwd_prep(FrontTab T, const int* __
     if (c < 0) continue;
     const int nsc = T.ns[c], nbc = T.m[c] - nsc;
     const int* rel = T.rel + T.blist_off[c];
-    for (int i = t; i < nbc; i += nth) {
-      const int ri = rel[i];
+    // four entries per thread and pass, all loads before the first store (the targets of one child are distinct, but
+    // the compiler cannot know that: written as a plain loop every read-modify-write waits for the previous one)
+    for (int i0 = t; i0 < nbc; i0 += 4 * nth) {
+      int ri[4];
+      double v[NRHS][4], o[NRHS][4];
 #pragma unroll
-      for (int r = 0; r < NRHS; ++r) {
-        const double* wc = work + (size_t)r * work_stride + T.work_off[c];
-        w[r][ri] = w[r][ri] + wc[nsc + i];
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * nth;
+        ri[u] = i < nbc ? rel[i] : -1;
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * nth;
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+          v[r][u] = ri[u] >= 0 ? work[(size_t)r * work_stride + T.work_off[c] + nsc + i] : 0.0;
+          o[r][u] = ri[u] >= 0 ? w[r][ri[u]] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r)
+          if (ri[u] >= 0) w[r][ri[u]] = o[r][u] + v[r][u];
     }
     __syncthreads();
   }
@@ -312,7 +329,7 @@ __global__ void __launch_bounds__(256) k_tinv_fwd_prep(FrontTab T, const int* __
 // (64 rows x 4 threads left the 2001-row root front on 32 SMs with 16 KB in flight each: 160 us).
 constexpr int TV_ROWS = 32, TV_G = 16;
 template <int NRHS, bool FWD>
-__global__ void __launch_bounds__(TV_ROWS* TV_G) k_tinv_matvec(FrontTab T, const int* __restrict__ nodes,
+__global__ void __launch_bounds__(TV_ROWS* TV_G, 2) k_tinv_matvec(FrontTab T, const int* __restrict__ nodes,
                                                                const double* __restrict__ tinv,
                                                                const int* __restrict__ rowperm, double* work,
                                                                int64_t work_stride, double* xp, int na, int ld_b) {
@@ -410,7 +427,8 @@ void tinv_forward_level(Handle& h, LUDevice& d, const LUSymbolic& S, int lev, do
   cudaStream_t s = h.stream;
   const int nfront = S.level_start[lev + 1] - S.level_start[lev];
   const int* nodes = d.level_nodes.p + S.level_start[lev];
-  k_tinv_fwd_prep<NRHS><<<nfront, 256, 0, s>>>(d.tab(), nodes, work, S.work_entries, xp, na);
+  const int prep_threads = S.level_max_m[lev] > 2048 ? 1024 : S.level_max_m[lev] > 768 ? 512 : 256;
+  k_tinv_fwd_prep<NRHS><<<nfront, prep_threads, 0, s>>>(d.tab(), nodes, work, S.work_entries, xp, na);
   launch_matvec<NRHS, true>(d, S, lev, work, xp, na, s);
   h.tim.kernel_launches += 1;  // (the caller counts one launch per level)
 }

@@ -1,12 +1,13 @@
 #!/bin/bash
-# round-2 GPU batch X: fused small-front factorisation kernel
+# round-2 GPU batch X: occupancy hints (__launch_bounds__ min blocks) on the substitution kernels -- without one ptxas
+# minimises registers (32) and keeps ONE factor load in flight per thread
 mkdir -p gpurun_out/x
 cd "$(dirname "$0")/.."
-timeout 600 python -m pytest tests -m gpu -q --no-header -rf -p no:cacheprovider -x -k "lu_solve or config2_at_scale or compute_modes_matches or rectangle or metallic or bend" > gpurun_out/x/pytest_lu.log 2>&1
-tail -3 gpurun_out/x/pytest_lu.log
-for cfg in "" "FW_NO_FRONT_SMALL=1" "FW_FRONT_SMALL_MAX_M=160" "FW_FRONT_SMALL_MAX_M=300" "FW_FRONT_SMALL_MAX_M=600"; do
-  tag=$(echo "$cfg" | tr ' =' '__'); [ -z "$tag" ] && tag=default
-  env $cfg FW_FACTOR_TRACE=2 timeout 300 python scripts/trace_solve.py 500 2>&1 | grep -E "factor lev|lu factor: levels|residual" > gpurun_out/x/trace_$tag.log
-  echo "$tag: total $(grep 'factor lev' gpurun_out/x/trace_$tag.log | awk '{s+=$(NF-1)} END {print s}') $(grep residual gpurun_out/x/trace_$tag.log)"
+for combo in "0 0" "1 0" "2 0" "2 1" "2 2" "1 1"; do
+  set -- $combo
+  echo "== FW_UPD_VAR=$1 FW_CHAIN_VAR=$2" | tee -a gpurun_out/x/variants.log
+  FW_UPD_VAR=$1 FW_CHAIN_VAR=$2 timeout 300 python scripts/nrhs_probe.py 500 > gpurun_out/x/probe_$1_$2.log 2>&1
+  grep "fw-solve" gpurun_out/x/probe_$1_$2.log | sort -k4 -n | awk '{print $3, $4}' | sort | awk '{a[$1]=a[$1]" "$2} END {for (k in a) print "nrhs", k, a[k]}' | tee -a gpurun_out/x/variants.log
 done
-grep -E "lev (15|14|13|12|11|10) " gpurun_out/x/trace_default.log
+FW_UPD_VAR=2 FW_CHAIN_VAR=1 timeout 300 python scripts/trace_solve.py 500 > gpurun_out/x/trace_solve_2_1.log 2>&1
+grep -E "update|chain|residual" gpurun_out/x/trace_solve_2_1.log | head -70
