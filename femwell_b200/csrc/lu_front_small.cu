@@ -74,17 +74,26 @@ __device__ __forceinline__ void fs_gemm_tile(FsSmem<S>& sm, S* Fn, int m, int ns
     }
     __syncthreads();
   }
+  // all loads of the thread tile before the first store (see k_lu_gemm)
+  S old[4][4];
+  bool ok[4][4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int gc = cbase + ty * 4 + j;
-    if (gc >= c_hi) continue;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int gr = rbase + tx * 4 + i;
-      if (gr < m && !(skip_s22 && gr >= ns && gc >= ns)) {
-        S* dst = Fn + gr + (long long)gc * m;
-        *dst = *dst + acc[i][j];
-      }
+      ok[i][j] = gc < c_hi && gr < m && !(skip_s22 && gr >= ns && gc >= ns);
+      old[i][j] = ok[i][j] ? Fn[gr + (long long)gc * m] : scalar_traits<S>::zero();
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int gc = cbase + ty * 4 + j;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gr = rbase + tx * 4 + i;
+      if (ok[i][j]) Fn[gr + (long long)gc * m] = old[i][j] + acc[i][j];
     }
   }
 }

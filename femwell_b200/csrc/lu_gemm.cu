@@ -112,16 +112,32 @@ __global__ void __launch_bounds__(256) k_lu_gemm_big(FrontTab T, const int* __re
       buf ^= 1;
     }
   }
+  // C += acc, two columns of the thread tile at a time: all loads of the pair before the first store (written as one
+  // read-modify-write per entry the compiler must assume that a store aliases the next load, and every entry then
+  // waits a full memory round trip: SASS showed LDG, STG, LDG, STG ...)
 #pragma unroll
-  for (int j = 0; j < MT; ++j) {
-    const int gc = cbase + (j < H ? ty * H + j : TM / 2 + ty * H + (j - H));
-    if (gc >= m) continue;
+  for (int j0 = 0; j0 < MT; j0 += 2) {
+    S old[2][MT];
+    bool ok[2][MT];
 #pragma unroll
-    for (int i = 0; i < MT; ++i) {
-      const int gr = rbase + (i < H ? tx * H + i : TM / 2 + tx * H + (i - H));
-      if (gr < m && (SCHUR || gr < ns || gc < ns)) {
-        S* dst = Fn + gr + (long long)gc * m;
-        *dst = *dst + acc[i][j];
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = j0 + jj;
+      const int gc = cbase + (j < H ? ty * H + j : TM / 2 + ty * H + (j - H));
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const int gr = rbase + (i < H ? tx * H + i : TM / 2 + tx * H + (i - H));
+        ok[jj][i] = gc < m && gr < m && (SCHUR || gr < ns || gc < ns);
+        old[jj][i] = ok[jj][i] ? Fn[gr + (long long)gc * m] : scalar_traits<S>::zero();
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = j0 + jj;
+      const int gc = cbase + (j < H ? ty * H + j : TM / 2 + ty * H + (j - H));
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const int gr = rbase + (i < H ? tx * H + i : TM / 2 + tx * H + (i - H));
+        if (ok[jj][i]) Fn[gr + (long long)gc * m] = old[jj][i] + acc[i][j];
       }
     }
   }
@@ -234,21 +250,36 @@ __global__ void __launch_bounds__(TM * TM / 32, TM == 128 ? 1 : 3)
     }
   }
   // C -= acc: lane holds rows g of every 8 x 8 tile, columns 2 q and 2 q + 1
+  // (JG 8-column groups at a time -- 16 loads before the first store, 8 in the 512-thread variant with its
+  // 128-register budget; see the SIMT kernel above)
+  constexpr int JG = TM == 128 ? 1 : 2;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j0 = 0; j0 < 4; j0 += JG) {
+    double old[JG][2][4];
+    bool ok[JG][2][4];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int gc = cbase + wn * 32 + j * 8 + 2 * q + h;
-      if (gc >= m) continue;
+    for (int jj = 0; jj < JG; ++jj)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int gr = rbase + wm * 32 + i * 8 + g;
-        if (gr < m && (SCHUR || gr < ns || gc < ns)) {
-          double* dst = Fn + gr + (long long)gc * m;
-          *dst = *dst - acc[i][j][h];
+      for (int h = 0; h < 2; ++h) {
+        const int gc = cbase + wn * 32 + (j0 + jj) * 8 + 2 * q + h;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int gr = rbase + wm * 32 + i * 8 + g;
+          ok[jj][h][i] = gc < m && gr < m && (SCHUR || gr < ns || gc < ns);
+          old[jj][h][i] = ok[jj][h][i] ? Fn[gr + (long long)gc * m] : 0.0;
         }
       }
-    }
+#pragma unroll
+    for (int jj = 0; jj < JG; ++jj)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int gc = cbase + wn * 32 + (j0 + jj) * 8 + 2 * q + h;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int gr = rbase + wm * 32 + i * 8 + g;
+          if (ok[jj][h][i]) Fn[gr + (long long)gc * m] = old[jj][h][i] - acc[i][j0 + jj][h];
+        }
+      }
   }
 }
 

@@ -1078,17 +1078,27 @@ __global__ void __launch_bounds__(256) k_lu_gemm(FrontTab T, const int* __restri
     }
     __syncthreads();
   }
+  // C += acc: all loads of the thread tile before the first store (one read-modify-write per entry makes every entry
+  // wait a full memory round trip -- the compiler must assume that a store aliases the next load)
+  S old[4][4];
+  bool ok[4][4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int gc = cbase + ty * 4 + j;
-    if (gc >= cend) continue;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int gr = rbase + tx * 4 + i;
-      if (gr < m && (SCHUR || gr < ns || gc < ns)) {
-        S* dst = Fn + gr + (long long)gc * m;
-        *dst = *dst + acc[i][j];
-      }
+      ok[i][j] = gc < cend && gr < m && (SCHUR || gr < ns || gc < ns);
+      old[i][j] = ok[i][j] ? Fn[gr + (long long)gc * m] : scalar_traits<S>::zero();
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int gc = cbase + ty * 4 + j;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gr = rbase + tx * 4 + i;
+      if (ok[i][j]) Fn[gr + (long long)gc * m] = old[i][j] + acc[i][j];
     }
   }
 }
