@@ -56,7 +56,7 @@ struct LUDevice {
 };
 
 // selective inversion (lu_tinv.cu)
-constexpr int TINV_DEFAULT_MIN_NS = 110;
+constexpr int TINV_DEFAULT_MIN_NS = 200;  // re-tuned after the occupancy hints of the chain / update kernels (110 before)
 bool tinv_level_static(const LUSymbolic& S, int min_ns, int lev);
 bool tinv_level(const LUSymbolic& S, const LUDevice& d, int lev);
 void tinv_build(Handle& h, LUDevice& d, const LUSymbolic& S);  // after the numeric factorisation (f64 only)

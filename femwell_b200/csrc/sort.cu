@@ -113,20 +113,26 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_IPT = 16;
 constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 keys per block, 512 consecutive per warp
 
-__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restrict__ keys, int64_t n, int shift,
+__global__ void __launch_bounds__(RS_THREADS, 3) k_rs_hist(const uint64_t* __restrict__ keys, int64_t n, int shift,
                                                         uint32_t* __restrict__ hist, int nblocks) {
   __shared__ uint32_t sh[256];
   sh[threadIdx.x] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   int64_t base = (int64_t)blockIdx.x * RS_TILE;
-#pragma unroll 4
+  uint64_t key[RS_IPT];  // all keys of the thread first: the ranking below would otherwise wait for one load at a time
+#pragma unroll
+  for (int k = 0; k < RS_IPT; ++k) {
+    int64_t g = base + (int64_t)k * RS_THREADS + threadIdx.x;
+    key[k] = g < n ? keys[g] : 0;
+  }
+#pragma unroll
   for (int k = 0; k < RS_IPT; ++k) {
     int64_t g = base + (int64_t)k * RS_THREADS + threadIdx.x;
     bool valid = g < n;
     unsigned vm = __ballot_sync(0xffffffffu, valid);
     if (valid) {
-      uint32_t d = (uint32_t)(keys[g] >> shift) & 255u;
+      uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
       unsigned m = __match_any_sync(vm, d);
       if (lane == __ffs(m) - 1) atomicAdd(&sh[d], (uint32_t)__popc(m));
     }
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restri
 
 // Stable scatter: warp w of a block owns the 512 consecutive keys [w*512, (w+1)*512) of the
 // tile, walks them in rounds of 32, ranks equal digits with match_any.
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __restrict__ kin,
+__global__ void __launch_bounds__(RS_THREADS, 3) k_rs_scatter(const uint64_t* __restrict__ kin,
                                                            const uint32_t* __restrict__ vin,
                                                            uint64_t* __restrict__ kout, uint32_t* __restrict__ vout,
                                                            int64_t n, int shift, const uint32_t* __restrict__ offs,
@@ -148,12 +154,18 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
   __syncthreads();
   const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (RS_TILE / RS_WARPS);
   uint64_t key[RS_IPT];
+  uint32_t val[RS_IPT];
+#pragma unroll
+  for (int r = 0; r < RS_IPT; ++r) {  // all loads first (see k_rs_hist)
+    int64_t g = wbase + r * 32 + lane;
+    key[r] = g < n ? kin[g] : 0;
+    val[r] = (vin && g < n) ? vin[g] : (uint32_t)g;
+  }
 #pragma unroll
   for (int r = 0; r < RS_IPT; ++r) {
     int64_t g = wbase + r * 32 + lane;
     bool valid = g < n;
     unsigned vm = __ballot_sync(0xffffffffu, valid);
-    key[r] = valid ? kin[g] : 0;
     if (valid) {
       uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
       unsigned m = __match_any_sync(vm, d);
@@ -184,7 +196,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
       unsigned m = __match_any_sync(vm, d);
       uint32_t pos = wh[warp][d] + (uint32_t)__popc(m & lt);
       kout[pos] = key[r];
-      vout[pos] = vin ? vin[g] : (uint32_t)g;
+      vout[pos] = val[r];
       __syncwarp(vm);
       if (lane == __ffs(m) - 1) wh[warp][d] += (uint32_t)__popc(m);
     }

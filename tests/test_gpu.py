@@ -269,6 +269,8 @@ def test_lu_solve_schedules_agree(ctx, order, n, cplx, leaf, monkeypatch):
     for name, env in (("levels", {}), ("bands", {"FW_TREE": "1"}), ("one band", {"FW_TREE": "1", "FW_TREE_MIN_FRONTS": "1"}),
                       ("levels + L2 prefetch", {"FW_SOLVE_PF_KB": "48"}),
                       ("levels, substitution chains instead of inverse pivot blocks", {"FW_NO_TINV_SOLVE": "1"}),
+                      ("levels, serial 32-step diagonal solves instead of the pre-inverted diagonal blocks",
+                       {"FW_NO_DINV_CHAIN": "1"}),
                       ("one band, 64 threads", {"FW_TREE": "1", "FW_TREE_MIN_FRONTS": "1", "FW_TREE_SMALL_M": "100000",
                                                 "FW_TREE_THREADS_A": "64"})):
         with monkeypatch.context() as mp:
