@@ -815,8 +815,8 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_lu_panel_regs(FrontTab T, con
 // GATHER: the interchanges as one gather (two rounds of independent loads; 150 registers) -- levels of few fronts,
 // where the chain of w dependent read-modify-writes through L2 is what the step waits for; the sequential form keeps
 // the register count (and the occupancy) of the levels with thousands of small fronts.
-template <class S, bool GATHER>
-__global__ void __launch_bounds__(128) k_lu_swap_trsm(FrontTab T, const int* __restrict__ nodes, int kstep,
+template <class S, bool GATHER, int MINB = 0>
+__global__ void __launch_bounds__(128, MINB) k_lu_swap_trsm(FrontTab T, const int* __restrict__ nodes, int kstep,
                                                       S* __restrict__ F, const int* __restrict__ piv, int ctiles,
                                                       int ob) {
   __shared__ S D[PW][PW + 1];
@@ -1024,9 +1024,9 @@ struct GemmCfg<cplx> {
 // SCHUR = true : once per front after its last panel, S22 -= L21 U12 with the full inner dimension ns, so the
 //                 Schur complement (the bulk of the flops for nb >> ns) is read and written once.
 // ob > 0: inner update of two-level blocking -- only the columns of the current outer block of ob panels.
-template <class S, bool SCHUR>
-__global__ void __launch_bounds__(256) k_lu_gemm(FrontTab T, const int* __restrict__ nodes, int kstep,
-                                                 S* __restrict__ F, int ob = 0, int kw = PW) {
+template <class S, bool SCHUR, int MINB = 0>
+__global__ void __launch_bounds__(256, MINB) k_lu_gemm(FrontTab T, const int* __restrict__ nodes, int kstep,
+                                                       S* __restrict__ F, int ob = 0, int kw = PW) {
   constexpr int TM = 64, KC = GemmCfg<S>::KC;
   __shared__ S As[KC][TM];
   __shared__ S Bs[KC][TM + 1];
@@ -1188,6 +1188,16 @@ __global__ void __launch_bounds__(32) k_lu_diag_inverse(FrontTab T, const int* _
   for (int i = 0; i < PW; ++i) outU[i] = x[i];
 }
 
+// occupancy hint of the SIMT GEMM selected at run time (FW_GEMM_MINB = 0 | 3 | 4; default 4: 64 registers, 4 blocks per SM,
+// -2 ms per config-2 factorisation, profiles/factor_hints_r02.log)
+#define LU_GEMM_ARGS_(...) __VA_ARGS__
+#define LU_GEMM_LAUNCH(SCH, CFG, ARGS)                                                  \
+  do {                                                                                  \
+    if (gemm_minb == 4) k_lu_gemm<S, SCH, 4><<<LU_GEMM_ARGS_ CFG>>>(LU_GEMM_ARGS_ ARGS);        \
+    else if (gemm_minb == 3) k_lu_gemm<S, SCH, 3><<<LU_GEMM_ARGS_ CFG>>>(LU_GEMM_ARGS_ ARGS);   \
+    else k_lu_gemm<S, SCH><<<LU_GEMM_ARGS_ CFG>>>(LU_GEMM_ARGS_ ARGS);                          \
+  } while (0)
+
 template <class S, class V>
 static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA, S alphaB) {
   LU& lu = *h.lu;
@@ -1230,8 +1240,9 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
   const bool trace2 = tenv && atoi(tenv) >= 2;
   // (the tensor-core GEMM has a 64 x 64 tile variant for trailing blocks below ~900 rows, lu_gemm.cu)
   static const int big_gemm_min = getenv("FW_BIG_GEMM_MIN") ? atoi(getenv("FW_BIG_GEMM_MIN")) : 48;
+  static const int gemm_minb = getenv("FW_GEMM_MINB") ? atoi(getenv("FW_GEMM_MINB")) : 4;
   static const int swap_gather_max_fronts =
-      getenv("FW_SWAP_GATHER_MAX_FRONTS") ? atoi(getenv("FW_SWAP_GATHER_MAX_FRONTS")) : 512;
+      getenv("FW_SWAP_GATHER_MAX_FRONTS") ? atoi(getenv("FW_SWAP_GATHER_MAX_FRONTS")) : 4096;
   static const bool no_cluster_panel = getenv("FW_NO_CLUSTER_PANEL") != nullptr;
   static const bool no_regs_panel = getenv("FW_NO_REGS_PANEL") != nullptr;
   // two-level blocking (outer blocks of OB panels) for levels whose pivot blocks span more than one panel
@@ -1331,10 +1342,21 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
       // two-level blocking: rank-32 updates stay inside the current outer block of OB panels; the rest of the front
       // gets one rank-(32 OB) update per outer block (the 128 x 128 tensor-core GEMM needs a deep inner dimension)
       const int ob = (max_ns >= blocked_min_ns) ? OB : 0;
-      if (nfront_all <= swap_gather_max_fronts)
-        k_lu_swap_trsm<S, true><<<dim3(nfront, ctiles + rtiles), 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
-      else
-        k_lu_swap_trsm<S, false><<<dim3(nfront, ctiles + rtiles), 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
+      {
+        const dim3 grid(nfront, ctiles + rtiles);
+        // occupancy hint: 6 blocks of 128 threads (80 registers, a few spills) measured 2 ms faster per factorisation than the
+        // unconstrained 153-register build (profiles/factor_hints_r02.log); FW_SWAP_MINB=0 restores it
+        static const int swap_minb = getenv("FW_SWAP_MINB") ? atoi(getenv("FW_SWAP_MINB")) : 6;
+        if (nfront_all <= swap_gather_max_fronts) {
+          if (swap_minb == 4) k_lu_swap_trsm<S, true, 4><<<grid, 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
+          else if (swap_minb == 6) k_lu_swap_trsm<S, true, 6><<<grid, 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
+          else k_lu_swap_trsm<S, true><<<grid, 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
+        } else {
+          if (swap_minb == 4) k_lu_swap_trsm<S, false, 4><<<grid, 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
+          else if (swap_minb == 6) k_lu_swap_trsm<S, false, 6><<<grid, 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
+          else k_lu_swap_trsm<S, false><<<grid, 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
+        }
+      }
       const int rem = max_m - (k * PW);  // upper bound of the trailing size
       const int nt = (rem + 63) / 64;
       launches += 3;
@@ -1342,13 +1364,13 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
         if (rem >= big_gemm_min_panel)
           lu_gemm_big_launch<S>(T, nodes, nfront, k, F, rem, false, s);
         else if (nt > 0)
-          k_lu_gemm<S, false><<<dim3(nfront, nt, nt), 256, 0, s>>>(T, nodes, k, F, 0);
+          LU_GEMM_LAUNCH(false, (dim3(nfront, nt, nt), 256, 0, s), (T, nodes, k, F, 0));
         continue;
       }
       const bool last_inner = (k % ob == ob - 1) || k == npan - 1;
       if (!last_inner) {
         const int ct = (ob * PW - PW + 63) / 64;  // column tiles inside the outer block
-        if (nt > 0) k_lu_gemm<S, false><<<dim3(nfront, nt, ct), 256, 0, s>>>(T, nodes, k, F, ob);
+        if (nt > 0) LU_GEMM_LAUNCH(false, (dim3(nfront, nt, ct), 256, 0, s), (T, nodes, k, F, ob));
       } else {
         const int jb = k / ob;
         const int orem = max_m - jb * ob * PW;  // columns right of the block start (upper bound)
@@ -1357,7 +1379,7 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
         if (orem >= big_gemm_min_outer)
           lu_gemm_big_launch<S>(T, nodes, nfront, jb, F, orem, false, s, ob * PW);
         else
-          k_lu_gemm<S, false><<<dim3(nfront, (orem + 63) / 64, (orem + 63) / 64), 256, 0, s>>>(T, nodes, jb, F, 0, ob * PW);
+          LU_GEMM_LAUNCH(false, (dim3(nfront, (orem + 63) / 64, (orem + 63) / 64), 256, 0, s), (T, nodes, jb, F, 0, ob * PW));
         launches += 1;
       }
     }
@@ -1370,7 +1392,7 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
         if (Sy.level_max_nb[lev] >= big_gemm_min)
           lu_gemm_big_launch<S>(T, nodes, nfront, 0, F, Sy.level_max_nb[lev], true, s);
         else
-          k_lu_gemm<S, true><<<dim3(nfront, nt, nt), 256, 0, s>>>(T, nodes, 0, F);
+          LU_GEMM_LAUNCH(true, (dim3(nfront, nt, nt), 256, 0, s), (T, nodes, 0, F));
         launches += 1;
       }
     }
