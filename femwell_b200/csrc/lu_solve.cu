@@ -130,8 +130,19 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // 32 x 32 matrix-vector product, and the block itself is copied with cp.async into one of two shared-memory buffers
 // one panel ahead (ncu on the leaf level of config 2: 30 % of the backward kernel sat in the eight serialised
 // load + divide iterations per thread that filled D, another 35 % at the barriers around the serial solve).
-__device__ __forceinline__ void dinv_fetch(double* buf, const double* __restrict__ src, int t, int nthr) {
-  for (int c = t; c < PW * PW / 2; c += nthr) cp_async16(buf + 2 * c, src + 2 * c);
+// Only the non-zero triangle of the first wd columns is fetched (16-byte chunks = two rows of a column); the other chunks
+// of the buffer are zeroed, so the full 32 x 32 product of dinv_apply stays valid.  (Fetching the whole 8 KB block put
+// 1 GB per pass on top of the 2 GB of factor entries of the leaf level: ncu DRAM traffic 2.93 GB for the forward kernel.)
+template <bool LOWER>
+__device__ __forceinline__ void dinv_fetch(double* buf, const double* __restrict__ src, int wd, int t, int nthr) {
+  for (int c = t; c < PW * PW / 2; c += nthr) {
+    const int col = c >> 4, r2 = (c & 15) * 2;
+    const bool need = col < wd && r2 < wd && (LOWER ? r2 + 1 >= col : r2 <= col);
+    if (need)
+      cp_async16(buf + 2 * c, src + 2 * c);
+    else
+      *reinterpret_cast<double2*>(buf + 2 * c) = make_double2(0.0, 0.0);
+  }
 }
 // x = inv(D_kk) w_k by warp r (right-hand side r); Dv is column-major, ragged blocks are padded with the identity
 template <int NRHS>
@@ -208,7 +219,7 @@ __device__ __forceinline__ void fwd_chain_body(FrontTab T, const int node, const
   const double* dv = nullptr;
   if constexpr (DINV) {
     dv = dinv + T.dinv_off[node];
-    if (ns > 0) dinv_fetch(Dv[0], dv, t, nthr);  // independent of the right-hand side: in flight during the assembly
+    if (ns > 0) dinv_fetch<true>(Dv[0], dv, min(PW, ns), t, nthr);  // independent of the right-hand side: in flight during the assembly
   }
   // the first diagonal block and this thread's first row segment do not depend on the rhs: fetch them now
   S dn[DPT], ln[PW];
@@ -270,7 +281,7 @@ __device__ __forceinline__ void fwd_chain_body(FrontTab T, const int node, const
     if (pipelined && k1 < ns) diag_fetch<S>(dn, Fn, m, k1, min(PW, ns - k1), t, nthr);
     if constexpr (DINV) {
       const int kp = k0 / PW;
-      if (k1 < ns) dinv_fetch(Dv[(kp + 1) & 1], dv + (long long)(kp + 1) * PW * PW, t, nthr);
+      if (k1 < ns) dinv_fetch<true>(Dv[(kp + 1) & 1], dv + (long long)(kp + 1) * PW * PW, min(PW, ns - k1), t, nthr);
       if (t < 32 * NRHS) dinv_apply<NRHS>(Dv[kp & 1], work + (size_t)(t >> 5) * work_stride + T.work_off[node] + k0, wd, t, xs);
     } else if (t < 32 * NRHS) {  // replicated in every CTA of a cluster; rank 0 stores the result
       const int r = t >> 5, lane = t & 31;
@@ -394,7 +405,9 @@ __device__ __forceinline__ void bwd_chain_body(FrontTab T, const int node, const
   if constexpr (DINV) {
     // the first inv(U_kk) block does not depend on the right-hand side: in flight during the U12 pass
     const int np = (ns + PW - 1) / PW;
-    if (np > 0) dinv_fetch(Dv[(np - 1) & 1], dinv + T.dinv_off[node] + (long long)(2 * np - 1) * PW * PW, t, nthr);
+    if (np > 0)
+      dinv_fetch<false>(Dv[(np - 1) & 1], dinv + T.dinv_off[node] + (long long)(2 * np - 1) * PW * PW,
+                        ns - (np - 1) * PW, t, nthr);
   }
   if constexpr (FUSE) if (m > ns) {
     const int p = T.parent[node];
@@ -454,7 +467,7 @@ __device__ __forceinline__ void bwd_chain_body(FrontTab T, const int node, const
     __syncthreads();
     if (pipelined && kp > 0) diag_fetch<S>(dn, Fn, m, k0 - PW, PW, t, nthr);
     if constexpr (DINV) {
-      if (kp > 0) dinv_fetch(Dv[(kp - 1) & 1], dv + (long long)(kp - 1) * PW * PW, t, nthr);
+      if (kp > 0) dinv_fetch<false>(Dv[(kp - 1) & 1], dv + (long long)(kp - 1) * PW * PW, PW, t, nthr);
       if (t < 32 * NRHS) dinv_apply<NRHS>(Dv[kp & 1], work + (size_t)(t >> 5) * work_stride + T.work_off[node] + k0, wd, t, xs);
     } else if (t < 32 * NRHS) {
       const int r = t >> 5, lane = t & 31;
@@ -1117,6 +1130,7 @@ static void solve_typed(Handle& h, const S* b, S* x) {
   static const int fuse_max_m = getenv("FW_FUSE_MAX_M") ? atoi(getenv("FW_FUSE_MAX_M")) : 512;
   // forward fused kernel: two rows per thread (blockDim = m / 2) doubles the fronts in flight per SM -- the kernel is
   // bound by the latency of its dependent steps, not by issue slots: leaf level 0.98 -> 0.70 ms (FW_FUSE_TDIV)
+  static const int fuse_min_ns = getenv("FW_FUSE_MIN_NS") ? atoi(getenv("FW_FUSE_MIN_NS")) : 0;
   static const int fuse_tdiv = getenv("FW_FUSE_TDIV") ? std::max(1, atoi(getenv("FW_FUSE_TDIV"))) : 2;
   auto use_inv = [&](int max_ns) {
     return !scalar_traits<S>::is_complex && d.dinv_valid && !no_cluster && !no_inv && max_ns > CL_MIN_NS &&
@@ -1181,7 +1195,7 @@ static void solve_typed(Handle& h, const S* b, S* x) {
     // measured (500k triangles): forward fusion pays only when the pivot block spans several panels
     bool tinv = false;  // pivot-block solves as triangular matrix-vector products (selective inversion, lu_tinv.cu)
     if constexpr (!scalar_traits<S>::is_complex) tinv = !no_tinv && tinv_level(Sy, d, lev);
-    const bool fuse = !tinv && Sy.level_max_m[lev] <= fuse_max_m && nfront >= 296 && max_ns >= 64;
+    const bool fuse = !tinv && Sy.level_max_m[lev] <= fuse_max_m && nfront >= 296 && max_ns >= fuse_min_ns;
     if (tinv) {
       if constexpr (!scalar_traits<S>::is_complex) {
         tinv_forward_level<NRHS>(h, d, Sy, lev, work, xp, na);
