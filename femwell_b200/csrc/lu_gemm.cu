@@ -304,7 +304,7 @@ static void lu_gemm_dmma_launch_tm(FrontTab T, const int* nodes, int nfront, int
 static void lu_gemm_dmma_launch(FrontTab T, const int* nodes, int nfront, int kstep, double* F, int max_rem, bool schur,
                                 cudaStream_t s, int kw) {
   // trailing blocks below ~900 rows: 64 x 64 tiles (less ragged-edge waste, three CTAs per SM)
-  static const int small_max = getenv("FW_DMMA64_MAX") ? atoi(getenv("FW_DMMA64_MAX")) : 900;
+  static const int small_max = getenv("FW_DMMA64_MAX") ? atoi(getenv("FW_DMMA64_MAX")) : 2000;
   if (max_rem <= small_max)
     lu_gemm_dmma_launch_tm<64>(T, nodes, nfront, kstep, F, max_rem, schur, s, kw);
   else

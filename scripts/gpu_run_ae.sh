@@ -1,11 +1,8 @@
 #!/bin/bash
-# incidence-based pattern build of the FE space: parity suite (pattern bit-exact vs scipy / oracle), bench
+# round-2 GPU batch AE: which Schur-complement GEMM on the small-front levels (SIMT 64x64 with batched epilogue vs DMMA 64 / 128 tiles)
 mkdir -p gpurun_out/ae
 cd "$(dirname "$0")/.."
-timeout 900 python -m pytest tests -m gpu -q --no-header -rf -p no:cacheprovider -x > gpurun_out/ae/pytest.log 2>&1
-tail -3 gpurun_out/ae/pytest.log
-FW_TRACE=1 timeout 300 python scripts/assemble_only.py 500 1 2>&1 | grep -E "symbolic|rep 0" > gpurun_out/ae/symbolic_trace.log
-cat gpurun_out/ae/symbolic_trace.log
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ae/bench.json 2> gpurun_out/ae/bench.err
-tail -1 gpurun_out/ae/bench.err
-FW_SYMBOLIC_FULL_SORT=1 timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline 2>&1 >/dev/null | tail -1
+for v in "FW_X=0" "FW_BIG_GEMM_MIN=120" "FW_BIG_GEMM_MIN=200" "FW_BIG_GEMM_MIN=300" "FW_DMMA64_MAX=400" "FW_DMMA64_MAX=2000" "FW_BLOCKED_MIN_NS=65"; do
+  echo "== $v" | tee -a gpurun_out/ae/variants.log
+  env $v timeout 200 python scripts/factor_reps.py 500 2>&1 | tail -1 | tee -a gpurun_out/ae/variants.log
+done
