@@ -373,11 +373,11 @@ def main():
     t_pair = float(np.sum(solve_ms)) / 1000.0 / max(1.0, solve_pairs)
     solve_bytes = float(tt["lu_solve_entries"]) * sv
     solve_achieved = solve_bytes / t_pair / 1e9 if t_pair > 0 else 0.0
-    roofline = {"kernel": "sparse-LU triangular solves (k_fwd/bwd_chain_fused, k_fwd/bwd_chain, k_fwd/bwd_update, "
+    roofline = {"kernel": "sparse-LU triangular solves (k_fwd/bwd_chain_dinv on the small-front levels, k_fwd/bwd_update, "
                           "k_tinv_matvec on the inverse pivot blocks of the top levels): one forward + backward "
-                          "substitution pair per Arnoldi step, ~75 kernel nodes replayed as one CUDA graph",
+                          "substitution pair per Arnoldi step, ~85 kernel nodes replayed as one CUDA graph",
                 "bound": "hbm", "achieved": solve_achieved, "peak": peak, "unit": "GB/s", "frac": solve_achieved / peak,
-                "traffic": ncu_traffic("ncu_r02_solve_pair_full.csv", "k_", total=True),
+                "traffic": ncu_traffic("ncu_r02_final_solve_pair.csv", "k_", total=True),
                 "algorithmic_bytes_per_launch": solve_bytes, "seconds_per_launch": t_pair,
                 "launch_unit": "one solve pair (all its kernels); L and U entries of every front read once: "
                                "sum(m^2 - (m-ns)^2) x 8 B from the analysis tables",
