@@ -357,9 +357,9 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS, 2) k_fwd_chain_fused(FrontT
   fwd_chain_body<S, NRHS, SyncCta, true>(T, nodes[blockIdx.x], F, rowperm, work, work_stride, xp, na);
 }
 // DINV variants (f64, <= DINV_MAX_THREADS threads): see dinv_fetch / dinv_apply
-constexpr int DINV_MAX_THREADS = 128;
+constexpr int DINV_MAX_THREADS = 256;
 template <int NRHS, bool FUSE>
-__global__ void __launch_bounds__(DINV_MAX_THREADS, 8) k_fwd_chain_dinv(FrontTab T, const int* __restrict__ nodes,
+__global__ void __launch_bounds__(DINV_MAX_THREADS, 4) k_fwd_chain_dinv(FrontTab T, const int* __restrict__ nodes,
                                                                      const double* __restrict__ F,
                                                                      const double* __restrict__ dinv,
                                                                      const int* __restrict__ rowperm, double* work,
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(SOLVE_MAX_THREADS, 2) k_bwd_chain_fused(FrontT
   bwd_chain_body<S, NRHS, SyncCta, true>(T, nodes[blockIdx.x], F, work, work_stride, xp, na);
 }
 template <int NRHS, bool FUSE>
-__global__ void __launch_bounds__(DINV_MAX_THREADS, 8) k_bwd_chain_dinv(FrontTab T, const int* __restrict__ nodes,
+__global__ void __launch_bounds__(DINV_MAX_THREADS, 4) k_bwd_chain_dinv(FrontTab T, const int* __restrict__ nodes,
                                                                      const double* __restrict__ F,
                                                                      const double* __restrict__ dinv, double* work,
                                                                      int64_t work_stride, double* xp, int na) {
@@ -1138,8 +1138,10 @@ static void solve_typed(Handle& h, const S* b, S* x) {
   };
   // small fronts in real arithmetic: pre-inverted diagonal blocks + cp.async double buffer (FW_NO_DINV_CHAIN=1 disables)
   const bool no_dinv_chain = getenv("FW_NO_DINV_CHAIN") != nullptr || lu.no_tinv;
+  static const int dinv_max_threads =
+      getenv("FW_DINV_MAX_THREADS") ? std::min(DINV_MAX_THREADS, atoi(getenv("FW_DINV_MAX_THREADS"))) : DINV_MAX_THREADS;
   auto use_dinv = [&](int threads) {
-    return !scalar_traits<S>::is_complex && d.dinv_valid && !no_dinv_chain && threads <= DINV_MAX_THREADS;
+    return !scalar_traits<S>::is_complex && d.dinv_valid && !no_dinv_chain && threads <= dinv_max_threads;
   };
   // ---- dataflow bands over the lower levels (see k_tree_band): A = small fronts (128 threads), B = the rest
   // (the knobs are read per call so that the tests can switch the path; a captured graph keeps its own choice)
