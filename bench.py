@@ -124,6 +124,27 @@ def run_cpu_sample(n_sample, num_modes):
     return dt, int(m.nelements), r.timings, [float(x.real) for x in r.n_effs]
 
 
+def ncu_traffic(csv_name, kernel_substr, n_expected=None, total=False, profiles_dir=None):
+    """DRAM bytes (read + write) per launch of a kernel from a committed ncu summary (profiles/*.csv: a comment line, the
+    header, the unit row, one row per launch -- the format scripts/ncu_raw_to_summary.py writes), or None;
+    total=True: the sum over all rows (a launch UNIT made of many kernels, e.g. one substitution pair)"""
+    try:
+        import csv
+
+        path = os.path.join(profiles_dir or os.path.join(ROOT, "profiles"), csv_name)
+        rows = [r for r in csv.reader(open(path)) if r and not r[0].startswith("#")]
+        hdr, units = rows[0], rows[1]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        sel = [r for r in rows[2:] if kernel_substr in r[0] or (len(r) > 1 and kernel_substr in r[1])]
+        if not sel:
+            return None
+        tot = [float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0) for r in sel]
+        return float(np.sum(tot)) if total else float(np.mean(tot))
+    except Exception:
+        return None
+
+
 def fit_power_law(ne, seconds):
     """least squares of log t = log c + p log Ne"""
     x, y = np.log(np.asarray(ne, dtype=float)), np.log(np.asarray(seconds, dtype=float))
@@ -349,24 +370,6 @@ def main():
     peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     tt = stats["timings"]
-
-    def ncu_traffic(csv_name, kernel_substr, n_expected=None, total=False):
-        """DRAM bytes (read + write) per launch of a kernel from a committed `ncu --set full` summary, or None;
-        total=True: the sum over all rows (a launch UNIT made of many kernels, e.g. one substitution pair)"""
-        try:
-            import csv
-
-            rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", csv_name))) if r and not r[0].startswith("#")]
-            hdr, units = rows[0], rows[1]
-            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            sel = [r for r in rows[2:] if kernel_substr in r[0] or (len(r) > 1 and kernel_substr in r[1])]
-            if not sel:
-                return None
-            tot = [float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0) for r in sel]
-            return float(np.sum(tot)) if total else float(np.mean(tot))
-        except Exception:
-            return None
 
     # ---- dominant kernel family: the triangular solves of the sparse LU (one forward + backward pair per OP application)
     solve_pairs = float(np.sum(n_ops))

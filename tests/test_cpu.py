@@ -666,3 +666,34 @@ def test_bench_ladder_extrapolation_is_anchored_and_never_sublinear():
     assert p3 < 1 and abs(t_full - t_lin) < 1e-12 * t_lin
     assert "500000 triangles" in bench.workload_text(500, 4)
     assert bench.algorithmic_bytes_element_kernel(10, 8, 14, 8, 8, 8) == 10 * 20 + 8 * 16 + 10 * (196 + 64) * 8
+
+
+def test_ncu_summary_converter_and_roofline_traffic_reader(tmp_path):
+    """bench.py takes `roofline.traffic` from a committed per-launch ncu summary; scripts/ncu_raw_to_summary.py writes
+    that format from an `ncu --page raw --csv` export.  Round trip on a synthetic export, then the committed capture of
+    one substitution pair: its DRAM traffic cannot be below the algorithmic bytes the bench divides by."""
+    import importlib.util
+    import subprocess
+    import sys
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    raw = tmp_path / "raw.csv"
+    raw.write_text(
+        '==PROF== Connected to process 1\n'
+        '"ID","Process ID","Kernel Name","Block Size","Grid Size","dram__bytes_read.sum","dram__bytes_write.sum",'
+        '"gpu__time_duration.sum","launch__registers_per_thread"\n'
+        '"","","","","","byte","byte","ns","register/thread"\n'
+        '"0","7","void fw::k_fwd_update<double, 1, 1>(fw::FrontTab, const int *)","(128, 1, 1)","(16, 2, 1)","1,000","24","5,000","62"\n'
+        '"1","7","void fw::k_bwd_update<double, 1, 4>(fw::FrontTab, const int *)","(512, 1, 1)","(8, 1, 2)","3000","0","7000","62"\n')
+    out = tmp_path / "summary.csv"
+    subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_raw_to_summary.py"), str(raw), str(out), "synthetic"],
+                   check=True, capture_output=True)
+    assert out.read_text().startswith("# synthetic\n")
+    assert bench.ncu_traffic("summary.csv", "k_", total=True, profiles_dir=str(tmp_path)) == 4024.0
+    assert bench.ncu_traffic("summary.csv", "k_fwd_update", profiles_dir=str(tmp_path)) == 1024.0
+    assert bench.ncu_traffic("summary.csv", "no_such_kernel", profiles_dir=str(tmp_path)) is None
+    assert bench.ncu_traffic("missing.csv", "k_", profiles_dir=str(tmp_path)) is None
+    pair = bench.ncu_traffic("ncu_r02_final_solve_pair.csv", "k_", total=True)
+    assert pair is not None and 9.95e9 < pair < 2.0e10  # 9.95 GB of L and U entries per pair at config 2
