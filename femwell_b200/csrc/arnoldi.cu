@@ -427,6 +427,12 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
   const int64_t ld = n;
   int n_op = 0;
   double solve_ms = 0;
+  struct EventList {
+    std::vector<cudaEvent_t> ev;  // (start, stop) pairs
+    ~EventList() {
+      for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
+  } solve_events;
   const T sigT = HS::from_cd(sigma);
   const T minus1 = HS::from_cd(cd(-1.0, 0.0));
   const T zeroT = HS::from_cd(cd(0.0, 0.0));
@@ -448,7 +454,14 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
     } else {
       op_apply_impl<V, T>(h, act.p, zeroT, minus1, false, x, t1);
     }
-    Timer ts(s);
+    // event pair per application, read back once at the end: a synchronising timer here would stall the host (and leave
+    // the GPU idle until the CGS2 launches arrive) after every one of the ~50 solves
+    cudaEvent_t ea = nullptr, eb = nullptr;
+    FW_CHECK_CUDA(cudaEventCreate(&ea));
+    FW_CHECK_CUDA(cudaEventCreate(&eb));
+    solve_events.ev.push_back(ea);
+    solve_events.ev.push_back(eb);
+    FW_CHECK_CUDA(cudaEventRecord(ea, s));
     lu_solve_dev(h, t1, y, 1);
     for (int it = 0; it < refine; ++it) {
       // r = t1 - (K - sigma M) y = t1 - (-A + sigma B) y
@@ -458,7 +471,8 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
       k_axpy1<T><<<cdiv(n, 256), 256, 0, s>>>(y, t2, n, 1.0);
       h.tim.kernel_launches += 2;
     }
-    solve_ms += ts.stop();
+    FW_CHECK_CUDA(cudaEventRecord(eb, s));
+    if (getenv("FW_TRACE")) FW_CHECK_CUDA(cudaEventSynchronize(eb));  // the host wall-clock split of the trace needs it
     ++n_op;
   };
 
@@ -752,6 +766,11 @@ static void eigs_typed(Handle& h, const fw_eigs_params& prm, int refine, const s
     }
   }
   FW_CHECK_CUDA(cudaStreamSynchronize(s));
+  for (size_t i = 0; i + 1 < solve_events.ev.size(); i += 2) {
+    float ms = 0;
+    FW_CHECK_CUDA(cudaEventElapsedTime(&ms, solve_events.ev[i], solve_events.ev[i + 1]));
+    solve_ms += ms;
+  }
   if (st) {
     st->nconv = noconv ? kout : nconv;
     st->iterations = iterations;
