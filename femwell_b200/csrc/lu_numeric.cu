@@ -1240,7 +1240,8 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
   const bool trace2 = tenv && atoi(tenv) >= 2;
   // (the tensor-core GEMM has a 64 x 64 tile variant for trailing blocks below ~900 rows, lu_gemm.cu)
   static const int big_gemm_min = getenv("FW_BIG_GEMM_MIN") ? atoi(getenv("FW_BIG_GEMM_MIN")) : 48;
-  static const int gemm_minb = getenv("FW_GEMM_MINB") ? atoi(getenv("FW_GEMM_MINB")) : 4;
+  static const int gemm_minb_env = getenv("FW_GEMM_MINB") ? atoi(getenv("FW_GEMM_MINB")) : 4;
+  const int gemm_minb = scalar_traits<S>::is_complex ? 0 : gemm_minb_env;  // the c128 kernel uses 128 registers
   static const int swap_gather_max_fronts =
       getenv("FW_SWAP_GATHER_MAX_FRONTS") ? atoi(getenv("FW_SWAP_GATHER_MAX_FRONTS")) : 4096;
   static const bool no_cluster_panel = getenv("FW_NO_CLUSTER_PANEL") != nullptr;
@@ -1346,7 +1347,10 @@ static void factor_typed(Handle& h, const Values& VA, const Values& VB, S alphaA
         const dim3 grid(nfront, ctiles + rtiles);
         // occupancy hint: 6 blocks of 128 threads (80 registers, a few spills) measured 2 ms faster per factorisation than the
         // unconstrained 153-register build (profiles/factor_hints_r02.log); FW_SWAP_MINB=0 restores it
-        static const int swap_minb = getenv("FW_SWAP_MINB") ? atoi(getenv("FW_SWAP_MINB")) : 6;
+        // (real arithmetic only: the c128 instantiation needs 234 registers and spills badly under the cap -- config-3 probe:
+        // factor 1.93 -> 2.00 s)
+        static const int swap_minb_env = getenv("FW_SWAP_MINB") ? atoi(getenv("FW_SWAP_MINB")) : 6;
+        const int swap_minb = scalar_traits<S>::is_complex ? 0 : swap_minb_env;
         if (nfront_all <= swap_gather_max_fronts) {
           if (swap_minb == 4) k_lu_swap_trsm<S, true, 4><<<grid, 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
           else if (swap_minb == 6) k_lu_swap_trsm<S, true, 6><<<grid, 128, 0, s>>>(T, nodes, k, F, d.piv.p, ctiles, ob);
