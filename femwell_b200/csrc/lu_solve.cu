@@ -125,7 +125,7 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-// ---- DINV chains (real arithmetic, blocks of up to 128 threads): the 32 x 32 diagonal blocks come pre-inverted from
+// ---- DINV chains (real arithmetic, blocks of up to DINV_MAX_THREADS = 256 threads): the 32 x 32 diagonal blocks come pre-inverted from
 // LUDevice::dinv (k_lu_diag_inverse, all fronts), so the 32 dependent shuffle/FMA steps of a diagonal solve become one
 // 32 x 32 matrix-vector product, and the block itself is copied with cp.async into one of two shared-memory buffers
 // one panel ahead (ncu on the leaf level of config 2: 30 % of the backward kernel sat in the eight serialised
