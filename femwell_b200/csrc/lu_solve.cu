@@ -1140,7 +1140,11 @@ static void solve_typed(Handle& h, const S* b, S* x) {
   const bool no_dinv_chain = getenv("FW_NO_DINV_CHAIN") != nullptr || lu.no_tinv;
   static const int dinv_max_threads =
       getenv("FW_DINV_MAX_THREADS") ? std::min(DINV_MAX_THREADS, atoi(getenv("FW_DINV_MAX_THREADS"))) : DINV_MAX_THREADS;
-  auto use_dinv = [&](int threads) {
+  // FW_DINV_FWD_ONLY=1 / FW_DINV_BWD_ONLY=1: inverse diagonal blocks in one pass only (inv(L_kk) of the unit lower blocks is
+  // benign, the accuracy price of the DINV chains comes from inv(U_kk))
+  const bool dinv_fwd_only = getenv("FW_DINV_FWD_ONLY") != nullptr, dinv_bwd_only = getenv("FW_DINV_BWD_ONLY") != nullptr;
+  auto use_dinv = [&](int threads, bool fwd) {
+    if ((fwd && dinv_bwd_only) || (!fwd && dinv_fwd_only)) return false;
     return !scalar_traits<S>::is_complex && d.dinv_valid && !no_dinv_chain && threads <= dinv_max_threads;
   };
   // ---- dataflow bands over the lower levels (see k_tree_band): A = small fronts (128 threads), B = the rest
@@ -1204,12 +1208,12 @@ static void solve_typed(Handle& h, const S* b, S* x) {
       }
     } else if (fuse) {
       const int threads = chain_threads(Sy.level_max_m[lev] / fuse_tdiv);
-      if (use_dinv(threads)) {
+      if (use_dinv(threads, true)) {
         if constexpr (!scalar_traits<S>::is_complex)
           k_fwd_chain_dinv<NRHS, true><<<nfront, threads, 0, s>>>(T, nodes, F, d.dinv.p, d.rowperm.p, work, Sy.work_entries, xp, na);
       } else
         k_fwd_chain_fused<S, NRHS><<<nfront, threads, 0, s>>>(T, nodes, F, d.rowperm.p, work, Sy.work_entries, xp, na);
-    } else if (use_dinv(chain_threads(max_ns)) && !use_inv(max_ns) && !(max_ns > CL_MIN_NS && !no_cluster)) {
+    } else if (use_dinv(chain_threads(max_ns), true) && !use_inv(max_ns) && !(max_ns > CL_MIN_NS && !no_cluster)) {
       if constexpr (!scalar_traits<S>::is_complex)
         k_fwd_chain_dinv<NRHS, false><<<nfront, chain_threads(max_ns), 0, s>>>(T, nodes, F, d.dinv.p, d.rowperm.p, work, Sy.work_entries, xp, na);
     } else if (use_inv(max_ns))
@@ -1272,12 +1276,12 @@ static void solve_typed(Handle& h, const S* b, S* x) {
       }
     } else if (fuse) {
       const int threads = chain_threads(std::max(max_ns, 64));
-      if (use_dinv(threads)) {
+      if (use_dinv(threads, false)) {
         if constexpr (!scalar_traits<S>::is_complex)
           k_bwd_chain_dinv<NRHS, true><<<nfront, threads, 0, s>>>(T, nodes, F, d.dinv.p, work, Sy.work_entries, xp, na);
       } else
         k_bwd_chain_fused<S, NRHS><<<nfront, threads, 0, s>>>(T, nodes, F, work, Sy.work_entries, xp, na);
-    } else if (use_dinv(chain_threads(max_ns)) && !use_inv(max_ns) && !(max_ns > CL_MIN_NS && !no_cluster)) {
+    } else if (use_dinv(chain_threads(max_ns), false) && !use_inv(max_ns) && !(max_ns > CL_MIN_NS && !no_cluster)) {
       if constexpr (!scalar_traits<S>::is_complex)
         k_bwd_chain_dinv<NRHS, false><<<nfront, chain_threads(max_ns), 0, s>>>(T, nodes, F, d.dinv.p, work, Sy.work_entries, xp, na);
     } else if (use_inv(max_ns))
